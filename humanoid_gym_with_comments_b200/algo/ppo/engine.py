@@ -1,0 +1,217 @@
+"""Host-side orchestration of the learner kernels (private to this package).
+
+`FlatParams` owns the flat fp32 arenas (parameters | gradients | Adam moments) that the nn.Parameters of
+`ActorCritic` are views of, plus the bf16 shadows of the hidden-layer weights that the tensor-core GEMMs read.
+`MLPEngine` launches grouped forward / backward passes over the three MLPs through the C ABI.
+
+Reference being replaced: the torch autograd graph of `humanoid/algo/ppo/actor_critic.py:52-89` (three
+nn.Sequential of Linear/ELU) as driven by `ppo.py:116-126` (rollout) and `ppo.py:154-214` (update).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ..._lib import (EPI_ATOMIC_F32, EPI_BIAS_ELU_BF16, EPI_DELU_BF16, HG_STATS_SLOTS, HgBf16Shadow,
+                     HgGemmProblem, check, current_stream, ptr)
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class NetSpec:
+    """One MLP: list of (weight, bias) Parameters, hidden layers first, output layer last."""
+
+    def __init__(self, name: str, seq: nn.Sequential):
+        self.name = name
+        self.linears: List[nn.Linear] = [m for m in seq if isinstance(m, nn.Linear)]
+        others = [m for m in seq if not isinstance(m, nn.Linear)]
+        for m in others:
+            if not (isinstance(m, nn.ELU) and m.alpha == 1.0):
+                raise NotImplementedError(
+                    f"{name}: only nn.ELU(alpha=1) between Linear layers has a CUDA kernel here (got {type(m).__name__})")
+        self.in_dim = self.linears[0].in_features
+        self.hidden = [l.out_features for l in self.linears[:-1]]
+        self.out_dim = self.linears[-1].out_features
+        for w in self.hidden:
+            if w % 8 != 0:
+                raise NotImplementedError(f"{name}: hidden widths must be multiples of 8 (got {w})")
+        if not self.hidden or self.hidden[-1] > 256:
+            raise NotImplementedError(f"{name}: needs >=1 hidden layer and a last hidden width <= 256")
+        self.num_hidden = len(self.hidden)
+
+    def widths(self) -> List[int]:
+        """input width followed by the hidden widths: widths()[l] is the K of hidden layer l+1."""
+        return [self.in_dim] + self.hidden
+
+
+class FlatParams:
+    """Flat fp32 arenas + bf16 weight shadows for a list of nn.Parameters (in `module.parameters()` order)."""
+
+    def __init__(self, module: nn.Module, nets: Sequence[NetSpec]):
+        self.module = module
+        self.nets = list(nets)
+        self.params: List[nn.Parameter] = list(module.parameters())
+        dev = self.params[0].device
+        _lib.require_cuda(*self.params)
+        self.device = dev
+        self.offsets: Dict[int, int] = {}
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise _lib.HgError("parameters must be float32")
+            self.offsets[id(p)] = off
+            off += round_up(p.numel(), 4)            # 16-byte aligned starts
+        self.count = off
+        n = self.count + HG_STATS_SLOTS
+        self.p = torch.zeros(n, device=dev)
+        self.g = torch.zeros(n, device=dev)
+        self.m = torch.zeros(n, device=dev)
+        self.v = torch.zeros(n, device=dev)
+        self.stats = self.g[self.count:]              # loss statistics ride behind the gradients (one all-reduce)
+        with torch.no_grad():
+            for p in self.params:
+                o = self.offsets[id(p)]
+                view = self.p[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.g[o:o + p.numel()].view(p.shape)
+        # bf16 shadows of the hidden-layer weights, rows padded to 16 bytes
+        self.w16: Dict[int, torch.Tensor] = {}
+        self._shadow_list: List[HgBf16Shadow] = []
+        for net in self.nets:
+            for lin in net.linears[:-1]:
+                w = lin.weight
+                ld = round_up(w.shape[1], 8)
+                sh = torch.zeros(w.shape[0], ld, dtype=torch.bfloat16, device=dev)
+                self.w16[id(w)] = sh
+                self._shadow_list.append(HgBf16Shadow(self.offsets[id(w)], w.shape[0], w.shape[1], sh.data_ptr(), ld))
+        if len(self._shadow_list) > _lib.HG_MAX_SHADOWS:
+            raise NotImplementedError("too many hidden layers for one optimiser launch")
+        self.shadow_array = (HgBf16Shadow * len(self._shadow_list))(*self._shadow_list)
+        self.refresh_shadows()
+
+    # -- views ------------------------------------------------------------------------------
+    def grad_view(self, p: nn.Parameter) -> torch.Tensor:
+        o = self.offsets[id(p)]
+        return self.g[o:o + p.numel()].view(p.shape)
+
+    def moment_views(self, p: nn.Parameter):
+        o = self.offsets[id(p)]
+        return self.m[o:o + p.numel()].view(p.shape), self.v[o:o + p.numel()].view(p.shape)
+
+    def attached(self) -> bool:
+        """False if someone re-materialised the parameters (e.g. `.to()` / `load_state_dict(assign=True)`)."""
+        p0 = self.params[0]
+        return p0.data.data_ptr() == self.p.data_ptr() + 4 * self.offsets[id(p0)]
+
+    def refresh_shadows(self) -> None:
+        """Re-cast every bf16 shadow from the fp32 master weights (after load_state_dict / manual edits)."""
+        lib = _lib.load()
+        st = current_stream()
+        for net in self.nets:
+            for lin in net.linears[:-1]:
+                w = lin.weight
+                sh = self.w16[id(w)]
+                check(lib.hg_cast_weight_bf16(ptr(w.data), w.shape[0], w.shape[1], ptr(sh), sh.shape[1], st))
+
+
+class Workspace:
+    """Activation / gradient buffers for `rows` rows of every net (bf16)."""
+
+    def __init__(self, nets: Sequence[NetSpec], rows: int, device, with_grads: bool):
+        self.rows = rows
+        self.h: Dict[str, List[torch.Tensor]] = {}
+        self.dz: Dict[str, List[torch.Tensor]] = {}
+        for net in nets:
+            self.h[net.name] = [torch.empty(rows, w, dtype=torch.bfloat16, device=device) for w in net.hidden]
+            if with_grads:
+                self.dz[net.name] = [torch.empty(rows, w, dtype=torch.bfloat16, device=device) for w in net.hidden]
+
+
+class MLPEngine:
+    def __init__(self, flat: FlatParams):
+        self.flat = flat
+        self.lib = _lib.load()
+        self.num_sms = torch.cuda.get_device_properties(flat.device).multi_processor_count
+
+    # -- helpers ----------------------------------------------------------------------------
+    @staticmethod
+    def _block_n(ns: Sequence[int]) -> int:
+        return 256 if min(ns) >= 256 else 128
+
+    def _launch(self, problems: List[HgGemmProblem], epi: int, block_n: int) -> None:
+        arr = (HgGemmProblem * len(problems))(*problems)
+        check(self.lib.hg_gemm_grouped(arr, len(problems), epi, block_n, current_stream()))
+
+    # -- forward of all hidden layers ---------------------------------------------------------
+    def forward_hidden(self, nets: Sequence[NetSpec], inputs: Dict[str, torch.Tensor], in_cols: Dict[str, int],
+                       ws: Workspace, rows: int) -> None:
+        """inputs[name]: bf16 [rows, ld] (ld multiple of 8; only the first in_cols[name] columns are read).
+        Fills ws.h[name][l] = elu(W_l h_{l-1} + b_l) for every hidden layer, one grouped launch per depth."""
+        depth = max(n.num_hidden for n in nets)
+        for l in range(depth):
+            probs, ns = [], []
+            for net in nets:
+                if l >= net.num_hidden:
+                    continue
+                lin = net.linears[l]
+                a = inputs[net.name] if l == 0 else ws.h[net.name][l - 1]
+                k = in_cols[net.name] if l == 0 else net.hidden[l - 1]
+                w16 = self.flat.w16[id(lin.weight)]
+                out = ws.h[net.name][l]
+                probs.append(HgGemmProblem(
+                    A=ptr(a), B=ptr(w16), lda=a.stride(0), ldb=w16.stride(0), a_mn_major=0, b_mn_major=0,
+                    M=rows, N=lin.out_features, K=k, k_splits=1, out=ptr(out), ldo=out.stride(0),
+                    bias=ptr(lin.bias.data), act=0, ldact=0, colsum=0))
+                ns.append(lin.out_features)
+            self._launch(probs, EPI_BIAS_ELU_BF16, self._block_n(ns))
+
+    # -- backward of all hidden layers ----------------------------------------------------------
+    def backward_hidden(self, nets: Sequence[NetSpec], inputs: Dict[str, torch.Tensor], in_cols: Dict[str, int],
+                        ws: Workspace, rows: int) -> None:
+        """Expects ws.dz[name][-1] (top hidden layer pre-activation gradient) and its bias gradient to be
+        already produced by the head kernel.  Accumulates weight gradients into the gradient arena and
+        bias gradients of the lower layers, walking down one layer per step, grouped across nets."""
+        depth = max(n.num_hidden for n in nets)
+        for s in range(depth):
+            dw, dx, dw_n, dx_n = [], [], [], []
+            for net in nets:
+                j = net.num_hidden - 1 - s            # hidden layer index whose dZ is available
+                if j < 0:
+                    continue
+                lin = net.linears[j]
+                dz = ws.dz[net.name][j]
+                below = inputs[net.name] if j == 0 else ws.h[net.name][j - 1]
+                k_in = in_cols[net.name] if j == 0 else net.hidden[j - 1]
+                gw = self.flat.grad_view(lin.weight)
+                # dW_j [out, in] += dZ_j^T [out, rows] * H_{j-1} [rows, in]     (both operands MN-major)
+                dw.append(HgGemmProblem(
+                    A=ptr(dz), B=ptr(below), lda=dz.stride(0), ldb=below.stride(0), a_mn_major=1, b_mn_major=1,
+                    M=lin.out_features, N=k_in, K=rows, k_splits=1, out=ptr(gw), ldo=k_in,
+                    bias=0, act=0, ldact=0, colsum=0))
+                dw_n.append(k_in)
+                if j >= 1:
+                    # dZ_{j-1} = (dZ_j [rows,out] * W_j [out,in]) . elu'(H_{j-1});  b-grad of layer j-1 = colsum
+                    w16 = self.flat.w16[id(lin.weight)]
+                    out = ws.dz[net.name][j - 1]
+                    gb = self.flat.grad_view(net.linears[j - 1].bias)
+                    dx.append(HgGemmProblem(
+                        A=ptr(dz), B=ptr(w16), lda=dz.stride(0), ldb=w16.stride(0), a_mn_major=0, b_mn_major=1,
+                        M=rows, N=k_in, K=lin.out_features, k_splits=1, out=ptr(out), ldo=out.stride(0),
+                        bias=0, act=ptr(below), ldact=below.stride(0), colsum=ptr(gb)))
+                    dx_n.append(k_in)
+            if dw:
+                bn = self._block_n(dw_n)
+                tiles = sum(((p.M + 127) // 128) * ((p.N + bn - 1) // bn) for p in dw)
+                splits = max(1, min((rows + 63) // 64, (2 * self.num_sms) // max(tiles, 1)))
+                for p in dw:
+                    p.k_splits = splits
+                self._launch(dw, EPI_ATOMIC_F32, bn)
+            if dx:
+                self._launch(dx, EPI_DELU_BF16, self._block_n(dx_n))

@@ -1,0 +1,325 @@
+"""`PPO` with the reference's constructor, attributes and methods (reference: humanoid/algo/ppo/ppo.py:42-226),
+every tensor operation on sm_100a kernels and no host synchronisation inside rollout or update (one device->host
+read of the loss log at the end of `update()`).
+
+Per rollout step (`act` + `process_env_step`, ppo.py:116-138): 2 ingest launches, one grouped tcgen05 GEMM launch per
+hidden depth (actor + critic together), 1 fused head launch (output layers, Gaussian sample, log-prob, value, written
+straight into the storage slot), 1 reward/done launch.
+Per minibatch (`update`, ppo.py:150-218): grouped forward GEMMs, 1 fused head+loss+head-backward launch, grouped
+dW / dX GEMMs, optional NCCL all-reduce of the flat gradient arena (+KL slot), 3 optimiser launches.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.optim as optim
+
+from ... import _lib
+from ..._lib import HgAdamArgs, HgHeadNet, HgLossArgs, check, current_stream, ptr
+from .actor_critic import ActorCritic
+from .rollout_storage import RolloutStorage
+
+
+class FusedAdam(optim.Adam):
+    """torch.optim.Adam-shaped facade (state_dict / load_state_dict / param_groups) over the fused
+    clip+Adam kernel: `exp_avg` / `exp_avg_sq` of every parameter are views of the flat moment arenas."""
+
+    def __init__(self, actor_critic: ActorCritic, lr: float):
+        super().__init__(actor_critic.parameters(), lr=lr)
+        self._ac = actor_critic
+        self._flat = None
+        # device scalars: [0] lr [1] step [2] grad sumsq [3] clip coef [4] step size [5] sqrt(1-b2^t) [6] grad norm
+        self.opt_state = None
+
+    def bind(self):
+        flat = self._ac.flat
+        if flat is self._flat:
+            return
+        old = self._flat
+        self._flat = flat
+        lr = float(self.param_groups[0]["lr"])
+        step = 0.0
+        if old is not None and old.count == flat.count:
+            flat.m.copy_(old.m)
+            flat.v.copy_(old.v)
+            step = float(self.opt_state[1].item())
+        self.opt_state = torch.zeros(8, dtype=torch.float64, device=flat.device)
+        self.opt_state[0] = lr
+        self.opt_state[1] = step
+        for p in flat.params:
+            m, v = flat.moment_views(p)
+            self.state[p] = {"step": torch.tensor(step), "exp_avg": m, "exp_avg_sq": v}
+
+    def sync_host(self):
+        """Mirror device-side lr / step into param_groups and state (one small D2H copy)."""
+        if self.opt_state is None:
+            return
+        lr, step = self.opt_state[:2].tolist()
+        for g in self.param_groups:
+            g["lr"] = lr
+        for st in self.state.values():
+            st["step"] = torch.tensor(float(step))
+
+    def set_lr(self, lr: float):
+        for g in self.param_groups:
+            g["lr"] = lr
+        if self.opt_state is not None:
+            self.opt_state[0] = lr
+
+    def state_dict(self):
+        self.sync_host()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        flat = self._ac.flat
+        self._flat = None
+        loaded = {id(p): self.state.get(p) for p in flat.params}
+        step = 0.0
+        with torch.no_grad():
+            for p in flat.params:
+                st = loaded[id(p)]
+                m, v = flat.moment_views(p)
+                if st:
+                    m.copy_(st["exp_avg"])
+                    v.copy_(st["exp_avg_sq"])
+                    step = float(st["step"])
+        self._flat = flat
+        self.opt_state = torch.zeros(8, dtype=torch.float64, device=flat.device)
+        self.opt_state[0] = float(self.param_groups[0]["lr"])
+        self.opt_state[1] = step
+        for p in flat.params:
+            m, v = flat.moment_views(p)
+            self.state[p] = {"step": torch.tensor(step), "exp_avg": m, "exp_avg_sq": v}
+
+    def zero_grad(self, set_to_none: bool = False):
+        self._ac.flat.g.zero_()
+
+    def fused_step(self, *, rows_global, max_grad_norm, adaptive, desired_kl, loss_log, log_slot):
+        self.bind()
+        flat = self._flat
+        g = self.param_groups[0]
+        args = HgAdamArgs(
+            params=ptr(flat.p), grads=ptr(flat.g), exp_avg=ptr(flat.m), exp_avg_sq=ptr(flat.v), count=flat.count,
+            opt_state=ptr(self.opt_state), loss_log=ptr(loss_log), log_slot=log_slot, rows_global=rows_global,
+            beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"],
+            max_grad_norm=float(max_grad_norm) if max_grad_norm is not None else 3.0e38,
+            adaptive=1 if adaptive else 0, desired_kl=float(desired_kl) if desired_kl is not None else 0.0,
+            lr_min=1e-5, lr_max=1e-2, shadows_host=flat.shadow_array, num_shadows=len(flat.shadow_array),
+            zero_grads=1)
+        check(_lib.load().hg_clip_adam_step(C.byref(args), current_stream()))
+
+    def step(self, closure=None):
+        """Plain Adam step on whatever is in the gradient arena (no clipping, fixed lr)."""
+        self.bind()
+        self.opt_state[0] = float(self.param_groups[0]["lr"])
+        self.fused_step(rows_global=1, max_grad_norm=None, adaptive=False, desired_kl=None, loss_log=None, log_slot=0)
+
+
+class PPO:
+    actor_critic: ActorCritic
+
+    def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
+                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0,
+                 use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, device='cpu', sym_loss=False,
+                 obs_permutation=None, act_permutation=None, frame_stack=0, sym_coef=1.0, base_lin_vel_coef=1.0):
+        if torch.device(device).type != "cuda":
+            raise _lib.HgError("PPO(device=...) must be a CUDA device: this implementation has no CPU fallback")
+        if sym_loss:
+            raise NotImplementedError("the mirror-symmetry loss (ppo.py:93-105,197-202) is off in the shipped config and "
+                                      "has no fused kernel yet (SURVEY 8f rank 4)")
+        self.device = device
+        self.desired_kl = desired_kl
+        self.schedule = schedule
+        self.learning_rate = learning_rate
+
+        # PPO components
+        self.actor_critic = actor_critic
+        self.actor_critic.to(self.device)
+        self.actor_critic.engine()
+        self.storage = None  # initialized later
+        self.optimizer = FusedAdam(self.actor_critic, lr=learning_rate)
+        self.optimizer.bind()
+        self.transition = RolloutStorage.Transition()
+
+        # PPO parameters
+        self.clip_param = clip_param
+        self.num_learning_epochs = num_learning_epochs
+        self.num_mini_batches = num_mini_batches
+        self.value_loss_coef = value_loss_coef
+        self.entropy_coef = entropy_coef
+        self.gamma = gamma
+        self.lam = lam
+        self.max_grad_norm = max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.base_lin_vel_coef = base_lin_vel_coef
+        self.sym_loss = sym_loss
+        self.sym_coef = sym_coef
+
+        # implementation switches
+        self.torch_rng = True        # draw eps / burn the update-time sample() through torch's generator (seed parity)
+        self.world_size = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        self.last_update_log = None  # [epochs*minibatches, 8] per-minibatch statistics of the last update()
+        self._perm_bufs = None
+        self._lr_synced = learning_rate
+        # test hooks: replay externally drawn randomness (parity tests feed the oracle's eps / permutation)
+        self.eps_override = None     # callable(step) -> [N, A] standard-normal draws
+        self.perm_override = None    # int64 [num_mini_batches * mini_batch_size] permutation
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
+
+    def test_mode(self):
+        self.actor_critic.eval()   # the reference calls a non-existent .test() (ppo.py:111)
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    # ------------------------------------------------------------------ rollout
+    def act(self, obs, critic_obs):
+        ac, st = self.actor_critic, self.storage
+        eng = ac.engine()
+        st.check_room()
+        t, N, A = st.step, st.num_envs, ac.num_actions
+        if critic_obs is None:
+            critic_obs = obs
+        o16, p16 = st.ingest(obs, critic_obs, t)
+        ws = ac.workspace(N)
+        eng.forward_hidden((ac.net_actor, ac.net_critic), {"actor": o16, "critic": p16},
+                           {"actor": st.obs_cols, "critic": st.priv_cols}, ws, N)
+        if self.eps_override is not None:
+            eps = self.eps_override(t).to(st.actions.device).float().contiguous()
+        else:
+            eps = torch.randn(N, A, device=st.actions.device) if self.torch_rng else None
+        out = dict(actions=st.actions[t], mu=st.mu[t], sigma=st.sigma[t], log_prob=st.actions_log_prob[t],
+                   values=st.values[t])
+        ac._head_rollout(ws, N, True, eps, out)
+        tr = self.transition
+        tr.actions = st.actions[t]
+        tr.values = st.values[t]
+        tr.actions_log_prob = st.actions_log_prob[t].view(-1)
+        tr.action_mean = st.mu[t]
+        tr.action_sigma = st.sigma[t]
+        tr.observations = obs
+        tr.critic_observations = critic_obs
+        return tr.actions
+
+    def process_env_step(self, rewards, dones, infos):
+        st = self.storage
+        st.check_room()
+        t, N = st.step, st.num_envs
+        _lib.require_cuda(rewards, dones)
+        rewards = rewards.reshape(-1)
+        if rewards.dtype != torch.float32 or not rewards.is_contiguous():
+            rewards = rewards.float().contiguous()
+        d8 = dones.reshape(-1)
+        d8 = d8 if d8.dtype in (torch.bool, torch.uint8) else (d8 != 0)
+        d8 = d8.contiguous()
+        to8 = None
+        if 'time_outs' in infos:
+            to8 = infos['time_outs'].reshape(-1).to(self.device)
+            to8 = to8 if to8.dtype in (torch.bool, torch.uint8) else (to8 != 0)
+            to8 = to8.contiguous()
+        check(_lib.load().hg_store_rewards_dones(ptr(rewards), ptr(st.values[t]), ptr(to8), ptr(d8), float(self.gamma), N,
+                                                 ptr(st.rewards[t]), ptr(st.dones[t]), current_stream()))
+        self.transition.rewards = st.rewards[t].view(-1)
+        self.transition.dones = dones
+        st.step += 1
+        self.transition.clear()
+        self.actor_critic.reset(dones)
+
+    def compute_returns(self, last_critic_obs):
+        ac, st = self.actor_critic, self.storage
+        eng = ac.engine()
+        N = last_critic_obs.shape[0]
+        c16 = ac._to_bf16(last_critic_obs, "last_critic")
+        ws = ac.workspace(N)
+        eng.forward_hidden((ac.net_critic,), {"critic": c16}, {"critic": last_critic_obs.shape[1]}, ws, N)
+        last_values = torch.empty(N, 1, device=st.values.device)
+        ac._head_rollout(ws, N, False, None, dict(values=last_values))
+        st.compute_returns(last_values, self.gamma, self.lam)
+
+    # ------------------------------------------------------------------ update
+    def _head_net(self, net, ws, flat) -> HgHeadNet:
+        last = net.linears[-1]
+        top = net.linears[-2]
+        h = ws.h[net.name][-1]
+        dz = ws.dz[net.name][-1]
+        return HgHeadNet(h=ptr(h), ld_h=h.stride(0), H=h.shape[1], n_out=last.out_features,
+                         W=ptr(last.weight.data), b=ptr(last.bias.data), gW=ptr(flat.grad_view(last.weight)),
+                         gb=ptr(flat.grad_view(last.bias)), dZ=ptr(dz), ld_dz=dz.stride(0),
+                         gb_hidden=ptr(flat.grad_view(top.bias)))
+
+    def update(self):
+        ac, st = self.actor_critic, self.storage
+        eng = ac.engine()
+        flat = ac.flat
+        lib = _lib.load()
+        self.optimizer.bind()
+        if abs(self.learning_rate - self._lr_synced) > 0:       # user changed alg.learning_rate by hand
+            self.optimizer.set_lr(self.learning_rate)
+        nmb, nep = self.num_mini_batches, self.num_learning_epochs
+        A = ac.num_actions
+        indices, M = st.draw_permutation(nmb)                    # once per update, reused by every epoch
+        if self.perm_override is not None:
+            indices = self.perm_override.to(indices.device).long().contiguous()
+        total = nmb * M
+        # gather the bf16 observation rows of all minibatches once (both epochs reuse them)
+        if self._perm_bufs is None or self._perm_bufs[0].shape[0] != total:
+            self._perm_bufs = (torch.empty(total, st.obs_ld, dtype=torch.bfloat16, device=indices.device),
+                               torch.empty(total, st.priv_ld, dtype=torch.bfloat16, device=indices.device)
+                               if st.privileged_observations is not None else None)
+        xperm, pperm = self._perm_bufs
+        check(lib.hg_gather_rows_bf16(ptr(st.obs16), st.obs_ld, ptr(indices), total, ptr(xperm), current_stream()))
+        if pperm is not None:
+            check(lib.hg_gather_rows_bf16(ptr(st.priv16), st.priv_ld, ptr(indices), total, ptr(pperm), current_stream()))
+        else:
+            pperm = xperm
+        cobs = st.privileged_observations if st.privileged_observations is not None else st.observations
+        ws = ac.workspace(M, with_grads=True)
+        nets = (ac.net_actor, ac.net_critic, ac.net_linvel)
+        n_updates = nep * nmb
+        loss_log = torch.zeros(n_updates, 8, dtype=torch.float64, device=indices.device)
+        adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
+        slot = 0
+        for epoch in range(nep):
+            for i in range(nmb):
+                x = xperm[i * M:(i + 1) * M]
+                p = pperm[i * M:(i + 1) * M]
+                idx = indices[i * M:(i + 1) * M]
+                if self.torch_rng:
+                    torch.randn(M, A, device=indices.device)     # the reference's unused sample() (ppo.py:154) burns RNG
+                inputs = {"actor": x, "critic": p, "base_lin_vel": x}
+                cols = {"actor": st.obs_cols, "critic": st.priv_cols, "base_lin_vel": st.obs_cols}
+                eng.forward_hidden(nets, inputs, cols, ws, M)
+                largs = HgLossArgs(
+                    actor=self._head_net(ac.net_actor, ws, flat), critic=self._head_net(ac.net_critic, ws, flat),
+                    linvel=self._head_net(ac.net_linvel, ws, flat), rows=M, A=A, idx=ptr(idx),
+                    actions=ptr(st.actions), old_mu=ptr(st.mu), old_sigma=ptr(st.sigma),
+                    old_log_prob=ptr(st.actions_log_prob), advantages=ptr(st.advantages), returns=ptr(st.returns),
+                    old_values=ptr(st.values), critic_obs=ptr(cobs), ld_cobs=cobs.shape[-1], lv_col=53,
+                    std=ptr(ac.std.data), g_std=ptr(flat.grad_view(ac.std)), clip_param=float(self.clip_param),
+                    value_loss_coef=float(self.value_loss_coef), entropy_coef=float(self.entropy_coef),
+                    lin_vel_coef=float(self.base_lin_vel_coef),
+                    use_clipped_value_loss=1 if self.use_clipped_value_loss else 0,
+                    inv_world=1.0 / self.world_size, stats=ptr(flat.stats))
+                check(lib.hg_ppo_head_loss(C.byref(largs), current_stream()))
+                eng.backward_hidden(nets, inputs, cols, ws, M)
+                if self.world_size > 1:
+                    # the only collective of the path: SUM over ranks of [gradients | KL and loss sums]
+                    torch.distributed.all_reduce(flat.g)
+                self.optimizer.fused_step(rows_global=M * self.world_size, max_grad_norm=self.max_grad_norm,
+                                          adaptive=adaptive, desired_kl=self.desired_kl, loss_log=loss_log, log_slot=slot)
+                slot += 1
+        log = loss_log.cpu()                                      # the single host sync of update()
+        self.last_update_log = log
+        self.learning_rate = float(log[-1, 5])
+        self._lr_synced = self.learning_rate
+        for g in self.optimizer.param_groups:
+            g['lr'] = self.learning_rate
+        mean_value_loss = float(log[:, 0].mean())
+        mean_surrogate_loss = float(log[:, 1].mean())
+        mean_base_lin_vel_loss = float(log[:, 2].mean())
+        st.clear()
+        return mean_value_loss, mean_surrogate_loss, 0, mean_base_lin_vel_loss

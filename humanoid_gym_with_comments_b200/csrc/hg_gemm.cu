@@ -1,0 +1,452 @@
+// Grouped bf16 GEMM on 5th-generation tensor cores (tcgen05.mma, TMEM accumulators, TMA loads).
+//
+//   C[M,N] = A[M,K] * B[N,K]^T   (fp32 accumulate), up to HG_MAX_GROUP problems per launch.
+//
+// One persistent CTA per SM, 8 warps:
+//   warp 0    TMA producer (one lane): cp.async.bulk.tensor 2D boxes -> SWIZZLE_128B smem ring
+//   warp 1    MMA issuer  (one lane): tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16 per instruction
+//   warp 2    TMEM allocator (2*BLOCK_N columns: two accumulator buffers so the epilogue of tile i
+//             overlaps the main loop of tile i+1)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+//
+// Operands may be K-major (row-major [rows,K]) or MN-major (row-major [K,rows]); the latter lets the
+// backward GEMMs (dX = dZ*W, dW = dZ^T*H) read the same row-major activations / weights as the forward
+// pass, so no transposed copies exist anywhere.  Shared-memory layouts follow the canonical UMMA
+// SWIZZLE_128B forms documented in CUTLASS cute/atom/mma_traits_sm100.hpp:
+//   K-major : rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO)            -> one TMA box {64, rows}
+//   MN-major: atoms of [64 k-rows x 64 mn] (k-row = 128 B, 8-row groups SBO=1024 B apart), atoms of
+//             successive 64-wide mn chunks LBO = 8192 B apart                      -> one TMA box {64,64} per atom
+#include <stdarg.h>
+
+#include "hg_common.cuh"
+
+namespace hg {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int SMEM_RING_BYTES = 192 * 1024;
+constexpr int NUM_THREADS = 256;
+constexpr int MN_ATOM_BYTES = BLOCK_K * 128;  // 8192: one [64 x 64] bf16 atom
+
+struct DevProblem {
+  int M, N, K;
+  int a_mn, b_mn;
+  int k_splits, kb_per_split, num_kb;
+  int tiles_m, tiles_n;
+  int tile_begin, tile_end;
+  void* out;
+  long long ldo;
+  const float* bias;
+  const __nv_bfloat16* act;
+  long long ldact;
+  float* colsum;
+};
+
+struct alignas(64) GroupParams {
+  CUtensorMap tma_a[HG_MAX_GROUP];
+  CUtensorMap tma_b[HG_MAX_GROUP];
+  DevProblem p[HG_MAX_GROUP];
+  int num_problems;
+  int total_tiles;
+};
+
+struct Tile {
+  int g, m_blk, n_blk, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ Tile decode_tile(const GroupParams& P, int t) {
+  int g = 0;
+  while (g + 1 < P.num_problems && t >= P.p[g].tile_end) ++g;
+  const DevProblem& q = P.p[g];
+  int local = t - q.tile_begin;
+  Tile ti;
+  ti.g = g;
+  ti.n_blk = local % q.tiles_n;
+  local /= q.tiles_n;
+  ti.m_blk = local % q.tiles_m;
+  int ks = local / q.tiles_m;
+  ti.kb_begin = ks * q.kb_per_split;
+  ti.kb_end = min(q.num_kb, ti.kb_begin + q.kb_per_split);
+  return ti;
+}
+
+__device__ __forceinline__ uint64_t desc_base() {
+  // version=1 (bits 46-47), layout SWIZZLE_128B=2 (bits 61-63), SBO = 1024 B (bits 32-45, >>4)
+  return (uint64_t(1) << 46) | (uint64_t(2) << 61) | (uint64_t(1024 >> 4) << 32);
+}
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+  return desc_base() | (uint64_t(1) << 16) | uint64_t((saddr & 0x3FFFFu) >> 4);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+  return desc_base() | (uint64_t(MN_ATOM_BYTES >> 4) << 16) | uint64_t((saddr & 0x3FFFFu) >> 4);
+}
+
+// ------------------------------------------------------------------------------------------ epilogues
+// Column sums over the 32 rows held by a warp (one row per lane, 32 columns in registers).
+// Butterfly "transpose-reduce": 31 shuffles; on return lane L holds the sum of column L in d[0].
+__device__ __forceinline__ float warp_colsum32(float (&d)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = upper ? d[i] : d[i + off];
+      float keep = upper ? d[i + off] : d[i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return d[0];
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int n0, uint32_t (&v)[32], int lane) {
+  const bool row_ok = row < q.M;
+  const bool full = (n0 + 32 <= q.N);
+  if constexpr (EPI == HG_EPI_STORE_F32) {
+    float* o = reinterpret_cast<float*>(q.out) + (long long)row * q.ldo + n0;
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < q.N) o[j] = __uint_as_float(v[j]) + (q.bias ? __ldg(q.bias + n0 + j) : 0.f);
+    }
+  } else if constexpr (EPI == HG_EPI_ATOMIC_F32) {
+    float* o = reinterpret_cast<float*>(q.out) + (long long)row * q.ldo + n0;
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < q.N) atomicAdd(o + j, __uint_as_float(v[j]));
+    }
+  } else if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(q.out) + (long long)row * q.ldo + n0;
+    float z[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float b = (q.bias && n0 + j < q.N) ? __ldg(q.bias + n0 + j) : 0.f;
+      float t = __uint_as_float(v[j]) + b;
+      z[j] = (EPI == HG_EPI_BIAS_ELU_BF16) ? elu1(t) : t;
+    }
+    if (row_ok) {
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 w = make_uint4(pack_bf16x2(z[j], z[j + 1]), pack_bf16x2(z[j + 2], z[j + 3]),
+                               pack_bf16x2(z[j + 4], z[j + 5]), pack_bf16x2(z[j + 6], z[j + 7]));
+          *reinterpret_cast<uint4*>(o + j) = w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < q.N) o[j] = __float2bfloat16_rn(z[j]);
+      }
+    }
+  } else if constexpr (EPI == HG_EPI_DELU_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(q.out) + (long long)row * q.ldo + n0;
+    const __nv_bfloat16* a = q.act + (long long)row * q.ldact + n0;
+    float d[32];
+    if (row_ok && full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 hw = *reinterpret_cast<const uint4*>(a + j);
+        uint32_t hv[4] = {hw.x, hw.y, hw.z, hw.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 h = unpack_bf16x2(hv[k]);
+          d[j + 2 * k] = __uint_as_float(v[j + 2 * k]) * (h.x > 0.f ? 1.f : h.x + 1.f);
+          d[j + 2 * k + 1] = __uint_as_float(v[j + 2 * k + 1]) * (h.y > 0.f ? 1.f : h.y + 1.f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 w = make_uint4(pack_bf16x2(d[j], d[j + 1]), pack_bf16x2(d[j + 2], d[j + 3]),
+                             pack_bf16x2(d[j + 4], d[j + 5]), pack_bf16x2(d[j + 6], d[j + 7]));
+        *reinterpret_cast<uint4*>(o + j) = w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float val = 0.f;
+        if (row_ok && n0 + j < q.N) {
+          float h = __bfloat162float(a[j]);
+          val = __uint_as_float(v[j]) * (h > 0.f ? 1.f : h + 1.f);
+          o[j] = __float2bfloat16_rn(val);
+        }
+        d[j] = val;
+      }
+    }
+    if (q.colsum) {
+      // bias gradient of the layer below = column sums of what was just written (bf16-rounded values
+      // are what the weight-gradient GEMM will read, but the fp32 sum is the better estimate).
+      float s = warp_colsum32(d, lane);
+      if (n0 + lane < q.N) atomicAdd(q.colsum + n0 + lane, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ GroupParams P) {
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;            // 16 KB
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;            // 16 / 32 KB
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = SMEM_RING_BYTES / STAGE_BYTES;     // 6 / 4
+  constexpr int TMEM_COLS = 2 * BLOCK_N;                    // 256 / 512
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int g = 0; g < P.num_problems; ++g) {
+      tma_prefetch_desc(&P.tma_a[g]);
+      tma_prefetch_desc(&P.tma_b[g]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        const Tile ti = decode_tile(P, t);
+        const DevProblem& q = P.p[ti.g];
+        const void* ta = &P.tma_a[ti.g];
+        const void* tb = &P.tma_b[ti.g];
+        for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          if (!q.a_mn) {
+            tma_load_2d(sa, ta, fb, kb * BLOCK_K, ti.m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_2d(sa + j * MN_ATOM_BYTES, ta, fb, ti.m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
+          }
+          if (!q.b_mn) {
+            tma_load_2d(sb, tb, fb, kb * BLOCK_K, ti.n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * MN_ATOM_BYTES, tb, fb, ti.n_blk * BLOCK_N + j * 64, kb * BLOCK_K);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        const Tile ti = decode_tile(P, t);
+        const DevProblem& q = P.p[ti.g];
+        // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), majors, N>>3 at 17, M>>4 at 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(q.a_mn) << 15) |
+                               (uint32_t(q.b_mn) << 16) | (uint32_t(BLOCK_N >> 3) << 17) |
+                               (uint32_t(BLOCK_M >> 4) << 24);
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        uint32_t accumulate = 0;
+        for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const int k_left = q.K - kb * BLOCK_K;
+          const int nk = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
+          for (int k = 0; k < nk; ++k) {
+            // K-major: +32 B per 16 bf16 inside the 128 B swizzle span; MN-major: +16 k-rows * 128 B
+            const uint64_t ad = q.a_mn ? desc_mnmajor(sa + k * (UMMA_K * 128)) : desc_kmajor(sa + k * (UMMA_K * 2));
+            const uint64_t bd = q.b_mn ? desc_mnmajor(sb + k * (UMMA_K * 128)) : desc_kmajor(sb + k * (UMMA_K * 2));
+            umma_bf16(d_tmem, ad, bd, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));   // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));        // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue (warps 4..7 <-> TMEM lanes 32*(warp-4)..)
+    const int quad = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      const Tile ti = decode_tile(P, t);
+      const DevProblem& q = P.p[ti.g];
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const int row = ti.m_blk * BLOCK_M + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int n0 = ti.n_blk * BLOCK_N + c * 32;
+        if (n0 >= q.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        epilogue_chunk<EPI>(q, row, n0, v, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over row-major [outer, inner] with row stride ld elements, box {64, box_outer}, 128 B swizzle.
+static int make_tmap(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld, int box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  HG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  HG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address must be 16-byte aligned");
+  HG_CHECK(ld % 8 == 0, "leading dimension %lld must be a multiple of 8 bf16 elements", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (inner %lld outer %lld ld %lld)", (int)r, inner,
+           outer, ld);
+  return HG_OK;
+}
+
+template <int BLOCK_N, int EPI>
+static int launch(const GroupParams& gp, cudaStream_t stream) {
+  constexpr int STAGE_BYTES = BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2;
+  constexpr int STAGES = SMEM_RING_BYTES / STAGE_BYTES;
+  const int smem = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static bool configured = false;
+  if (!configured) {
+    HG_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = gp.total_tiles < num_sms() ? gp.total_tiles : num_sms();
+  gemm_kernel<BLOCK_N, EPI><<<grid, NUM_THREADS, smem, stream>>>(gp);
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch_epi(const GroupParams& gp, int epi, cudaStream_t s) {
+  switch (epi) {
+    case HG_EPI_STORE_F32: return launch<BLOCK_N, HG_EPI_STORE_F32>(gp, s);
+    case HG_EPI_BIAS_ELU_BF16: return launch<BLOCK_N, HG_EPI_BIAS_ELU_BF16>(gp, s);
+    case HG_EPI_DELU_BF16: return launch<BLOCK_N, HG_EPI_DELU_BF16>(gp, s);
+    case HG_EPI_ATOMIC_F32: return launch<BLOCK_N, HG_EPI_ATOMIC_F32>(gp, s);
+    case HG_EPI_BIAS_BF16: return launch<BLOCK_N, HG_EPI_BIAS_BF16>(gp, s);
+  }
+  set_error("unknown epilogue %d", epi);
+  return HG_ERR_INVALID;
+}
+
+}  // namespace hg
+
+extern "C" int hg_gemm_grouped(const HgGemmProblem* pr, int n, int epilogue, int block_n, void* stream) {
+  using namespace hg;
+  HG_CHECK(pr != nullptr && n >= 1 && n <= HG_MAX_GROUP, "num_problems must be in [1,%d]", HG_MAX_GROUP);
+  HG_CHECK(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
+  GroupParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.num_problems = n;
+  int tiles = 0;
+  for (int g = 0; g < n; ++g) {
+    const HgGemmProblem& h = pr[g];
+    DevProblem& q = gp.p[g];
+    HG_CHECK(h.M > 0 && h.N > 0 && h.K > 0, "problem %d: empty dims", g);
+    HG_CHECK(h.A && h.B && h.out, "problem %d: null pointer", g);
+    HG_CHECK(h.k_splits >= 1, "problem %d: k_splits", g);
+    HG_CHECK(h.k_splits == 1 || epilogue == HG_EPI_ATOMIC_F32, "split-K needs the atomic epilogue");
+    HG_CHECK(epilogue != HG_EPI_DELU_BF16 || h.act, "problem %d: DELU epilogue needs act", g);
+    q.M = h.M; q.N = h.N; q.K = h.K;
+    q.a_mn = h.a_mn_major ? 1 : 0;
+    q.b_mn = h.b_mn_major ? 1 : 0;
+    q.num_kb = (h.K + BLOCK_K - 1) / BLOCK_K;
+    int ks = h.k_splits < q.num_kb ? h.k_splits : q.num_kb;
+    q.kb_per_split = (q.num_kb + ks - 1) / ks;
+    q.k_splits = (q.num_kb + q.kb_per_split - 1) / q.kb_per_split;   // no empty split
+    q.tiles_m = (h.M + BLOCK_M - 1) / BLOCK_M;
+    q.tiles_n = (h.N + block_n - 1) / block_n;
+    q.tile_begin = tiles;
+    tiles += q.tiles_m * q.tiles_n * q.k_splits;
+    q.tile_end = tiles;
+    q.out = h.out; q.ldo = h.ldo; q.bias = h.bias;
+    q.act = reinterpret_cast<const __nv_bfloat16*>(h.act); q.ldact = h.ldact; q.colsum = h.colsum;
+    if (epilogue == HG_EPI_BIAS_ELU_BF16 || epilogue == HG_EPI_DELU_BF16 || epilogue == HG_EPI_BIAS_BF16)
+      HG_CHECK(h.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(h.out) & 15) == 0, "problem %d: bf16 output alignment", g);
+    if (epilogue == HG_EPI_DELU_BF16)
+      HG_CHECK(h.ldact % 8 == 0 && (reinterpret_cast<uintptr_t>(h.act) & 15) == 0, "problem %d: act alignment", g);
+    int rc;
+    if (!q.a_mn) rc = make_tmap(&gp.tma_a[g], h.A, h.K, h.M, h.lda, BLOCK_M);
+    else rc = make_tmap(&gp.tma_a[g], h.A, h.M, h.K, h.lda, BLOCK_K);
+    if (rc != HG_OK) return rc;
+    if (!q.b_mn) rc = make_tmap(&gp.tma_b[g], h.B, h.K, h.N, h.ldb, block_n);
+    else rc = make_tmap(&gp.tma_b[g], h.B, h.N, h.K, h.ldb, BLOCK_K);
+    if (rc != HG_OK) return rc;
+  }
+  gp.total_tiles = tiles;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return block_n == 128 ? dispatch_epi<128>(gp, epilogue, s) : dispatch_epi<256>(gp, epilogue, s);
+}

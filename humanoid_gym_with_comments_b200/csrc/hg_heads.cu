@@ -1,0 +1,478 @@
+// Output layers ("heads") of the three MLPs, in fp32 SIMT, fused with everything that follows them.
+//
+// The last Linear of each net is tiny (H x {A,1,3}, H = 128 for XBot) and feeds scalar-heavy math, so it
+// stays in fp32 on CUDA cores and is fused:
+//   rollout : mu = W_a h_a + b_a, a = mu + std*eps, log-prob, V = W_c h_c + b_c     (PPO.act, ppo.py:116-126)
+//   update  : forward of the 3 heads + log-prob/KL/ratio/clipped surrogate/clipped value loss/entropy/lin-vel
+//             MSE (ppo.py:154-208) + dLoss/dOutputs + backward through the output Linear (dW, db, dH) and
+//             through the ELU of the last hidden layer (dZ, bias gradient), + d/d std.
+// Keeping the output layer in fp32 also keeps the policy mean's response to small Adam steps exact,
+// which the PPO ratio is sensitive to ("numerics").
+#include "hg_common.cuh"
+
+namespace hg {
+
+constexpr float LOG_SQRT_2PI = 0.9189385332046727f;  // log(sqrt(2*pi)) as torch.distributions.Normal uses it
+constexpr float HALF_LOG_2PI_PLUS_HALF = 1.4189385332046727f;
+
+// ------------------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = (a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  const float u2 = b * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+// standard normal number `j` of row `row` for (seed, counter)
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t counter, uint32_t row, uint32_t j) {
+  uint4 r = philox4x32_10(make_uint4(row, j >> 2, (uint32_t)counter, (uint32_t)(counter >> 32)),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
+  const int k = j & 3;
+  return k == 0 ? n01.x : k == 1 ? n01.y : k == 2 ? n23.x : n23.y;
+}
+
+// ------------------------------------------------------------------------------------------ shared helpers
+// Stage `rows` rows of a bf16 activation matrix into shared memory as [rows][H + 8] (the +8 keeps 16-byte row
+// alignment and staggers banks), rows beyond `valid` are zero.
+__device__ __forceinline__ void stage_h(const __nv_bfloat16* __restrict__ h, long long ld, int H, int row0, int valid,
+                                        int rows, __nv_bfloat16* sh) {
+  const int chunks = H >> 3;
+  const int pitch = H + 8;
+  for (int i = threadIdx.x; i < rows * chunks; i += blockDim.x) {
+    const int r = i / chunks, c = i - r * chunks;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < valid) v = __ldg(reinterpret_cast<const uint4*>(h + (long long)(row0 + r) * ld) + c);
+    *reinterpret_cast<uint4*>(sh + r * pitch + c * 8) = v;
+  }
+}
+__device__ __forceinline__ void stage_f32(const float* __restrict__ src, int n, float* dst) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// Partial dot products of one staged row with n_out weight rows, for the k-chunks owned by `sub` of `nsub`
+// cooperating lanes; reduced over the nsub lanes (nsub is a power of two <= 32, lanes are adjacent).
+template <int MAX_OUT>
+__device__ __forceinline__ void head_forward_row(const __nv_bfloat16* hrow, int H, const float* W, const float* b,
+                                                 int n_out, int sub, int nsub, float (&out)[MAX_OUT]) {
+#pragma unroll
+  for (int a = 0; a < MAX_OUT; ++a) out[a] = 0.f;
+  for (int c = sub; c < (H >> 3); c += nsub) {
+    const uint4 hv = *reinterpret_cast<const uint4*>(hrow + c * 8);
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+    float hf[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(hw[k]);
+      hf[2 * k] = f.x;
+      hf[2 * k + 1] = f.y;
+    }
+#pragma unroll
+    for (int a = 0; a < MAX_OUT; ++a) {
+      if (a < n_out) {
+        const float4 w0 = *reinterpret_cast<const float4*>(W + a * H + c * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(W + a * H + c * 8 + 4);
+        out[a] += hf[0] * w0.x + hf[1] * w0.y + hf[2] * w0.z + hf[3] * w0.w + hf[4] * w1.x + hf[5] * w1.y +
+                  hf[6] * w1.z + hf[7] * w1.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < MAX_OUT; ++a) {
+    if (a < n_out) {
+      for (int o = nsub >> 1; o > 0; o >>= 1) out[a] += __shfl_xor_sync(0xffffffffu, out[a], o);
+      out[a] += b[a];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ rollout head
+constexpr int RH_ROWS = 32;      // rows per block
+constexpr int RH_SUB = 8;        // lanes per row
+constexpr int MAX_A = 32;        // max num_actions
+
+__global__ void __launch_bounds__(RH_ROWS* RH_SUB)
+    policy_head_rollout_kernel(const __nv_bfloat16* __restrict__ ha, long long ld_ha, int H_a, const float* __restrict__ W_a,
+                               const float* __restrict__ b_a, const float* __restrict__ std, const __nv_bfloat16* __restrict__ hc,
+                               long long ld_hc, int H_c, const float* __restrict__ W_c, const float* __restrict__ b_c,
+                               const float* __restrict__ eps, uint64_t seed, uint64_t counter, int n, int A,
+                               float* __restrict__ actions, float* __restrict__ mu, float* __restrict__ sigma,
+                               float* __restrict__ log_prob, float* __restrict__ values) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* sWa = reinterpret_cast<float*>(smem);                 // [A][H_a]
+  float* sWc = sWa + A * H_a;                                  // [H_c]
+  float* sb = sWc + H_c;                                       // [A] b_a, [1] b_c, [A] std
+  __nv_bfloat16* sha = reinterpret_cast<__nv_bfloat16*>(sb + 2 * MAX_A + 4);
+  __nv_bfloat16* shc = ha ? sha + RH_ROWS * (H_a + 8) : sha;
+  const int row0 = blockIdx.x * RH_ROWS;
+  const int valid = min(RH_ROWS, n - row0);
+  if (ha) {
+    stage_f32(W_a, A * H_a, sWa);
+    stage_f32(b_a, A, sb);
+    stage_f32(std, A, sb + MAX_A + 1);
+    stage_h(ha, ld_ha, H_a, row0, valid, RH_ROWS, sha);
+  }
+  stage_f32(W_c, H_c, sWc);
+  if (threadIdx.x == 0) sb[MAX_A] = b_c[0];
+  stage_h(hc, ld_hc, H_c, row0, valid, RH_ROWS, shc);
+  __syncthreads();
+
+  const int r = threadIdx.x / RH_SUB, sub = threadIdx.x % RH_SUB;
+  const int row = row0 + r;
+  float v1[1];
+  head_forward_row<1>(shc + r * (H_c + 8), H_c, sWc, sb + MAX_A, 1, sub, RH_SUB, v1);
+  if (sub == 0 && row < n) values[row] = v1[0];
+  if (!ha) return;
+  float m[MAX_A];
+  head_forward_row<MAX_A>(sha + r * (H_a + 8), H_a, sWa, sb, A, sub, RH_SUB, m);
+  if (row >= n) return;
+  // lanes of the row split the actions; log-prob summed in action order by lane 0 for determinism
+  float lp = 0.f;
+  if (sub == 0) {
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {
+      if (a < A) {
+        const float sd = sb[MAX_A + 1 + a];
+        const float e = eps ? eps[(long long)row * A + a] : philox_normal(seed, counter, (uint32_t)row, (uint32_t)a);
+        const float act = m[a] + sd * e;                       // Normal(mu, std).sample()  (actor_critic.py:129,133)
+        const float d = act - m[a];
+        lp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;   // Normal.log_prob
+        actions[(long long)row * A + a] = act;
+        mu[(long long)row * A + a] = m[a];
+        sigma[(long long)row * A + a] = sd;
+      }
+    }
+    log_prob[row] = lp;
+  }
+}
+
+__global__ void __launch_bounds__(RH_ROWS* RH_SUB)
+    head_forward_kernel(const __nv_bfloat16* __restrict__ h, long long ld_h, int H, const float* __restrict__ W,
+                        const float* __restrict__ b, int n_out, int n, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* sW = reinterpret_cast<float*>(smem);                  // [n_out][H]
+  float* sb = sW + n_out * H;                                  // [MAX_A]
+  __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(sb + MAX_A);
+  const int row0 = blockIdx.x * RH_ROWS;
+  const int valid = min(RH_ROWS, n - row0);
+  stage_f32(W, n_out * H, sW);
+  stage_f32(b, n_out, sb);
+  stage_h(h, ld_h, H, row0, valid, RH_ROWS, sh);
+  __syncthreads();
+  const int r = threadIdx.x / RH_SUB, sub = threadIdx.x % RH_SUB;
+  float m[MAX_A];
+  head_forward_row<MAX_A>(sh + r * (H + 8), H, sW, sb, n_out, sub, RH_SUB, m);
+  if (row0 + r < n) {
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a)
+      if (a < n_out && (a % RH_SUB) == sub) out[(long long)(row0 + r) * n_out + a] = m[a];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ update head + losses
+constexpr int LH_ROWS = 64;
+constexpr int LH_THREADS = 256;
+constexpr int LH_SUB = LH_THREADS / LH_ROWS;   // 4 lanes per row in the forward / loss phase
+
+struct NetSmem {
+  __nv_bfloat16* h;   // [LH_ROWS][H+8]
+  float* W;           // [n_out][H]
+  float* b;           // [n_out]
+  float* dOut;        // [LH_ROWS][n_out]
+};
+
+// Backward of one head for the block's rows: column-parallel over the hidden index k.
+//   dH[r,k] = sum_a dOut[r,a] W[a,k];  dZ = dH * elu'(h);  gW[a,k] += dOut[r,a] h[r,k];  gb_hidden[k] += dZ[r,k]
+__device__ __forceinline__ void head_backward(const HgHeadNet& net, const NetSmem& s, int row0, int valid, float* red) {
+  const int H = net.H, n_out = net.n_out, pitch = H + 8;
+  const int groups = LH_THREADS / 128;              // row groups working on the same k in parallel
+  const int grp = threadIdx.x / 128;
+  for (int k0 = 0; k0 < H; k0 += 128) {            // uniform trip count: the loop body holds block barriers
+    const int k = k0 + (threadIdx.x % 128);
+    const bool k_ok = k < H;
+    float gw[MAX_A], w[MAX_A];
+#pragma unroll
+    for (int a = 0; a < MAX_A; ++a) {
+      gw[a] = 0.f;
+      w[a] = (k_ok && a < n_out) ? s.W[a * H + k] : 0.f;
+    }
+    float gbh = 0.f;
+    if (k_ok) {
+      for (int r = grp; r < valid; r += groups) {
+        const float h = __bfloat162float(s.h[r * pitch + k]);
+        float dh = 0.f;
+#pragma unroll
+        for (int a = 0; a < MAX_A; ++a) {
+          if (a < n_out) {
+            const float d = s.dOut[r * n_out + a];
+            dh += d * w[a];
+            gw[a] += d * h;
+          }
+        }
+        const float dz = dh * (h > 0.f ? 1.f : h + 1.f);
+        reinterpret_cast<__nv_bfloat16*>(net.dZ)[(long long)(row0 + r) * net.ld_dz + k] = __float2bfloat16_rn(dz);
+        gbh += dz;
+      }
+    }
+    // combine the row groups through shared memory, then one atomic per (a,k) per block
+    if (grp > 0) {
+      float* slot = red + (size_t)((grp - 1) * 128 + (threadIdx.x % 128)) * (MAX_A + 1);
+#pragma unroll
+      for (int a = 0; a < MAX_A; ++a)
+        if (a < n_out) slot[a] = gw[a];
+      slot[MAX_A] = gbh;
+    }
+    __syncthreads();
+    if (grp == 0 && k_ok) {
+      for (int g = 1; g < groups; ++g) {
+        const float* slot = red + (size_t)((g - 1) * 128 + (threadIdx.x % 128)) * (MAX_A + 1);
+#pragma unroll
+        for (int a = 0; a < MAX_A; ++a)
+          if (a < n_out) gw[a] += slot[a];
+        gbh += slot[MAX_A];
+      }
+#pragma unroll
+      for (int a = 0; a < MAX_A; ++a)
+        if (a < n_out) atomicAdd(net.gW + a * H + k, gw[a]);
+      atomicAdd(net.gb_hidden + k, gbh);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_constant__ HgLossArgs L) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int A = L.A;
+  // ---- carve shared memory
+  uint8_t* p = smem;
+  auto carve = [&](size_t bytes) { uint8_t* q = p; p += (bytes + 15) & ~size_t(15); return q; };
+  NetSmem sa, sc, sl;
+  const HgHeadNet* nets[3] = {&L.actor, &L.critic, &L.linvel};
+  NetSmem* ss[3] = {&sa, &sc, &sl};
+  for (int i = 0; i < 3; ++i) {
+    ss[i]->h = reinterpret_cast<__nv_bfloat16*>(carve((size_t)LH_ROWS * (nets[i]->H + 8) * 2));
+    ss[i]->W = reinterpret_cast<float*>(carve((size_t)nets[i]->n_out * nets[i]->H * 4));
+    ss[i]->b = reinterpret_cast<float*>(carve((size_t)nets[i]->n_out * 4));
+    ss[i]->dOut = reinterpret_cast<float*>(carve((size_t)LH_ROWS * nets[i]->n_out * 4));
+  }
+  float* s_std = reinterpret_cast<float*>(carve(MAX_A * 4));
+  float* s_gstd = reinterpret_cast<float*>(carve(MAX_A * 4));
+  double* s_stats = reinterpret_cast<double*>(carve(8 * 8));
+  float* s_red = reinterpret_cast<float*>(carve((size_t)(LH_THREADS / 128 - 1) * 128 * (MAX_A + 1) * 4 + 16));
+
+  const int row0 = blockIdx.x * LH_ROWS;
+  const int valid = min(LH_ROWS, L.rows - row0);
+  for (int i = 0; i < 3; ++i) {
+    stage_h(reinterpret_cast<const __nv_bfloat16*>(nets[i]->h), nets[i]->ld_h, nets[i]->H, row0, valid, LH_ROWS, ss[i]->h);
+    stage_f32(nets[i]->W, nets[i]->n_out * nets[i]->H, ss[i]->W);
+    stage_f32(nets[i]->b, nets[i]->n_out, ss[i]->b);
+  }
+  stage_f32(L.std, A, s_std);
+  if (threadIdx.x < MAX_A) s_gstd[threadIdx.x] = 0.f;
+  if (threadIdx.x < 8) s_stats[threadIdx.x] = 0.0;
+  __syncthreads();
+
+  // ---- forward of the three heads + losses, LH_SUB lanes per row
+  const int r = threadIdx.x / LH_SUB, sub = threadIdx.x % LH_SUB;
+  float m[MAX_A], v1[1], lv[3];
+  head_forward_row<MAX_A>(sa.h + r * (L.actor.H + 8), L.actor.H, sa.W, sa.b, A, sub, LH_SUB, m);
+  head_forward_row<1>(sc.h + r * (L.critic.H + 8), L.critic.H, sc.W, sc.b, 1, sub, LH_SUB, v1);
+  head_forward_row<3>(sl.h + r * (L.linvel.H + 8), L.linvel.H, sl.W, sl.b, 3, sub, LH_SUB, lv);
+
+  if (sub == 0) {
+    if (r < valid) {
+      const long long src = L.idx ? L.idx[row0 + r] : (long long)(row0 + r);
+      const float inv_rows = L.inv_world / (float)L.rows;      // 1 / (rows over all ranks)
+      // -- Gaussian log-prob, entropy, KL(old || new)   (actor_critic.py:123-138, ppo.py:165-166)
+      float logp = 0.f, ent = 0.f, kl = 0.f;
+#pragma unroll
+      for (int a = 0; a < MAX_A; ++a) {
+        if (a < A) {
+          const float sd = s_std[a];
+          const float d = L.actions[src * A + a] - m[a];
+          logp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;
+          ent += HALF_LOG_2PI_PLUS_HALF + logf(sd);
+          const float osd = L.old_sigma[src * A + a];
+          const float dm = L.old_mu[src * A + a] - m[a];
+          kl += logf(sd / osd + 1.e-5f) + (osd * osd + dm * dm) / (2.f * sd * sd) - 0.5f;
+        }
+      }
+      // -- clipped surrogate (ppo.py:178-184)
+      const float adv = L.advantages[src];
+      const float ratio = expf(logp - L.old_log_prob[src]);
+      const float s1 = -adv * ratio;
+      const float s2 = -adv * fminf(fmaxf(ratio, 1.f - L.clip_param), 1.f + L.clip_param);
+      const float surr = fmaxf(s1, s2);
+      const float g_logp = (s1 >= s2 ? s1 : 0.f) * inv_rows;   // d surr / d logp  (ties: clamp passes gradient)
+      // -- value loss (ppo.py:187-194)
+      const float R = L.returns[src], v = v1[0];
+      float vl, g_v;
+      if (L.use_clipped_value_loss) {
+        const float vo = L.old_values[src];
+        const float dv = v - vo;
+        const float vc = vo + fminf(fmaxf(dv, -L.clip_param), L.clip_param);
+        const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+        const float pass = (dv >= -L.clip_param && dv <= L.clip_param) ? 1.f : 0.f;
+        vl = fmaxf(l1, l2);
+        g_v = l1 > l2 ? 2.f * (v - R) : (l1 < l2 ? 2.f * (vc - R) * pass : (v - R) + (vc - R) * pass);
+      } else {
+        vl = (R - v) * (R - v);
+        g_v = 2.f * (v - R);
+      }
+      sc.dOut[r] = L.value_loss_coef * g_v * inv_rows;
+      // -- lin-vel regression (ppo.py:205; target = critic_obs[:, 53:56], rollout_storage.py:164)
+      float lsq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float e = lv[j] - L.critic_obs[src * L.ld_cobs + L.lv_col + j];
+        lsq += e * e;
+        sl.dOut[r * 3 + j] = L.lin_vel_coef * 2.f * e * inv_rows * (1.f / 3.f);
+      }
+      // -- gradients wrt mean and std
+#pragma unroll
+      for (int a = 0; a < MAX_A; ++a) {
+        if (a < A) {
+          const float sd = s_std[a];
+          const float d = L.actions[src * A + a] - m[a];
+          sa.dOut[r * A + a] = g_logp * d / (sd * sd);
+          const float gs = g_logp * (d * d / (sd * sd * sd) - 1.f / sd) - L.entropy_coef * inv_rows / sd;
+          atomicAdd(&s_gstd[a], gs);
+        }
+      }
+      atomicAdd(&s_stats[0], (double)vl);
+      atomicAdd(&s_stats[1], (double)surr);
+      atomicAdd(&s_stats[2], (double)lsq);
+      atomicAdd(&s_stats[3], (double)kl);
+      atomicAdd(&s_stats[4], (double)ent);
+    } else {
+      sc.dOut[r] = 0.f;
+      for (int j = 0; j < 3; ++j) sl.dOut[r * 3 + j] = 0.f;
+      for (int a = 0; a < A; ++a) sa.dOut[r * A + a] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- output-layer bias gradients, std gradient and statistics: a handful of atomics per block
+  for (int i = 0; i < 3; ++i) {
+    const int n_out = nets[i]->n_out;
+    if (threadIdx.x < n_out) {
+      float g = 0.f;
+      for (int rr = 0; rr < valid; ++rr) g += ss[i]->dOut[rr * n_out + threadIdx.x];
+      atomicAdd(nets[i]->gb + threadIdx.x, g);
+    }
+  }
+  if (threadIdx.x < A) atomicAdd(L.g_std + threadIdx.x, s_gstd[threadIdx.x]);
+  if (threadIdx.x < 5) atomicAdd(L.stats + threadIdx.x, (float)s_stats[threadIdx.x]);
+
+  // ---- backward through the three output layers and the ELU below them
+  head_backward(L.actor, sa, row0, valid, s_red);
+  head_backward(L.critic, sc, row0, valid, s_red);
+  head_backward(L.linvel, sl, row0, valid, s_red);
+}
+
+static size_t loss_smem_bytes(const HgLossArgs& L) {
+  auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
+  size_t t = 0;
+  const HgHeadNet* nets[3] = {&L.actor, &L.critic, &L.linvel};
+  for (int i = 0; i < 3; ++i) {
+    t += al((size_t)LH_ROWS * (nets[i]->H + 8) * 2) + al((size_t)nets[i]->n_out * nets[i]->H * 4) +
+         al((size_t)nets[i]->n_out * 4) + al((size_t)LH_ROWS * nets[i]->n_out * 4);
+  }
+  t += al(MAX_A * 4) * 2 + al(64) + al((size_t)(LH_THREADS / 128 - 1) * 128 * (MAX_A + 1) * 4 + 16);
+  return t;
+}
+
+}  // namespace hg
+
+extern "C" int hg_policy_head_rollout(const void* h_actor, int64_t ld_ha, int H_a, const float* W_a, const float* b_a,
+                                      const float* std, const void* h_critic, int64_t ld_hc, int H_c, const float* W_c,
+                                      const float* b_c, const float* eps, uint64_t seed, uint64_t counter, int n, int A,
+                                      float* actions, float* mu, float* sigma, float* log_prob, float* values, void* stream) {
+  using namespace hg;
+  HG_CHECK(h_critic && W_c && b_c && values && n > 0, "hg_policy_head_rollout: bad critic arguments");
+  HG_CHECK(H_c % 8 == 0 && H_c <= 512 && ld_hc % 8 == 0, "critic hidden width must be a multiple of 8, <= 512");
+  if (h_actor) {
+    HG_CHECK(W_a && b_a && std && actions && mu && sigma && log_prob, "hg_policy_head_rollout: null actor pointer");
+    HG_CHECK(A >= 1 && A <= MAX_A, "num_actions must be in [1,%d]", MAX_A);
+    HG_CHECK(H_a % 8 == 0 && H_a <= 512 && ld_ha % 8 == 0, "actor hidden width must be a multiple of 8, <= 512");
+  } else {
+    H_a = 0;
+    A = 0;
+  }
+  const size_t smem = (size_t)(A * H_a + H_c + 2 * MAX_A + 4) * 4 +
+                      (size_t)RH_ROWS * ((h_actor ? H_a + 8 : 0) + H_c + 8) * 2 + 32;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    HG_CUDA(cudaFuncSetAttribute(policy_head_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  policy_head_rollout_kernel<<<(n + RH_ROWS - 1) / RH_ROWS, RH_ROWS * RH_SUB, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h_actor), ld_ha, H_a, W_a, b_a, std,
+      reinterpret_cast<const __nv_bfloat16*>(h_critic), ld_hc, H_c, W_c, b_c, eps, seed, counter, n, A, actions, mu,
+      sigma, log_prob, values);
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
+}
+
+extern "C" int hg_value_head(const void* h_critic, int64_t ld_hc, int H_c, const float* W_c, const float* b_c, int n,
+                             float* values, void* stream) {
+  return hg_policy_head_rollout(nullptr, 0, 0, nullptr, nullptr, nullptr, h_critic, ld_hc, H_c, W_c, b_c, nullptr, 0, 0,
+                                n, 0, nullptr, nullptr, nullptr, nullptr, values, stream);
+}
+
+extern "C" int hg_head_forward(const void* h, int64_t ld_h, int H, const float* W, const float* b, int n_out, int n,
+                               float* out, void* stream) {
+  using namespace hg;
+  HG_CHECK(h && W && b && out && n > 0, "hg_head_forward: bad arguments");
+  HG_CHECK(n_out >= 1 && n_out <= MAX_A, "hg_head_forward: n_out must be in [1,%d]", MAX_A);
+  HG_CHECK(H % 8 == 0 && H >= 8 && H <= 512 && ld_h % 8 == 0, "hg_head_forward: hidden width must be a multiple of 8, <= 512");
+  const size_t smem = (size_t)(n_out * H + MAX_A) * 4 + (size_t)RH_ROWS * (H + 8) * 2 + 32;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    HG_CUDA(cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  head_forward_kernel<<<(n + RH_ROWS - 1) / RH_ROWS, RH_ROWS * RH_SUB, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h), ld_h, H, W, b, n_out, n, out);
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
+}
+
+extern "C" int hg_ppo_head_loss(const HgLossArgs* L, void* stream) {
+  using namespace hg;
+  HG_CHECK(L != nullptr && L->rows > 0, "hg_ppo_head_loss: bad arguments");
+  HG_CHECK(L->A >= 1 && L->A <= MAX_A && L->actor.n_out == L->A, "num_actions must be in [1,%d] and match the actor head", MAX_A);
+  HG_CHECK(L->critic.n_out == 1 && L->linvel.n_out == 3, "critic head must have 1 output, lin-vel head 3");
+  const HgHeadNet* nets[3] = {&L->actor, &L->critic, &L->linvel};
+  for (int i = 0; i < 3; ++i) {
+    HG_CHECK(nets[i]->H % 8 == 0 && nets[i]->H >= 8 && nets[i]->H <= 256, "head %d: hidden width must be a multiple of 8 in [8,256]", i);
+    HG_CHECK(nets[i]->h && nets[i]->W && nets[i]->b && nets[i]->gW && nets[i]->gb && nets[i]->dZ && nets[i]->gb_hidden, "head %d: null pointer", i);
+    HG_CHECK(nets[i]->ld_h % 8 == 0, "head %d: ld_h alignment", i);
+  }
+  HG_CHECK(L->actions && L->old_mu && L->old_sigma && L->old_log_prob && L->advantages && L->returns && L->old_values &&
+               L->critic_obs && L->std && L->g_std && L->stats, "hg_ppo_head_loss: null pointer");
+  const size_t smem = loss_smem_bytes(*L);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    HG_CUDA(cudaFuncSetAttribute(ppo_head_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ppo_head_loss_kernel<<<(L->rows + LH_ROWS - 1) / LH_ROWS, LH_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*L);
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
+}

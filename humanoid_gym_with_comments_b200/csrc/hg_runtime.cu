@@ -1,0 +1,36 @@
+// Library-level plumbing: error text, launch counter, device attributes.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "hg_common.cuh"
+
+namespace hg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+}  // namespace hg
+
+extern "C" const char* hg_last_error(void) { return hg::g_err; }
+extern "C" int hg_abi_version(void) { return HG_ABI_VERSION; }
+extern "C" int64_t hg_launch_count(void) { return hg::g_launches.load(std::memory_order_relaxed); }

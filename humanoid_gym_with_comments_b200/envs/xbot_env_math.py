@@ -1,0 +1,303 @@
+"""Env-side hot path: the tensor math of `XBotLFreeEnv.post_physics_step` as ONE fused CUDA launch.
+
+Reference being replaced (humanoid/envs/custom/humanoid_env.py): base-frame quantities :784-788,
+`check_termination` :811-816, `compute_reward` + 22 `_reward_*` :889-907/:1170-1437, the buffer and history
+zeroing of `reset_idx` :1132-1139/:1160-1163, `compute_observations` (+ `compute_ref_state`, `_get_gait_phase`,
+noise, 15/3-frame history) :683-744/:818-887, the hand-over :802-806 and the +-18 clips :654-657.
+
+`XBotEnvMath` keeps the reference's attribute names for the persistent tensors so a subclass of the real
+`XBotLFreeEnv` can delegate to it.  `SyntheticXBotEnv` is the `VecEnv`-shaped stand-in used by
+bench.py and the tests: Isaac Gym's closed PhysX step is replaced by a pool of synthetic Isaac-Gym-shaped state
+tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+
+from .. import _lib
+from .._lib import (ENV_PHASE_ALL, HG_NUM_REWARDS, REWARD_NAMES, HgEnvBuffers, HgEnvConfig, check, current_stream, ptr)
+
+# humanoid_config.py:395-430 (XBotLCfg.rewards.scales)
+XBOT_REWARD_SCALES = dict(
+    joint_pos=1.6, feet_clearance=1.0, feet_contact_number=1.2, feet_air_time=1.0, foot_slip=-0.05,
+    feet_distance=0.2, knee_distance=0.2, feet_contact_forces=-0.01, tracking_lin_vel=1.2,
+    tracking_ang_vel=1.1, vel_mismatch_exp=0.5, low_speed=0.2, track_vel_hard=0.5,
+    default_joint_pos=0.5, orientation=1.0, base_height=0.2, base_acc=0.2, action_smoothness=-0.002,
+    torques=-1e-5, dof_vel=-5e-4, dof_acc=-1e-7, collision=-1.0)
+
+
+@dataclass
+class XBotMathConfig:
+    """The scalars of XBotLCfg that the env math reads (humanoid_config.py: env :37-68, noise :162-182,
+    rewards :372-430, normalization :432-459) + the body/DOF layout."""
+    num_envs: int = 4096
+    num_dof: int = 12
+    leg_offset: int = 0                  # 0: upstream 12-DOF XBot-L, 6: shipped 18-DOF fork (arms first)
+    num_bodies: int = 13
+    feet_indices: tuple = (6, 12)
+    knee_indices: tuple = (4, 10)
+    termination_contact_indices: tuple = (0,)
+    penalised_contact_indices: tuple = (0,)
+    frame_stack: int = 15
+    c_frame_stack: int = 3
+    dt: float = 0.01
+    cycle_time: float = 0.64
+    episode_length_s: float = 24.0
+    target_joint_pos_scale: float = 0.17
+    base_height_target: float = 0.94
+    min_dist: float = 0.2
+    max_dist: float = 0.5
+    target_feet_height: float = 0.1
+    tracking_sigma: float = 5.0
+    max_contact_force: float = 700.0
+    only_positive_rewards: bool = True
+    lin_vel_scale: float = 2.0
+    ang_vel_scale: float = 1.0
+    dof_pos_scale: float = 1.0
+    dof_vel_scale: float = 0.05
+    quat_scale: float = 1.0
+    clip_observations: float = 18.0
+    add_noise: bool = True
+    noise_level: float = 0.6
+    noise_dof_pos: float = 0.05
+    noise_dof_vel: float = 0.5
+    noise_ang_vel: float = 0.1
+    noise_quat: float = 0.03
+    reward_scales: Dict[str, float] = field(default_factory=lambda: dict(XBOT_REWARD_SCALES))
+    phase_mul_reciprocal: bool = False   # True reproduces torch-CUDA's x/c == x*(1/c)
+
+    @staticmethod
+    def for_dof(num_dof: int, num_envs: int = 4096) -> "XBotMathConfig":
+        if num_dof == 12:
+            return XBotMathConfig(num_envs=num_envs)
+        if num_dof == 18:
+            return XBotMathConfig(num_envs=num_envs, num_dof=18, leg_offset=6, num_bodies=19,
+                                  feet_indices=(12, 18), knee_indices=(10, 16))
+        raise ValueError("num_dof must be 12 or 18")
+
+    @property
+    def num_single_obs(self) -> int:
+        return 11 + 3 * self.num_dof
+
+    @property
+    def single_num_privileged_obs(self) -> int:
+        return 25 + 4 * self.num_dof
+
+    @property
+    def num_observations(self) -> int:
+        return self.frame_stack * self.num_single_obs
+
+    @property
+    def num_privileged_obs(self) -> int:
+        return self.c_frame_stack * self.single_num_privileged_obs
+
+    def noise_scale_vec(self) -> torch.Tensor:
+        """`_get_noise_scale_vec` (:748-768).  The 18-DOF fork's hard-coded slices (misaligned with its
+        65-wide frame) are reproduced as data."""
+        v = torch.zeros(self.num_single_obs)
+        D = self.num_dof
+        if D == 18:
+            v[5:23] = self.noise_dof_pos * self.dof_pos_scale
+            v[23:41] = self.noise_dof_vel * self.dof_vel_scale
+            v[53:56] = self.noise_ang_vel * self.ang_vel_scale
+            v[56:59] = self.noise_quat * self.quat_scale
+        else:
+            v[5:5 + D] = self.noise_dof_pos * self.dof_pos_scale
+            v[5 + D:5 + 2 * D] = self.noise_dof_vel * self.dof_vel_scale
+            v[5 + 3 * D:8 + 3 * D] = self.noise_ang_vel * self.ang_vel_scale
+            v[8 + 3 * D:11 + 3 * D] = self.noise_quat * self.quat_scale
+        return v
+
+
+class XBotEnvMath:
+    """Persistent env-math state + the fused step.  Attribute names follow `XBotLFreeEnv._init_buffers`."""
+
+    def __init__(self, cfg: XBotMathConfig, device, default_dof_pos: Optional[torch.Tensor] = None,
+                 noise_scale_vec: Optional[torch.Tensor] = None):
+        if torch.device(device).type != "cuda":
+            raise _lib.HgError("XBotEnvMath needs a CUDA device (no CPU fallback)")
+        for k in cfg.reward_scales:
+            if k not in REWARD_NAMES and cfg.reward_scales[k] != 0:
+                raise NotImplementedError(f"reward term '{k}' has no fused implementation")
+        self.cfg, self.device = cfg, torch.device(device)
+        N, D = cfg.num_envs, cfg.num_dof
+        z = lambda *s, **k: torch.zeros(*s, device=self.device, **k)
+        self.num_envs, self.num_dof = N, D
+        self.max_episode_length = math.ceil(cfg.episode_length_s / cfg.dt)
+        self.actions, self.last_actions, self.last_last_actions = z(N, D), z(N, D), z(N, D)
+        self.last_dof_vel, self.last_root_vel = z(N, D), z(N, 6)
+        self.feet_air_time = z(N, 2)
+        self.last_contacts = z(N, 2, dtype=torch.bool)
+        self.feet_height = z(N, 2)
+        self.last_feet_z = torch.full((N, 2), 0.05, device=self.device)
+        self.ref_dof_pos = z(N, D)
+        self.episode_length_buf = z(N, dtype=torch.long)
+        self.episode_sums_tensor = z(HG_NUM_REWARDS, N)
+        self.default_dof_pos = z(1, D) if default_dof_pos is None else default_dof_pos.reshape(1, D).to(self.device).float().contiguous()
+        nv = cfg.noise_scale_vec() if noise_scale_vec is None else noise_scale_vec
+        self.noise_scale_vec = nv.to(self.device).float().contiguous()
+        self.rew_buf = z(N)
+        self.reset_buf = z(N, dtype=torch.bool)
+        self.time_out_buf = z(N, dtype=torch.bool)
+        self.reward_terms = None
+        # double-buffered stacked observations (history in -> out must not alias)
+        self._obs = [z(N, cfg.num_observations), z(N, cfg.num_observations)]
+        self._priv = [z(N, cfg.num_privileged_obs), z(N, cfg.num_privileged_obs)]
+        self._cur = 0
+        self.obs_buf, self.privileged_obs_buf = self._obs[0], self._priv[0]
+        self.step_counter = 0
+        self.seed = 0
+
+        c = HgEnvConfig()
+        c.num_envs, c.D, c.leg_offset, c.num_bodies = N, D, cfg.leg_offset, cfg.num_bodies
+        c.feet[0], c.feet[1] = cfg.feet_indices
+        c.knees[0], c.knees[1] = cfg.knee_indices
+        c.num_term_bodies = len(cfg.termination_contact_indices)
+        for i, b in enumerate(cfg.termination_contact_indices):
+            c.term_bodies[i] = b
+        c.num_pen_bodies = len(cfg.penalised_contact_indices)
+        for i, b in enumerate(cfg.penalised_contact_indices):
+            c.pen_bodies[i] = b
+        c.frame_stack, c.c_frame_stack = cfg.frame_stack, cfg.c_frame_stack
+        c.dt, c.cycle_time, c.max_episode_length = cfg.dt, cfg.cycle_time, float(self.max_episode_length)
+        c.target_joint_pos_scale, c.base_height_target = cfg.target_joint_pos_scale, cfg.base_height_target
+        c.min_dist, c.max_dist, c.target_feet_height = cfg.min_dist, cfg.max_dist, cfg.target_feet_height
+        c.tracking_sigma, c.max_contact_force = cfg.tracking_sigma, cfg.max_contact_force
+        c.only_positive_rewards = 1 if cfg.only_positive_rewards else 0
+        c.lin_vel_scale, c.ang_vel_scale, c.dof_pos_scale = cfg.lin_vel_scale, cfg.ang_vel_scale, cfg.dof_pos_scale
+        c.dof_vel_scale, c.quat_scale, c.clip_obs = cfg.dof_vel_scale, cfg.quat_scale, cfg.clip_observations
+        c.noise_level = cfg.noise_level if cfg.add_noise else 0.0
+        for k, name in enumerate(REWARD_NAMES):
+            c.reward_scale_dt[k] = cfg.reward_scales.get(name, 0.0) * cfg.dt     # python double product, as :212
+        c.phase_mul_reciprocal = 1 if cfg.phase_mul_reciprocal else 0
+        c.phases = ENV_PHASE_ALL
+        self._c = c
+
+    @property
+    def episode_sums(self) -> Dict[str, torch.Tensor]:
+        return {name: self.episode_sums_tensor[k] for k, name in enumerate(REWARD_NAMES)
+                if self.cfg.reward_scales.get(name, 0.0) != 0}
+
+    def reset_history(self):
+        for b in self._obs + self._priv:
+            b.zero_()
+
+    def step(self, sim: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None, phases: int = ENV_PHASE_ALL,
+             obs_out: Optional[torch.Tensor] = None, priv_out: Optional[torch.Tensor] = None):
+        """One fused post-physics step on the Isaac-Gym-shaped tensors in `sim` (keys: root_states, dof_state,
+        contact_forces, rigid_state, commands, torques, rand_push_force, rand_push_torque, env_frictions, body_mass;
+        optional `actions` [N,D] = the actions applied this step, copied into `self.actions` first).
+        `noise`: N(0,1) draws [N, num_single_obs] (the reference's `randn_like`, :877) or None for in-kernel Philox.
+        `obs_out` / `priv_out`: optional destinations (e.g. the learner's storage slot) instead of the internal
+        double buffer.  Returns (obs_buf, privileged_obs_buf, rew_buf, reset_buf, time_out_buf)."""
+        _lib.require_cuda(*[v for v in sim.values() if torch.is_tensor(v)])
+        if "actions" in sim and sim["actions"] is not None:
+            self.actions.copy_(sim["actions"])
+        nxt = 1 - self._cur
+        obs_next = obs_out if obs_out is not None else self._obs[nxt]
+        priv_next = priv_out if priv_out is not None else self._priv[nxt]
+        b = HgEnvBuffers()
+        for k in ("root_states", "dof_state", "contact_forces", "rigid_state", "commands", "torques",
+                  "rand_push_force", "rand_push_torque", "env_frictions", "body_mass"):
+            t = sim[k]
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise _lib.HgError(f"sim['{k}'] must be a contiguous float32 tensor")
+            setattr(b, k, ptr(t))
+        b.default_dof_pos, b.noise_scale_vec = ptr(self.default_dof_pos), ptr(self.noise_scale_vec)
+        b.noise = ptr(noise)
+        self.step_counter += 1
+        b.seed, b.counter = self.seed, self.step_counter
+        for k in ("actions", "last_actions", "last_last_actions", "last_dof_vel", "last_root_vel", "feet_air_time",
+                  "last_contacts", "feet_height", "last_feet_z", "ref_dof_pos", "episode_length_buf"):
+            setattr(b, k, ptr(getattr(self, k)))
+        b.episode_sums = ptr(self.episode_sums_tensor)
+        b.obs_prev, b.obs_prev_ld = ptr(self.obs_buf), self.obs_buf.stride(0)
+        b.priv_prev, b.priv_prev_ld = ptr(self.privileged_obs_buf), self.privileged_obs_buf.stride(0)
+        b.obs_next, b.obs_next_ld = ptr(obs_next), obs_next.stride(0)
+        b.priv_next, b.priv_next_ld = ptr(priv_next), priv_next.stride(0)
+        b.rew_buf, b.reset_buf, b.time_out_buf = ptr(self.rew_buf), ptr(self.reset_buf), ptr(self.time_out_buf)
+        b.reward_terms = ptr(self.reward_terms)
+        self._c.phases = phases
+        check(_lib.load().hg_env_step(C.byref(self._c), C.byref(b), current_stream()))
+        if phases & 2:
+            self.obs_buf, self.privileged_obs_buf = obs_next, priv_next
+            if obs_out is None:
+                self._cur = nxt
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.time_out_buf
+
+
+def synthetic_sim_state(cfg: XBotMathConfig, gen: torch.Generator, device, upright: bool = True,
+                        base_contact_frac: float = 0.02) -> Dict[str, torch.Tensor]:
+    """Isaac-Gym-shaped synthetic tensors, generated on `device`."""
+    N, D, B = cfg.num_envs, cfg.num_dof, cfg.num_bodies
+    rn = lambda *s: torch.randn(*s, generator=gen, device=device)
+    ru = lambda *s: torch.rand(*s, generator=gen, device=device)
+    root = torch.zeros(N, 13, device=device)
+    root[:, :3] = torch.tensor([0.0, 0.0, 0.95], device=device) + 0.1 * rn(N, 3)
+    quat = torch.cat((0.1 * rn(N, 3), torch.ones(N, 1, device=device)), dim=1) if upright else rn(N, 4)
+    root[:, 3:7] = quat / quat.norm(dim=1, keepdim=True)
+    root[:, 7:13] = 0.3 * rn(N, 6)
+    cf = (20.0 * rn(N, B, 3)).abs()
+    hit = ru(N) < base_contact_frac
+    tb = list(cfg.termination_contact_indices)
+    cf[:, tb, :] = torch.where(hit[:, None, None], cf[:, tb, :], 0.05 * rn(N, len(tb), 3))
+    rigid = 0.3 * rn(N, B, 13)
+    rigid[:, list(cfg.feet_indices), 2] = 0.15 * ru(N, 2)
+    return dict(root_states=root, dof_state=0.2 * rn(N * D, 2), contact_forces=cf.contiguous(),
+                rigid_state=rigid.contiguous(), commands=0.3 * rn(N, 4), torques=10.0 * rn(N, D),
+                rand_push_force=0.2 * rn(N, 3), rand_push_torque=0.4 * rn(N, 3),
+                env_frictions=0.1 + 1.9 * ru(N, 1), body_mass=20.0 + 10.0 * ru(N, 1))
+
+
+class SyntheticXBotEnv:
+    """`VecEnv`-shaped (reference humanoid/algo/vec_env.py:39-63) synthetic environment: the PhysX step is
+    replaced by cycling through a pool of pre-generated Isaac-Gym-shaped state tensors; everything after it
+    (the hot path) is the fused kernel.  Drives `OnPolicyRunner`-style loops in bench.py and the tests."""
+
+    def __init__(self, cfg: XBotMathConfig, device, pool: int = 4, seed: int = 0, torch_rng_noise: bool = True):
+        self.cfg, self.device = cfg, torch.device(device)
+        self.math = XBotEnvMath(cfg, device)
+        self.num_envs = cfg.num_envs
+        self.num_obs = cfg.num_observations
+        self.num_privileged_obs = cfg.num_privileged_obs
+        self.num_actions = cfg.num_dof
+        self.max_episode_length = self.math.max_episode_length
+        gen = torch.Generator(device=self.device).manual_seed(seed)
+        self.pool = [synthetic_sim_state(cfg, gen, self.device, upright=(i % 2 == 0)) for i in range(pool)]
+        self.math.episode_length_buf.copy_(torch.randint(0, self.max_episode_length, (self.num_envs,), generator=gen,
+                                                         device=self.device))
+        self.torch_rng_noise = torch_rng_noise
+        self.extras = {}
+        self._i = 0
+        self.obs_buf, self.privileged_obs_buf = self.math.obs_buf, self.math.privileged_obs_buf
+        self.rew_buf, self.reset_buf = self.math.rew_buf, self.math.reset_buf
+        self.episode_length_buf = self.math.episode_length_buf
+
+    def set_host_pool(self, host_pool):
+        """Optional: pinned-host copies of the state pool, for end-to-end timing with H2D copies per step."""
+        self._host_pool = host_pool
+
+    def get_observations(self):
+        return self.obs_buf
+
+    def get_privileged_observations(self):
+        return self.privileged_obs_buf
+
+    def reset(self):
+        return self.obs_buf, self.privileged_obs_buf
+
+    def step(self, actions):
+        sim = self.pool[self._i % len(self.pool)]
+        self._i += 1
+        clip = 18.0
+        torch.clamp(actions, -clip, clip, out=self.math.actions)    # stand-in for the pre-physics action path (:624-635)
+        noise = torch.randn(self.num_envs, self.cfg.num_single_obs, device=self.device) if (
+            self.torch_rng_noise and self.cfg.add_noise) else None
+        self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, to = self.math.step(sim, noise)
+        self.extras["time_outs"] = to
+        return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras

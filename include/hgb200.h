@@ -1,0 +1,289 @@
+/* hgb200.h -- C ABI of libhgb200.so: the B200 (sm_100a) kernels of humanoid-gym's PPO hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer unless the
+ * name ends in _host.  `stream` is a cudaStream_t passed as void*.  Every function returns
+ * HG_OK (0) or a negative HG_ERR_* code; hg_last_error() returns the text.  There is no CPU
+ * fallback anywhere: a call that cannot run on the GPU fails.
+ *
+ * Each entry point names the reference code it replaces (paths relative to the reference root,
+ * Rengar-Yang/humanoid-gym-with-comments).
+ */
+#ifndef HGB200_H_
+#define HGB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_OK 0
+#define HG_ERR_INVALID (-1)
+#define HG_ERR_CUDA (-2)
+
+#define HG_ABI_VERSION 1
+
+const char* hg_last_error(void);
+int hg_abi_version(void);
+/* Number of kernel launches issued through this library since load (bench.py's gpu_launches). */
+int64_t hg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense contractions: grouped bf16 GEMM on tcgen05 tensor cores (TMA loads, TMEM accumulators).
+ * Replaces every nn.Linear forward/backward of the three MLPs (humanoid/algo/ppo/actor_critic.py:
+ * 62,76,89 via torch autograd) and the ELU forward/backward between them (:44).
+ *
+ *   C[M,N] = A[M,K] * B[N,K]^T      fp32 accumulate
+ *
+ * A is row-major [M,lda] ("K-major") or, with a_mn_major=1, stored as [K,lda] with M contiguous.
+ * Same for B with N.  Leading dimensions are in elements and must be multiples of 8 (16 bytes).
+ * Up to HG_MAX_GROUP independent problems run in ONE launch (actor / critic / lin-vel layers).
+ */
+#define HG_MAX_GROUP 4
+
+enum HgEpilogue {
+  HG_EPI_STORE_F32 = 0,     /* out f32 [M,ldo] = acc (+ bias[n] if bias)                              */
+  HG_EPI_BIAS_ELU_BF16 = 1, /* out bf16 [M,ldo] = elu(acc + bias[n])        (Linear+ELU forward)      */
+  HG_EPI_DELU_BF16 = 2,     /* out bf16 [M,ldo] = acc * elu'(act[m,n]); colsum[n] += column sums      */
+                            /*   (dX of a Linear, times ELU' of the layer below, + its bias gradient) */
+  HG_EPI_ATOMIC_F32 = 3,    /* out f32 [M,ldo] += acc   (split-K weight gradient)                     */
+  HG_EPI_BIAS_BF16 = 4      /* out bf16 [M,ldo] = acc + bias[n]                                       */
+};
+
+typedef struct HgGemmProblem {
+  const void* A;   /* bf16 */
+  const void* B;   /* bf16 */
+  int64_t lda, ldb;
+  int32_t a_mn_major, b_mn_major;
+  int32_t M, N, K;
+  int32_t k_splits; /* >=1; >1 only with HG_EPI_ATOMIC_F32 */
+  void* out;
+  int64_t ldo;
+  const float* bias;  /* [N] or NULL */
+  const void* act;    /* bf16 [M,ldact] (HG_EPI_DELU_BF16) */
+  int64_t ldact;
+  float* colsum;      /* [N] or NULL (HG_EPI_DELU_BF16) */
+} HgGemmProblem;
+
+/* block_n: 128 or 256 (UMMA N of one accumulator tile). */
+int hg_gemm_grouped(const HgGemmProblem* problems_host, int num_problems, int epilogue, int block_n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GAE: replaces RolloutStorage.compute_returns (humanoid/algo/ppo/rollout_storage.py:122-143).
+ * rewards/values/returns/advantages are [T,N] fp32, dones [T,N] uint8, last_values [N].
+ * One reverse-time scan per env, then mean / unbiased std over all T*N and normalisation.
+ * scratch: 4 doubles (zeroed by the call).  Bit-exact with the reference's fp32 op order for
+ * `returns`; advantages agree to fp32 rounding of the mean/std reduction.
+ */
+int hg_gae_returns(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                   float gamma, float lam, int T, int N, float* returns, float* advantages, double* scratch,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Rollout-side learner glue.
+ */
+/* obs ingest: replaces the two big copy_ of RolloutStorage.add_transitions (rollout_storage.py:90-91)
+ * and produces the bf16, 16-byte-row-aligned shadow the tensor-core layers read.
+ * src f32 [rows, src_ld] -> dst_f32 [rows, dst_ld] (may be NULL) and dst_bf16 [rows, ld16] with the
+ * columns [cols, ld16) zero-filled. */
+int hg_ingest_rows(const float* src, int64_t src_ld, int rows, int cols, float* dst_f32, int64_t dst_ld,
+                   void* dst_bf16, int64_t ld16, void* stream);
+
+/* Minibatch gather (rollout_storage.py:176-181): dst[r,:] = src[idx[r],:] for bf16 rows of `ld` elements. */
+int hg_gather_rows_bf16(const void* src, int64_t ld, const int64_t* idx, int rows, void* dst, void* stream);
+
+/* Output layers of actor and critic + Gaussian sampling + log-prob for one rollout step.
+ * Replaces ActorCritic.act / evaluate / get_actions_log_prob as used by PPO.act
+ * (actor_critic.py:127-138,144-146; ppo.py:116-126) for the last Linear of each net.
+ *   h_actor  bf16 [n, ld_ha] (last hidden activations, width H_a), W_a f32 [A,H_a], b_a [A], std [A]
+ *   h_critic bf16 [n, ld_hc], W_c f32 [1,H_c], b_c [1]
+ *   eps f32 [n,A] ~ N(0,1) or NULL (then Philox4x32-10 keyed by (seed, counter, row) is used)
+ * outputs (all f32): actions [n,A] = mu + std*eps, mu [n,A], sigma [n,A], log_prob [n], values [n]. */
+int hg_policy_head_rollout(const void* h_actor, int64_t ld_ha, int H_a, const float* W_a, const float* b_a,
+                           const float* std, const void* h_critic, int64_t ld_hc, int H_c, const float* W_c,
+                           const float* b_c, const float* eps, uint64_t seed, uint64_t counter, int n, int A,
+                           float* actions, float* mu, float* sigma, float* log_prob, float* values, void* stream);
+
+/* Value-only head (PPO.compute_returns' critic pass on the last observation, ppo.py:140-141). */
+int hg_value_head(const void* h_critic, int64_t ld_hc, int H_c, const float* W_c, const float* b_c, int n,
+                  float* values, void* stream);
+
+/* Generic fp32 output layer: out[n, n_out] = h[n,:H] * W[n_out,H]^T + b (ActorCritic.act_inference / evaluate /
+ * base_get_lin_vel, actor_critic.py:140-148, for callers outside the fused PPO paths). */
+int hg_head_forward(const void* h, int64_t ld_h, int H, const float* W, const float* b, int n_out, int n,
+                    float* out, void* stream);
+
+/* rewards + gamma * values * time_outs and the uint8 dones (ppo.py:129-133, rollout_storage.py:93-94). */
+int hg_store_rewards_dones(const float* rewards, const float* values, const uint8_t* time_outs,
+                           const uint8_t* dones, float gamma, int n, float* out_rewards, uint8_t* out_dones,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Update-side: output layers + all PPO losses + their gradients, one launch per minibatch.
+ * Replaces ppo.py:154-208 (log-prob, KL, ratio, clipped surrogate, clipped value loss, entropy bonus,
+ * lin-vel MSE) and the autograd backward of the three output Linear layers and of the ELU below them.
+ */
+typedef struct HgHeadNet {
+  const void* h;     /* bf16 [rows, ld_h]: last hidden activations of this net for the minibatch */
+  int64_t ld_h;
+  int32_t H;         /* hidden width (<=256, multiple of 32) */
+  int32_t n_out;     /* 12 / 1 / 3 */
+  const float* W;    /* f32 [n_out, H] */
+  const float* b;    /* f32 [n_out] */
+  float* gW;         /* f32 [n_out, H], accumulated atomically */
+  float* gb;         /* f32 [n_out] */
+  void* dZ;          /* bf16 [rows, ld_dz]: dLoss/d(pre-activation of the last hidden layer) */
+  int64_t ld_dz;
+  float* gb_hidden;  /* f32 [H]: bias gradient of the last hidden layer (column sums of dZ) */
+} HgHeadNet;
+
+typedef struct HgLossArgs {
+  HgHeadNet actor, critic, linvel;
+  int32_t rows;            /* minibatch size */
+  int32_t A;               /* num actions */
+  const int64_t* idx;      /* [rows] flat row indices t*N+n into the storage tensors below */
+  const float* actions;    /* [TN, A] */
+  const float* old_mu;     /* [TN, A] */
+  const float* old_sigma;  /* [TN, A] */
+  const float* old_log_prob; /* [TN] */
+  const float* advantages; /* [TN] */
+  const float* returns;    /* [TN] */
+  const float* old_values; /* [TN] */
+  const float* critic_obs; /* f32 [TN, ld_cobs] : lin-vel target = cols [lv_col, lv_col+3) (rollout_storage.py:164) */
+  int64_t ld_cobs;
+  int32_t lv_col;
+  const float* std;        /* [A] */
+  float* g_std;            /* [A] */
+  float clip_param, value_loss_coef, entropy_coef, lin_vel_coef;
+  int32_t use_clipped_value_loss;
+  float inv_world;         /* 1/world_size: gradients are pre-scaled so that a SUM all-reduce yields the global mean */
+  /* stats[0..4] += {sum value-loss terms, sum surrogate terms, sum lin-vel sq err, sum kl, sum entropy} over the
+   * minibatch rows (fp32, one atomic per 64-row block).  Lives in the 8 floats that FOLLOW the gradient arena so
+   * that the single gradient all-reduce also reduces the KL (every rank derives the same learning rate). */
+  float* stats;
+} HgLossArgs;
+
+int hg_ppo_head_loss(const HgLossArgs* args_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser: replaces nn.utils.clip_grad_norm_ + torch.optim.Adam.step + the adaptive-KL learning
+ * rate (ppo.py:162-174, 211-214) on flat fp32 arenas, with no host synchronisation.
+ *   grads: [count + HG_STATS_SLOTS] floats; grads[count + j] are the loss statistics of hg_ppo_head_loss.
+ *   opt_state (device, 8 doubles): [0] lr  [1] step  [2] grad sum-sq (scratch, must start at 0)
+ *                                  [3] clip coef  [4] step size lr/(1-b1^t)  [5] sqrt(1-b2^t)  [6] grad norm
+ *   loss_log[log_slot*8 + {0..7}] = {value loss, surrogate loss, lin-vel loss, kl, entropy, lr, grad norm, clip coef}
+ *   (means over rows_global rows) -- read back by the host once per update.
+ */
+#define HG_STATS_SLOTS 8
+#define HG_MAX_SHADOWS 16
+typedef struct HgBf16Shadow {   /* refresh of one bf16 weight copy after the step */
+  int64_t param_offset;         /* offset of the [rows, cols] fp32 weight in the arena */
+  int32_t rows, cols;
+  void* dst;                    /* bf16 [rows, ld] */
+  int64_t ld;
+} HgBf16Shadow;
+
+typedef struct HgAdamArgs {
+  float* params; float* grads; float* exp_avg; float* exp_avg_sq;
+  int64_t count;
+  double* opt_state;
+  double* loss_log; int32_t log_slot;
+  int64_t rows_global;          /* rows in the minibatch over all ranks (kl / loss means) */
+  float beta1, beta2, eps, max_grad_norm;
+  int32_t adaptive; float desired_kl; float lr_min, lr_max;
+  const HgBf16Shadow* shadows_host; int32_t num_shadows;
+  int32_t zero_grads;           /* clear the gradient arena after the step */
+} HgAdamArgs;
+
+int hg_clip_adam_step(const HgAdamArgs* args_host, void* stream);
+
+/* fp32 [rows, cols] (row stride cols) -> bf16 [rows, ld], zero pad; used once at start-up. */
+int hg_cast_weight_bf16(const float* src, int rows, int cols, void* dst, int64_t ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Env tensor math: one fused launch per env step.  Replaces, in humanoid/envs/custom/humanoid_env.py,
+ * post_physics_step's tensor work (:780-806): base-frame quantities (:784-788), check_termination
+ * (:811-816), compute_reward with the 22 active _reward_* terms (:889-907,:1170-1437), the buffer and
+ * history zeroing of reset_idx (:1132-1139,:1160-1163), compute_observations incl. compute_ref_state,
+ * noise and the 15/3-frame history stacks (:717-744,:818-887), the state hand-over (:802-806) and the
+ * +-18 clips of step (:654-657).
+ */
+#define HG_NUM_REWARDS 22
+/* alphabetical order of the active reward terms (utils/helpers.py:43-58 walks dir()) */
+enum HgReward {
+  HG_R_ACTION_SMOOTHNESS = 0, HG_R_BASE_ACC, HG_R_BASE_HEIGHT, HG_R_COLLISION, HG_R_DEFAULT_JOINT_POS,
+  HG_R_DOF_ACC, HG_R_DOF_VEL, HG_R_FEET_AIR_TIME, HG_R_FEET_CLEARANCE, HG_R_FEET_CONTACT_FORCES,
+  HG_R_FEET_CONTACT_NUMBER, HG_R_FEET_DISTANCE, HG_R_FOOT_SLIP, HG_R_JOINT_POS, HG_R_KNEE_DISTANCE,
+  HG_R_LOW_SPEED, HG_R_ORIENTATION, HG_R_TORQUES, HG_R_TRACK_VEL_HARD, HG_R_TRACKING_ANG_VEL,
+  HG_R_TRACKING_LIN_VEL, HG_R_VEL_MISMATCH_EXP
+};
+
+typedef struct HgEnvConfig {
+  int32_t num_envs, D, leg_offset, num_bodies;
+  int32_t feet[2], knees[2];
+  int32_t num_term_bodies, term_bodies[4];
+  int32_t num_pen_bodies, pen_bodies[4];
+  int32_t frame_stack, c_frame_stack;
+  float dt, cycle_time, max_episode_length;
+  float target_joint_pos_scale, base_height_target, min_dist, max_dist, target_feet_height;
+  float tracking_sigma, max_contact_force;
+  int32_t only_positive_rewards;
+  float lin_vel_scale, ang_vel_scale, dof_pos_scale, dof_vel_scale, quat_scale;
+  float clip_obs, noise_level;
+  float reward_scale_dt[HG_NUM_REWARDS]; /* scale*dt per term; 0 disables the term */
+  int32_t phase_mul_reciprocal;  /* 0: phase = len*dt/cycle (torch-CPU semantics); 1: len*dt*(1/cycle) (torch-CUDA) */
+  /* HG_ENV_PHASE_REWARD: episode_length += 1, termination, rewards (what precedes reset_idx in post_physics_step);
+   * HG_ENV_PHASE_OBS: buffer/history zeroing of reset envs, observations, history, hand-over (what follows it).
+   * A real Isaac Gym env launches the two separately around its gym reset calls; synthetic loops pass both. */
+  int32_t phases;
+} HgEnvConfig;
+#define HG_ENV_PHASE_REWARD 1
+#define HG_ENV_PHASE_OBS 2
+#define HG_ENV_PHASE_ALL 3
+
+typedef struct HgEnvBuffers {
+  /* Isaac-Gym-shaped inputs */
+  const float* root_states;     /* [N,13] */
+  const float* dof_state;       /* [N*D,2] interleaved pos,vel */
+  const float* contact_forces;  /* [N,B,3] */
+  const float* rigid_state;     /* [N,B,13] */
+  const float* commands;        /* [N,4] */
+  const float* torques;         /* [N,D] */
+  const float* rand_push_force; /* [N,3] */
+  const float* rand_push_torque;/* [N,3] */
+  const float* env_frictions;   /* [N] */
+  const float* body_mass;       /* [N] */
+  const float* default_dof_pos; /* [D] */
+  const float* noise_scale_vec; /* [So] */
+  const float* noise;           /* [N,So] N(0,1) draws, or NULL -> Philox(seed, counter) */
+  uint64_t seed, counter;
+  /* persistent state, updated in place */
+  float* actions;               /* [N,D] in: this step's applied actions; zeroed on reset */
+  float* last_actions; float* last_last_actions;   /* [N,D] */
+  float* last_dof_vel;          /* [N,D] */
+  float* last_root_vel;         /* [N,6] */
+  float* feet_air_time;         /* [N,2] */
+  uint8_t* last_contacts;       /* [N,2] */
+  float* feet_height;           /* [N,2] */
+  float* last_feet_z;           /* [N,2] */
+  float* ref_dof_pos;           /* [N,D] */
+  int64_t* episode_length_buf;  /* [N] */
+  float* episode_sums;          /* [HG_NUM_REWARDS, N] */
+  /* history in / out: stacked frames oldest->newest; prev and next may NOT alias */
+  const float* obs_prev; int64_t obs_prev_ld;   /* [N, F*So] */
+  const float* priv_prev; int64_t priv_prev_ld; /* [N, Fc*Sp] */
+  float* obs_next; int64_t obs_next_ld;
+  float* priv_next; int64_t priv_next_ld;
+  /* outputs */
+  float* rew_buf;               /* [N] */
+  uint8_t* reset_buf;           /* [N] */
+  uint8_t* time_out_buf;        /* [N] */
+  float* reward_terms;          /* [HG_NUM_REWARDS, N] or NULL (debug/parity) */
+} HgEnvBuffers;
+
+int hg_env_step(const HgEnvConfig* cfg_host, const HgEnvBuffers* buf_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGB200_H_ */

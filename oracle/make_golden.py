@@ -39,7 +39,7 @@ XBOT_NETS = dict(actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256
 
 
 def _np(t):
-    return t.detach().cpu().numpy()
+    return t.detach().cpu().numpy().copy()
 
 
 def _ref_alg(N, T, seed):

