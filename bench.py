@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- PPO env-steps/s (rollout + update, device-timed) of the B200-native hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs 4096] [--horizon 60]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one PPO iteration of BASELINE.json configs[1] (XBot-L humanoid_ppo defaults: 4096 envs x 60 steps per GPU,
+actor [512,256,128] / critic [768,256,128] / lin-vel [128,128], 2 epochs x 4 minibatches): 60 x (fused env step + act +
+process_env_step) + compute_returns + update, driven through the reference-facing PPO / VecEnv API exactly as
+OnPolicyRunner.learn does (on_policy_runner.py:125-168).  Isaac Gym's PhysX step is replaced by synthetic
+Isaac-Gym-shaped state tensors.  One JSON line is printed by rank 0.
+
+  value  : whole-job env-steps/s with the synthetic state already resident in HBM
+  e2e    : same loop, but every env step first copies that step's state tensors host(pinned)->device and every
+           iteration reads its losses + mean reward back to the host
+  roofline: the grouped tcgen05 GEMM launches (the dominant kernel), algorithmic FLOPs / CUDA-event time, against the
+           measured bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline: the oracle port (torch CPU fp32, all host threads) on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ppo_env_steps_per_sec"
+UNIT = "env-steps/s"
+NETS = dict(actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128])
+FALLBACK_BF16_TFLOPS = 1400.0     # B200_PROFILING.md fallback (sustained)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--horizon", type=int, default=60)
+    ap.add_argument("--cpu-sample-envs", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fast-rng", action="store_true", help="in-kernel Philox instead of torch.randn (loses seed parity)")
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {"workload": f"XBot-L humanoid_ppo: {a.envs} envs/GPU x {a.horizon} steps, obs 705 / priv 219 / 12 actions, "
+                        f"actor [512,256,128] critic [768,256,128] lin-vel [128,128], 2 epochs x 4 minibatches "
+                        f"(BASELINE.json configs[1]); synthetic Isaac-Gym-shaped state, fused env step in the loop",
+            "envs_per_gpu": a.envs, "horizon": a.horizon, "parallelism": f"env-sharded dp{world}",
+            "l2_policy": "per-iteration working set (storage 0.95 GB fp32 + 0.46 GB bf16) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_baseline(a, seconds_budget=20.0, iters=None):
+    """The reference algorithm (oracle restatement: torch CPU fp32, autograd backward, all host threads) on a bounded
+    sample: `cpu_sample_envs` envs x horizon steps, same nets / hyper-parameters / env math.  Returns env-steps/s."""
+    import torch
+    from oracle import env_oracle as eo
+    from oracle import ppo_oracle as po
+    torch.set_num_threads(os.cpu_count() or 1)
+    N, T = a.cpu_sample_envs, a.horizon
+    cfg = po.xbot_ppo_config()
+    torch.manual_seed(0)
+    p = po.init_params(705, 219, 12, (512, 256, 128), (768, 256, 128), (128, 128), 1.0)
+    spec = eo.xbot_spec(12)
+    est = eo.EnvState(spec, N)
+    g = torch.Generator().manual_seed(0)
+    pool = [eo.synthetic_sim_state(spec, N, g) for _ in range(4)]
+    st, lr = po.AdamState(), cfg.learning_rate
+    out = eo.env_step(spec, est, pool[0], torch.randn(N, spec.So, generator=g))
+    obs, priv = out["obs"], out["priv"]
+
+    def iteration(i):
+        nonlocal obs, priv, lr
+        z = torch.zeros
+        ro = po.Rollout(z(T, N, 705), z(T, N, 219), z(T, N, 12), z(T, N, 1), z(T, N, 1, dtype=torch.uint8), z(T, N, 1),
+                        z(T, N, 1), z(T, N, 12), z(T, N, 12))
+        with torch.no_grad():
+            for t in range(T):
+                m = po.policy_mean(p, obs)
+                act = po.sample_actions(m, p["std"], torch.randn(N, 12))
+                v = po.value(p, priv)
+                ro.observations[t], ro.privileged_observations[t], ro.actions[t], ro.values[t] = obs, priv, act, v
+                ro.actions_log_prob[t] = po.log_prob(m, p["std"], act).view(-1, 1)
+                ro.mu[t], ro.sigma[t] = m, m * 0 + p["std"]
+                sim = dict(pool[(i * T + t) % len(pool)])
+                sim["actions"] = act.clip(-18, 18)
+                out = eo.env_step(spec, est, sim, torch.randn(N, spec.So))
+                obs, priv = out["obs"], out["priv"]
+                ro.rewards[t] = po.bootstrap_rewards(out["rew"], v, out["time_out"], cfg.gamma).view(-1, 1)
+                ro.dones[t] = out["reset"].view(-1, 1)
+            ro.returns, ro.advantages = po.gae_returns(ro.rewards, ro.values, ro.dones, po.value(p, priv), cfg.gamma, cfg.lam)
+        _, _, _, lr = po.ppo_update(p, st, ro, torch.randperm(N * T), cfg, lr)
+
+    iteration(0)                                   # warm-up
+    times = []
+    t_end = time.perf_counter() + seconds_budget
+    i = 1
+    while (iters is None and time.perf_counter() < t_end and len(times) < 50) or (iters is not None and len(times) < iters):
+        t0 = time.perf_counter()
+        iteration(i)
+        times.append(time.perf_counter() - t0)
+        i += 1
+    med = statistics.median(times)
+    return {"value": N * T / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{N} envs x {T} steps per iteration (env math + rollout + GAE + update), median of {len(times)} "
+                      f"iterations after 1 warm-up, {med * 1e3:.0f} ms/iteration; oracle = torch-CPU fp32 restatement of the "
+                      f"reference pinned bit-exact to it (the reference itself is Python and is not present on this box)"}, med
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    base, med = cpu_baseline(a, iters=max(1, a.steps) + 0, seconds_budget=1e9) if a.steps <= 20 else cpu_baseline(a, 60.0)
+    line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a, world), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ ours
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from humanoid_gym_with_comments_b200 import _lib
+    from humanoid_gym_with_comments_b200.algo.ppo import PPO, ActorCritic
+    from humanoid_gym_with_comments_b200.algo.ppo import engine as eng_mod
+    from humanoid_gym_with_comments_b200.envs import SyntheticXBotEnv, XBotMathConfig
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    lib = _lib.load()
+    N, T = a.envs, a.horizon
+
+    torch.manual_seed(0)                         # identical initial weights on every rank
+    with contextlib.redirect_stdout(io.StringIO()):
+        ac = ActorCritic(705, 219, 12, init_noise_std=1.0, **NETS)
+    alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0.994, lam=0.9, value_loss_coef=1.0,
+              entropy_coef=0.001, learning_rate=1e-5, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
+              desired_kl=0.01, device=dev)
+    alg.init_storage(N, T, [705], [219], [12])
+    alg.torch_rng = not a.fast_rng
+    torch.manual_seed(1000 + rank)               # per-rank env / sampling streams
+    env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, pool=4, seed=rank, torch_rng_noise=not a.fast_rng)
+    obs, critic_obs = env.get_observations(), env.get_privileged_observations()
+    state = {"obs": obs, "critic_obs": critic_obs}
+    host_pool = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in env.pool]
+    h2d_bytes_per_env_step = sum(v.numel() * v.element_size() for v in host_pool[0].values())
+    rew_acc = torch.zeros((), device=dev)
+
+    def iteration(e2e: bool):
+        obs, critic_obs = state["obs"], state["critic_obs"]
+        with torch.inference_mode():
+            for i in range(T):
+                actions = alg.act(obs, critic_obs)
+                if e2e:       # this step's Isaac-Gym-shaped state arrives from the host
+                    slot = env._i % len(env.pool)
+                    for k, v in host_pool[slot].items():
+                        env.pool[slot][k].copy_(v, non_blocking=True)
+                obs, privileged_obs, rewards, dones, infos = env.step(actions)
+                critic_obs = privileged_obs if privileged_obs is not None else obs
+                alg.process_env_step(rewards, dones, infos)
+                if e2e:
+                    rew_acc.add_(rewards.mean())
+            alg.compute_returns(critic_obs)
+        losses = alg.update()                    # reads the loss log back (D2H) once per iteration
+        state["obs"], state["critic_obs"] = obs, critic_obs
+        if e2e:
+            return losses, float(rew_acc.item())
+        return losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(k, e2e):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.hg_launch_count()
+        ev0.record()
+        for _ in range(k):
+            iteration(e2e)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, lib.hg_launch_count() - l0
+
+    for _ in range(max(3, a.warmup)):
+        iteration(False)
+    with ClockSampler(local) as clocks:
+        ms, launches = timed(a.steps, False)
+    value = N * T * world * a.steps / (ms / 1e3)
+    e2e = None
+    if not a.no_e2e:
+        iteration(True)
+        ms_e, _ = timed(a.steps, True)
+        e2e = {"value": N * T * world * a.steps / (ms_e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d_bytes_per_env_step * T, "d2h_bytes_per_step": 8 * 8 * 8 + 4,
+               "ms_per_step": ms_e / a.steps}
+
+    # ---- roofline of the dominant kernel: every grouped tcgen05 GEMM launch of one more iteration, CUDA-event timed
+    records = []
+    orig = eng_mod.MLPEngine._launch
+
+    def probe(self, problems, epi, block_n):
+        fl = sum(2.0 * p.M * p.N * p.K for p in problems)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(self, problems, epi, block_n)
+        e1.record()
+        records.append((epi, block_n, fl, e0, e1, [(p.M, p.N, p.K) for p in problems]))
+
+    eng_mod.MLPEngine._launch = probe
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    iteration(False)
+    ev1.record()
+    torch.cuda.synchronize()
+    eng_mod.MLPEngine._launch = orig
+    iter_ms = ev0.elapsed_time(ev1)
+    by_kind = {}
+    for epi, bn, fl, e0, e1, shapes in records:
+        big = shapes[0][0] >= 8192 or shapes[0][2] >= 8192
+        key = f"{['store','fwd_bias_elu','dx_delu','dw_atomic','bias'][epi]}_bn{bn}_{'update' if big else 'rollout'}"
+        d = by_kind.setdefault(key, {"launches": 0, "ms": 0.0, "flop": 0.0})
+        d["launches"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flop"] += fl
+    upd = {k: v for k, v in by_kind.items() if k.endswith("update")}
+    g_ms = sum(v["ms"] for v in upd.values())
+    g_fl = sum(v["flop"] for v in upd.values())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_BF16_TFLOPS))
+    achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "hg::gemm_kernel (grouped tcgen05 GEMM; update-phase launches)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+                "traffic": None, "launches": sum(v["launches"] for v in upd.values()), "kernel_ms_per_iteration": g_ms,
+                "share_of_iteration": g_ms / iter_ms if iter_ms else None,
+                "by_kind": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
+                                "tflops": round(v["flop"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else None}
+                            for k, v in sorted(by_kind.items())}}
+
+    base = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        base, _ = cpu_baseline(a)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 tensor-core GEMMs with fp32 accumulate; fp32 elsewhere", "data": "synthetic",
+                "config": workload_config(a, world), "clocks": clocks.summary(), "e2e": e2e,
+                "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
+                "roofline": roofline, "cpu_baseline": base}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,7 @@ def learner_case(N, T, seed, n_updates, store_inputs):
     for u in range(n_updates):
         gen = torch.Generator().manual_seed(1000 * seed + 17 + u)
         gen_state = gen.get_state()
+        p_start = {k: v.clone() for k, v in p.items()}
         ro, last_c, inputs = po.synthetic_rollout(p, N, T, 705, 219, 12, cfg, gen, record_inputs=True)
         # replay the same stream through the reference (ppo.py:116-142)
         with torch.inference_mode():
@@ -145,6 +146,7 @@ def learner_case(N, T, seed, n_updates, store_inputs):
                          "actions_log_prob", "mu", "sigma"):
                 out[pre + name] = _np(getattr(ro, name))
             out[pre + "last_critic_obs"] = _np(last_c)
+            out[pre + "last_values"] = _np(po.value(p_start, last_c))
             out[pre + "eps"] = _np(torch.stack([i["eps"] for i in inputs]))
             out[pre + "raw_rewards"] = _np(torch.stack([i["rew"] for i in inputs]))
             out[pre + "env_dones"] = _np(torch.stack([i["dones"] for i in inputs]))

@@ -43,10 +43,7 @@ def test_gae_golden_fixture(golden_dir):
     z = np.load(f"{golden_dir}/learner_small.npz")
     rew, val = torch.tensor(z["u0.rewards"]), torch.tensor(z["u0.values"])
     dones = torch.tensor(z["u0.dones"])
-    # last values are not in the fixture: recover them through the oracle from the stored critic obs + seed-0 weights
-    torch.manual_seed(0)
-    p = po.init_params(705, 219, 12, (512, 256, 128), (768, 256, 128), (128, 128), 1.0)
-    last = po.value(p, torch.tensor(z["u0.last_critic_obs"])).detach()
+    last = torch.tensor(z["u0.last_values"])
     ret, adv = run_gae(rew, val, dones, last, 0.994, 0.9)
     assert torch.equal(ret, torch.tensor(z["u0.returns"]))
     assert torch.allclose(adv, torch.tensor(z["u0.advantages"]), rtol=1e-5, atol=2e-6)
