@@ -142,8 +142,13 @@ class MLPEngine:
 
     # -- helpers ----------------------------------------------------------------------------
     @staticmethod
-    def _block_n(ns: Sequence[int]) -> int:
-        return 256 if min(ns) >= 256 else 128
+    def _block_n(ns: Sequence[int], kind: str = "fwd") -> int:
+        """UMMA N of the accumulator tile, from tools/bench_gemm.py on B200: 256-wide tiles win whenever some
+        problem of the group is at least 256 wide (less shared-memory traffic per MMA), except for the dX launches
+        whose K is tiny and whose epilogue (ELU' + column sums) is the bound."""
+        if kind == "dx":
+            return 128
+        return 256 if max(ns) >= 256 else 128
 
     def _launch(self, problems: List[HgGemmProblem], epi: int, block_n: int) -> None:
         arr = (HgGemmProblem * len(problems))(*problems)
@@ -207,11 +212,11 @@ class MLPEngine:
                         bias=0, act=ptr(below), ldact=below.stride(0), colsum=ptr(gb)))
                     dx_n.append(k_in)
             if dw:
-                bn = self._block_n(dw_n)
+                bn = self._block_n(dw_n, "dw")
                 tiles = sum(((p.M + 127) // 128) * ((p.N + bn - 1) // bn) for p in dw)
-                splits = max(1, min((rows + 63) // 64, (2 * self.num_sms) // max(tiles, 1)))
+                splits = max(1, min((rows + 63) // 64, self.num_sms // max(tiles, 1)))
                 for p in dw:
                     p.k_splits = splits
                 self._launch(dw, EPI_ATOMIC_F32, bn)
             if dx:
-                self._launch(dx, EPI_DELU_BF16, self._block_n(dx_n))
+                self._launch(dx, EPI_DELU_BF16, self._block_n(dx_n, "dx"))

@@ -2,12 +2,13 @@
 //
 //   C[M,N] = A[M,K] * B[N,K]^T   (fp32 accumulate), up to HG_MAX_GROUP problems per launch.
 //
-// One persistent CTA per SM, 8 warps:
-//   warp 0    TMA producer (one lane): cp.async.bulk.tensor 2D boxes -> SWIZZLE_128B smem ring
-//   warp 1    MMA issuer  (one lane): tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16 per instruction
-//   warp 2    TMEM allocator (2*BLOCK_N columns: two accumulator buffers so the epilogue of tile i
-//             overlaps the main loop of tile i+1)
-//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+// One persistent CTA per SM, 12 warps:
+//   warp 0     TMA producer (one lane): cp.async.bulk.tensor 2D boxes -> SWIZZLE_128B smem ring
+//   warp 1     MMA issuer  (one lane): tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16 per instruction
+//   warp 2     TMEM allocator (2*BLOCK_N columns: two accumulator buffers so the epilogue of tile i
+//              overlaps the main loop of tile i+1)
+//   warps 4-11 epilogue (two per scheduler so they hide each other's latency): warp w reads TMEM lanes
+//              32*(w%4).. and the column half (w-4)/4 with tcgen05.ld 32x32b -> registers -> fused epilogue -> global
 //
 // Operands may be K-major (row-major [rows,K]) or MN-major (row-major [K,rows]); the latter lets the
 // backward GEMMs (dX = dZ*W, dW = dZ^T*H) read the same row-major activations / weights as the forward
@@ -26,7 +27,9 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int SMEM_RING_BYTES = 192 * 1024;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int EPI_TILE_FLOATS = 32 * 33;      // per-warp transpose tile of the split-K epilogue
 constexpr int MN_ATOM_BYTES = BLOCK_K * 128;  // 8192: one [64 x 64] bf16 atom
 
 struct DevProblem {
@@ -99,8 +102,14 @@ __device__ __forceinline__ float warp_colsum32(float (&d)[32], int lane) {
   return d[0];
 }
 
+__device__ __forceinline__ float exp2f_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int n0, uint32_t (&v)[32], int lane) {
+__device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int n0, uint32_t (&v)[32], int lane, float* tile) {
   const bool row_ok = row < q.M;
   const bool full = (n0 + 32 <= q.N);
   if constexpr (EPI == HG_EPI_STORE_F32) {
@@ -111,20 +120,37 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
         if (n0 + j < q.N) o[j] = __uint_as_float(v[j]) + (q.bias ? __ldg(q.bias + n0 + j) : 0.f);
     }
   } else if constexpr (EPI == HG_EPI_ATOMIC_F32) {
-    float* o = reinterpret_cast<float*>(q.out) + (long long)row * q.ldo + n0;
-    if (row_ok) {
+    // Transpose the warp's 32x32 chunk through shared memory so that every RED instruction adds 32 CONSECUTIVE
+    // floats of one output row (1-2 L2 lines per instruction instead of 32).
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < q.N) atomicAdd(o + j, __uint_as_float(v[j]));
+    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+    __syncwarp();
+    const int row_base = row - lane;
+    const bool col_ok = n0 + lane < q.N;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      if (col_ok && row_base + i < q.M)
+        atomicAdd(reinterpret_cast<float*>(q.out) + (long long)(row_base + i) * q.ldo + n0 + lane, tile[i * 33 + lane]);
     }
+    __syncwarp();
   } else if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(q.out) + (long long)row * q.ldo + n0;
-    float z[32];
+    float z[32], bv[32];
+    if (q.bias && full && ((reinterpret_cast<uintptr_t>(q.bias) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(q.bias + n0 + j));
+        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bv[j] = (q.bias && n0 + j < q.N) ? __ldg(q.bias + n0 + j) : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float b = (q.bias && n0 + j < q.N) ? __ldg(q.bias + n0 + j) : 0.f;
-      float t = __uint_as_float(v[j]) + b;
-      z[j] = (EPI == HG_EPI_BIAS_ELU_BF16) ? elu1(t) : t;
+      float t = __uint_as_float(v[j]) + bv[j];
+      // ELU with MUFU.EX2: |err| ~ 1e-7 absolute, far below the bf16 rounding of the stored activation
+      z[j] = (EPI == HG_EPI_BIAS_ELU_BF16) ? (t > 0.f ? t : exp2f_fast(t * 1.4426950408889634f) - 1.f) : t;
     }
     if (row_ok) {
       if (full) {
@@ -201,6 +227,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* epi_tiles = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -218,7 +245,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 4);
+      mbar_init(smem_u32(&tempty_bar[a]), NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -302,8 +329,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ================================================================ epilogue (warps 4..7 <-> TMEM lanes 32*(warp-4)..)
-    const int quad = warp - 4;
+    // ================================================================ epilogue: warps 4..11
+    const int quad = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;          // which half of the tile's columns
+    constexpr int CHUNKS = BLOCK_N / 64;       // 32-column chunks per warp
+    float* tile = epi_tiles + (warp - 4) * EPI_TILE_FLOATS;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
@@ -312,15 +342,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       const int row = ti.m_blk * BLOCK_M + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + half * (BLOCK_N / 2);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int n0 = ti.n_blk * BLOCK_N + c * 32;
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int n0 = ti.n_blk * BLOCK_N + half * (BLOCK_N / 2) + c * 32;
         if (n0 >= q.N) break;
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(q, row, n0, v, lane);
+        epilogue_chunk<EPI>(q, row, n0, v, lane, tile);
       }
       tc_fence_before();
       __syncwarp();
@@ -376,7 +406,8 @@ template <int BLOCK_N, int EPI>
 static int launch(const GroupParams& gp, cudaStream_t stream) {
   constexpr int STAGE_BYTES = BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2;
   constexpr int STAGES = SMEM_RING_BYTES / STAGE_BYTES;
-  const int smem = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  const int smem = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                   (EPI == HG_EPI_ATOMIC_F32 ? NUM_EPI_WARPS * EPI_TILE_FLOATS * 4 : 0);
   static bool configured = false;
   if (!configured) {
     HG_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

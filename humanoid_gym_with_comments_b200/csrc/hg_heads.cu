@@ -99,10 +99,11 @@ __device__ __forceinline__ void head_forward_row(const __nv_bfloat16* hrow, int 
 }
 
 // ------------------------------------------------------------------------------------------ rollout head
-constexpr int RH_ROWS = 32;      // rows per block
+constexpr int RH_ROWS = 16;      // rows per block (256 blocks at 4096 envs)
 constexpr int RH_SUB = 8;        // lanes per row
-constexpr int MAX_A = 32;        // max num_actions
+constexpr int MAX_A = 32;        // max num_actions (kernels are instantiated for action capacities 12 / 20 / 32)
 
+template <int AT>
 __global__ void __launch_bounds__(RH_ROWS* RH_SUB)
     policy_head_rollout_kernel(const __nv_bfloat16* __restrict__ ha, long long ld_ha, int H_a, const float* __restrict__ W_a,
                                const float* __restrict__ b_a, const float* __restrict__ std, const __nv_bfloat16* __restrict__ hc,
@@ -135,27 +136,26 @@ __global__ void __launch_bounds__(RH_ROWS* RH_SUB)
   head_forward_row<1>(shc + r * (H_c + 8), H_c, sWc, sb + MAX_A, 1, sub, RH_SUB, v1);
   if (sub == 0 && row < n) values[row] = v1[0];
   if (!ha) return;
-  float m[MAX_A];
-  head_forward_row<MAX_A>(sha + r * (H_a + 8), H_a, sWa, sb, A, sub, RH_SUB, m);
-  if (row >= n) return;
-  // lanes of the row split the actions; log-prob summed in action order by lane 0 for determinism
+  float m[AT];
+  head_forward_row<AT>(sha + r * (H_a + 8), H_a, sWa, sb, A, sub, RH_SUB, m);
+  // the row's lanes split the actions; the log-prob terms are then summed over the lanes
   float lp = 0.f;
-  if (sub == 0) {
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) {
-      if (a < A) {
-        const float sd = sb[MAX_A + 1 + a];
-        const float e = eps ? eps[(long long)row * A + a] : philox_normal(seed, counter, (uint32_t)row, (uint32_t)a);
-        const float act = m[a] + sd * e;                       // Normal(mu, std).sample()  (actor_critic.py:129,133)
-        const float d = act - m[a];
-        lp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;   // Normal.log_prob
-        actions[(long long)row * A + a] = act;
-        mu[(long long)row * A + a] = m[a];
-        sigma[(long long)row * A + a] = sd;
-      }
+  for (int a = 0; a < AT; ++a) {
+    if (a < A && (a % RH_SUB) == sub && row < n) {
+      const float sd = sb[MAX_A + 1 + a];
+      const float e = eps ? eps[(long long)row * A + a] : philox_normal(seed, counter, (uint32_t)row, (uint32_t)a);
+      const float act = m[a] + sd * e;                       // Normal(mu, std).sample()  (actor_critic.py:129,133)
+      const float d = act - m[a];
+      lp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;   // Normal.log_prob
+      actions[(long long)row * A + a] = act;
+      mu[(long long)row * A + a] = m[a];
+      sigma[(long long)row * A + a] = sd;
     }
-    log_prob[row] = lp;
   }
+#pragma unroll
+  for (int o = RH_SUB >> 1; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+  if (sub == 0 && row < n) log_prob[row] = lp;
 }
 
 __global__ void __launch_bounds__(RH_ROWS* RH_SUB)
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(RH_ROWS* RH_SUB)
 constexpr int LH_ROWS = 64;
 constexpr int LH_THREADS = 256;
 constexpr int LH_SUB = LH_THREADS / LH_ROWS;   // 4 lanes per row in the forward / loss phase
+constexpr int LH_GROUPS = LH_THREADS / 128;    // row groups in the backward phase
 
 struct NetSmem {
   __nv_bfloat16* h;   // [LH_ROWS][H+8]
@@ -195,26 +196,26 @@ struct NetSmem {
 
 // Backward of one head for the block's rows: column-parallel over the hidden index k.
 //   dH[r,k] = sum_a dOut[r,a] W[a,k];  dZ = dH * elu'(h);  gW[a,k] += dOut[r,a] h[r,k];  gb_hidden[k] += dZ[r,k]
+template <int NO>
 __device__ __forceinline__ void head_backward(const HgHeadNet& net, const NetSmem& s, int row0, int valid, float* red) {
   const int H = net.H, n_out = net.n_out, pitch = H + 8;
-  const int groups = LH_THREADS / 128;              // row groups working on the same k in parallel
   const int grp = threadIdx.x / 128;
   for (int k0 = 0; k0 < H; k0 += 128) {            // uniform trip count: the loop body holds block barriers
     const int k = k0 + (threadIdx.x % 128);
     const bool k_ok = k < H;
-    float gw[MAX_A], w[MAX_A];
+    float gw[NO], w[NO];
 #pragma unroll
-    for (int a = 0; a < MAX_A; ++a) {
+    for (int a = 0; a < NO; ++a) {
       gw[a] = 0.f;
       w[a] = (k_ok && a < n_out) ? s.W[a * H + k] : 0.f;
     }
     float gbh = 0.f;
     if (k_ok) {
-      for (int r = grp; r < valid; r += groups) {
+      for (int r = grp; r < valid; r += LH_GROUPS) {
         const float h = __bfloat162float(s.h[r * pitch + k]);
         float dh = 0.f;
 #pragma unroll
-        for (int a = 0; a < MAX_A; ++a) {
+        for (int a = 0; a < NO; ++a) {
           if (a < n_out) {
             const float d = s.dOut[r * n_out + a];
             dh += d * w[a];
@@ -228,23 +229,21 @@ __device__ __forceinline__ void head_backward(const HgHeadNet& net, const NetSme
     }
     // combine the row groups through shared memory, then one atomic per (a,k) per block
     if (grp > 0) {
-      float* slot = red + (size_t)((grp - 1) * 128 + (threadIdx.x % 128)) * (MAX_A + 1);
+      float* slot = red + (size_t)((grp - 1) * 128 + (threadIdx.x % 128)) * (NO + 1);
 #pragma unroll
-      for (int a = 0; a < MAX_A; ++a)
-        if (a < n_out) slot[a] = gw[a];
-      slot[MAX_A] = gbh;
+      for (int a = 0; a < NO; ++a) slot[a] = gw[a];
+      slot[NO] = gbh;
     }
     __syncthreads();
     if (grp == 0 && k_ok) {
-      for (int g = 1; g < groups; ++g) {
-        const float* slot = red + (size_t)((g - 1) * 128 + (threadIdx.x % 128)) * (MAX_A + 1);
+      for (int g = 1; g < LH_GROUPS; ++g) {
+        const float* slot = red + (size_t)((g - 1) * 128 + (threadIdx.x % 128)) * (NO + 1);
 #pragma unroll
-        for (int a = 0; a < MAX_A; ++a)
-          if (a < n_out) gw[a] += slot[a];
-        gbh += slot[MAX_A];
+        for (int a = 0; a < NO; ++a) gw[a] += slot[a];
+        gbh += slot[NO];
       }
 #pragma unroll
-      for (int a = 0; a < MAX_A; ++a)
+      for (int a = 0; a < NO; ++a)
         if (a < n_out) atomicAdd(net.gW + a * H + k, gw[a]);
       atomicAdd(net.gb_hidden + k, gbh);
     }
@@ -252,9 +251,11 @@ __device__ __forceinline__ void head_backward(const HgHeadNet& net, const NetSme
   }
 }
 
+template <int AT>
 __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_constant__ HgLossArgs L) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int A = L.A;
+  const int RS = 3 * A + 8;            // per-row gathered record: actions[A] old_mu[A] old_sigma[A] logp adv ret v tgt[3] pad
   // ---- carve shared memory
   uint8_t* p = smem;
   auto carve = [&](size_t bytes) { uint8_t* q = p; p += (bytes + 15) & ~size_t(15); return q; };
@@ -268,59 +269,78 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
     ss[i]->dOut = reinterpret_cast<float*>(carve((size_t)LH_ROWS * nets[i]->n_out * 4));
   }
   float* s_std = reinterpret_cast<float*>(carve(MAX_A * 4));
-  float* s_gstd = reinterpret_cast<float*>(carve(MAX_A * 4));
-  double* s_stats = reinterpret_cast<double*>(carve(8 * 8));
-  float* s_red = reinterpret_cast<float*>(carve((size_t)(LH_THREADS / 128 - 1) * 128 * (MAX_A + 1) * 4 + 16));
+  float* s_rec = reinterpret_cast<float*>(carve((size_t)LH_ROWS * RS * 4));
+  float* s_gs = reinterpret_cast<float*>(carve((size_t)LH_ROWS * A * 4));          // per-row d loss / d std[a]
+  float* s_stat = reinterpret_cast<float*>(carve((size_t)(LH_THREADS / 32) * 8 * 4));
+  long long* s_idx = reinterpret_cast<long long*>(carve((size_t)LH_ROWS * 8));
+  float* s_red = reinterpret_cast<float*>(carve((size_t)(LH_GROUPS - 1) * 128 * (AT + 1) * 4 + 16));
 
   const int row0 = blockIdx.x * LH_ROWS;
   const int valid = min(LH_ROWS, L.rows - row0);
+  if (threadIdx.x < LH_ROWS)
+    s_idx[threadIdx.x] = threadIdx.x < valid ? (L.idx ? L.idx[row0 + threadIdx.x] : (long long)(row0 + threadIdx.x)) : 0;
   for (int i = 0; i < 3; ++i) {
     stage_h(reinterpret_cast<const __nv_bfloat16*>(nets[i]->h), nets[i]->ld_h, nets[i]->H, row0, valid, LH_ROWS, ss[i]->h);
     stage_f32(nets[i]->W, nets[i]->n_out * nets[i]->H, ss[i]->W);
     stage_f32(nets[i]->b, nets[i]->n_out, ss[i]->b);
   }
   stage_f32(L.std, A, s_std);
-  if (threadIdx.x < MAX_A) s_gstd[threadIdx.x] = 0.f;
-  if (threadIdx.x < 8) s_stats[threadIdx.x] = 0.0;
+  __syncthreads();
+  // ---- cooperative gather of the rows' old-policy records (all loads independent -> full memory-level parallelism)
+  for (int i = threadIdx.x; i < valid * RS; i += LH_THREADS) {
+    const int r = i / RS, c = i - r * RS;
+    const long long src = s_idx[r];
+    float v = 0.f;
+    if (c < A) v = __ldg(L.actions + src * A + c);
+    else if (c < 2 * A) v = __ldg(L.old_mu + src * A + (c - A));
+    else if (c < 3 * A) v = __ldg(L.old_sigma + src * A + (c - 2 * A));
+    else if (c == 3 * A) v = __ldg(L.old_log_prob + src);
+    else if (c == 3 * A + 1) v = __ldg(L.advantages + src);
+    else if (c == 3 * A + 2) v = __ldg(L.returns + src);
+    else if (c == 3 * A + 3) v = __ldg(L.old_values + src);
+    else if (c < 3 * A + 7) v = __ldg(L.critic_obs + src * L.ld_cobs + L.lv_col + (c - 3 * A - 4));
+    s_rec[i] = v;
+  }
   __syncthreads();
 
   // ---- forward of the three heads + losses, LH_SUB lanes per row
   const int r = threadIdx.x / LH_SUB, sub = threadIdx.x % LH_SUB;
-  float m[MAX_A], v1[1], lv[3];
-  head_forward_row<MAX_A>(sa.h + r * (L.actor.H + 8), L.actor.H, sa.W, sa.b, A, sub, LH_SUB, m);
+  float m[AT], v1[1], lv[3];
+  head_forward_row<AT>(sa.h + r * (L.actor.H + 8), L.actor.H, sa.W, sa.b, A, sub, LH_SUB, m);
   head_forward_row<1>(sc.h + r * (L.critic.H + 8), L.critic.H, sc.W, sc.b, 1, sub, LH_SUB, v1);
   head_forward_row<3>(sl.h + r * (L.linvel.H + 8), L.linvel.H, sl.W, sl.b, 3, sub, LH_SUB, lv);
 
+  float st_v = 0.f, st_s = 0.f, st_l = 0.f, st_k = 0.f, st_e = 0.f;
   if (sub == 0) {
     if (r < valid) {
-      const long long src = L.idx ? L.idx[row0 + r] : (long long)(row0 + r);
+      const float* rec = s_rec + r * RS;
       const float inv_rows = L.inv_world / (float)L.rows;      // 1 / (rows over all ranks)
       // -- Gaussian log-prob, entropy, KL(old || new)   (actor_critic.py:123-138, ppo.py:165-166)
       float logp = 0.f, ent = 0.f, kl = 0.f;
 #pragma unroll
-      for (int a = 0; a < MAX_A; ++a) {
+      for (int a = 0; a < AT; ++a) {
         if (a < A) {
           const float sd = s_std[a];
-          const float d = L.actions[src * A + a] - m[a];
+          const float d = rec[a] - m[a];
           logp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;
           ent += HALF_LOG_2PI_PLUS_HALF + logf(sd);
-          const float osd = L.old_sigma[src * A + a];
-          const float dm = L.old_mu[src * A + a] - m[a];
+          const float osd = rec[2 * A + a];
+          const float dm = rec[A + a] - m[a];
           kl += logf(sd / osd + 1.e-5f) + (osd * osd + dm * dm) / (2.f * sd * sd) - 0.5f;
         }
       }
       // -- clipped surrogate (ppo.py:178-184)
-      const float adv = L.advantages[src];
-      const float ratio = expf(logp - L.old_log_prob[src]);
+      const float adv = rec[3 * A + 1];
+      const float ratio = expf(logp - rec[3 * A]);
       const float s1 = -adv * ratio;
       const float s2 = -adv * fminf(fmaxf(ratio, 1.f - L.clip_param), 1.f + L.clip_param);
       const float surr = fmaxf(s1, s2);
       const float g_logp = (s1 >= s2 ? s1 : 0.f) * inv_rows;   // d surr / d logp  (ties: clamp passes gradient)
       // -- value loss (ppo.py:187-194)
-      const float R = L.returns[src], v = v1[0];
+      const float R = rec[3 * A + 2], v = v1[0];
       float vl, g_v;
       if (L.use_clipped_value_loss) {
-        const float vo = L.old_values[src];
+        const float vo = rec[3 * A + 3];
         const float dv = v - vo;
         const float vc = vo + fminf(fmaxf(dv, -L.clip_param), L.clip_param);
         const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
@@ -336,53 +356,65 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
       float lsq = 0.f;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const float e = lv[j] - L.critic_obs[src * L.ld_cobs + L.lv_col + j];
+        const float e = lv[j] - rec[3 * A + 4 + j];
         lsq += e * e;
         sl.dOut[r * 3 + j] = L.lin_vel_coef * 2.f * e * inv_rows * (1.f / 3.f);
       }
       // -- gradients wrt mean and std
 #pragma unroll
-      for (int a = 0; a < MAX_A; ++a) {
+      for (int a = 0; a < AT; ++a) {
         if (a < A) {
           const float sd = s_std[a];
-          const float d = L.actions[src * A + a] - m[a];
+          const float d = rec[a] - m[a];
           sa.dOut[r * A + a] = g_logp * d / (sd * sd);
-          const float gs = g_logp * (d * d / (sd * sd * sd) - 1.f / sd) - L.entropy_coef * inv_rows / sd;
-          atomicAdd(&s_gstd[a], gs);
+          s_gs[r * A + a] = g_logp * (d * d / (sd * sd * sd) - 1.f / sd) - L.entropy_coef * inv_rows / sd;
         }
       }
-      atomicAdd(&s_stats[0], (double)vl);
-      atomicAdd(&s_stats[1], (double)surr);
-      atomicAdd(&s_stats[2], (double)lsq);
-      atomicAdd(&s_stats[3], (double)kl);
-      atomicAdd(&s_stats[4], (double)ent);
+      st_v = vl; st_s = surr; st_l = lsq; st_k = kl; st_e = ent;
     } else {
       sc.dOut[r] = 0.f;
       for (int j = 0; j < 3; ++j) sl.dOut[r * 3 + j] = 0.f;
-      for (int a = 0; a < A; ++a) sa.dOut[r * A + a] = 0.f;
+      for (int a = 0; a < A; ++a) { sa.dOut[r * A + a] = 0.f; s_gs[r * A + a] = 0.f; }
     }
+  }
+  // statistics: warp shuffle reduction, then one partial per warp in shared memory
+  st_v = warp_sum(st_v); st_s = warp_sum(st_s); st_l = warp_sum(st_l); st_k = warp_sum(st_k); st_e = warp_sum(st_e);
+  if ((threadIdx.x & 31) == 0) {
+    float* w = s_stat + (threadIdx.x >> 5) * 8;
+    w[0] = st_v; w[1] = st_s; w[2] = st_l; w[3] = st_k; w[4] = st_e;
   }
   __syncthreads();
 
   // ---- output-layer bias gradients, std gradient and statistics: a handful of atomics per block
-  for (int i = 0; i < 3; ++i) {
-    const int n_out = nets[i]->n_out;
-    if (threadIdx.x < n_out) {
+  {
+    const int t = threadIdx.x;
+    if (t < A) {                                  // actor output bias + std
+      float g = 0.f, gs = 0.f;
+      for (int rr = 0; rr < LH_ROWS; ++rr) { g += sa.dOut[rr * A + t]; gs += s_gs[rr * A + t]; }
+      atomicAdd(L.actor.gb + t, g);
+      atomicAdd(L.g_std + t, gs);
+    } else if (t >= 32 && t < 33) {
       float g = 0.f;
-      for (int rr = 0; rr < valid; ++rr) g += ss[i]->dOut[rr * n_out + threadIdx.x];
-      atomicAdd(nets[i]->gb + threadIdx.x, g);
+      for (int rr = 0; rr < LH_ROWS; ++rr) g += sc.dOut[rr];
+      atomicAdd(L.critic.gb, g);
+    } else if (t >= 64 && t < 67) {
+      float g = 0.f;
+      for (int rr = 0; rr < LH_ROWS; ++rr) g += sl.dOut[rr * 3 + (t - 64)];
+      atomicAdd(L.linvel.gb + (t - 64), g);
+    } else if (t >= 96 && t < 101) {
+      float g = 0.f;
+      for (int w = 0; w < LH_THREADS / 32; ++w) g += s_stat[w * 8 + (t - 96)];
+      atomicAdd(L.stats + (t - 96), g);
     }
   }
-  if (threadIdx.x < A) atomicAdd(L.g_std + threadIdx.x, s_gstd[threadIdx.x]);
-  if (threadIdx.x < 5) atomicAdd(L.stats + threadIdx.x, (float)s_stats[threadIdx.x]);
 
   // ---- backward through the three output layers and the ELU below them
-  head_backward(L.actor, sa, row0, valid, s_red);
-  head_backward(L.critic, sc, row0, valid, s_red);
-  head_backward(L.linvel, sl, row0, valid, s_red);
+  head_backward<AT>(L.actor, sa, row0, valid, s_red);
+  head_backward<1>(L.critic, sc, row0, valid, s_red);
+  head_backward<3>(L.linvel, sl, row0, valid, s_red);
 }
 
-static size_t loss_smem_bytes(const HgLossArgs& L) {
+static size_t loss_smem_bytes(const HgLossArgs& L, int AT) {
   auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
   size_t t = 0;
   const HgHeadNet* nets[3] = {&L.actor, &L.critic, &L.linvel};
@@ -390,8 +422,43 @@ static size_t loss_smem_bytes(const HgLossArgs& L) {
     t += al((size_t)LH_ROWS * (nets[i]->H + 8) * 2) + al((size_t)nets[i]->n_out * nets[i]->H * 4) +
          al((size_t)nets[i]->n_out * 4) + al((size_t)LH_ROWS * nets[i]->n_out * 4);
   }
-  t += al(MAX_A * 4) * 2 + al(64) + al((size_t)(LH_THREADS / 128 - 1) * 128 * (MAX_A + 1) * 4 + 16);
+  t += al(MAX_A * 4) + al((size_t)LH_ROWS * (3 * L.A + 8) * 4) + al((size_t)LH_ROWS * L.A * 4) +
+       al((size_t)(LH_THREADS / 32) * 8 * 4) + al((size_t)LH_ROWS * 8) + al((size_t)(LH_GROUPS - 1) * 128 * (AT + 1) * 4 + 16);
   return t;
+}
+
+template <int AT>
+static int launch_loss(const HgLossArgs& L, cudaStream_t s) {
+  const size_t smem = loss_smem_bytes(L, AT);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    HG_CUDA(cudaFuncSetAttribute(ppo_head_loss_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  ppo_head_loss_kernel<AT><<<(L.rows + LH_ROWS - 1) / LH_ROWS, LH_THREADS, smem, s>>>(L);
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
+}
+
+template <int AT>
+static int launch_rollout(const void* h_actor, int64_t ld_ha, int H_a, const float* W_a, const float* b_a, const float* std,
+                          const void* h_critic, int64_t ld_hc, int H_c, const float* W_c, const float* b_c, const float* eps,
+                          uint64_t seed, uint64_t counter, int n, int A, float* actions, float* mu, float* sigma,
+                          float* log_prob, float* values, cudaStream_t s) {
+  const size_t smem = (size_t)(A * H_a + H_c + 2 * MAX_A + 4) * 4 + (size_t)RH_ROWS * ((h_actor ? H_a + 8 : 0) + H_c + 8) * 2 + 32;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    HG_CUDA(cudaFuncSetAttribute(policy_head_rollout_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  policy_head_rollout_kernel<AT><<<(n + RH_ROWS - 1) / RH_ROWS, RH_ROWS * RH_SUB, smem, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(h_actor), ld_ha, H_a, W_a, b_a, std,
+      reinterpret_cast<const __nv_bfloat16*>(h_critic), ld_hc, H_c, W_c, b_c, eps, seed, counter, n, A, actions, mu,
+      sigma, log_prob, values);
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
 }
 
 }  // namespace hg
@@ -411,20 +478,15 @@ extern "C" int hg_policy_head_rollout(const void* h_actor, int64_t ld_ha, int H_
     H_a = 0;
     A = 0;
   }
-  const size_t smem = (size_t)(A * H_a + H_c + 2 * MAX_A + 4) * 4 +
-                      (size_t)RH_ROWS * ((h_actor ? H_a + 8 : 0) + H_c + 8) * 2 + 32;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    HG_CUDA(cudaFuncSetAttribute(policy_head_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  policy_head_rollout_kernel<<<(n + RH_ROWS - 1) / RH_ROWS, RH_ROWS * RH_SUB, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(h_actor), ld_ha, H_a, W_a, b_a, std,
-      reinterpret_cast<const __nv_bfloat16*>(h_critic), ld_hc, H_c, W_c, b_c, eps, seed, counter, n, A, actions, mu,
-      sigma, log_prob, values);
-  HG_LAUNCH_CHECK();
-  count_launch();
-  return HG_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (A <= 12)
+    return launch_rollout<12>(h_actor, ld_ha, H_a, W_a, b_a, std, h_critic, ld_hc, H_c, W_c, b_c, eps, seed, counter, n, A,
+                              actions, mu, sigma, log_prob, values, s);
+  if (A <= 20)
+    return launch_rollout<20>(h_actor, ld_ha, H_a, W_a, b_a, std, h_critic, ld_hc, H_c, W_c, b_c, eps, seed, counter, n, A,
+                              actions, mu, sigma, log_prob, values, s);
+  return launch_rollout<32>(h_actor, ld_ha, H_a, W_a, b_a, std, h_critic, ld_hc, H_c, W_c, b_c, eps, seed, counter, n, A,
+                            actions, mu, sigma, log_prob, values, s);
 }
 
 extern "C" int hg_value_head(const void* h_critic, int64_t ld_hc, int H_c, const float* W_c, const float* b_c, int n,
@@ -465,14 +527,8 @@ extern "C" int hg_ppo_head_loss(const HgLossArgs* L, void* stream) {
   }
   HG_CHECK(L->actions && L->old_mu && L->old_sigma && L->old_log_prob && L->advantages && L->returns && L->old_values &&
                L->critic_obs && L->std && L->g_std && L->stats, "hg_ppo_head_loss: null pointer");
-  const size_t smem = loss_smem_bytes(*L);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    HG_CUDA(cudaFuncSetAttribute(ppo_head_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  ppo_head_loss_kernel<<<(L->rows + LH_ROWS - 1) / LH_ROWS, LH_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*L);
-  HG_LAUNCH_CHECK();
-  count_launch();
-  return HG_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (L->A <= 12) return launch_loss<12>(*L, s);
+  if (L->A <= 20) return launch_loss<20>(*L, s);
+  return launch_loss<32>(*L, s);
 }
