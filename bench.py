@@ -50,7 +50,9 @@ def parse():
     ap.add_argument("--cpu-sample-envs", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--fast-rng", action="store_true", help="in-kernel Philox instead of torch.randn (loses seed parity)")
+    ap.add_argument("--torch-rng", action="store_true",
+                    help="draw action / observation noise with torch.randn (stream parity with the reference on the same device) instead of the in-kernel Philox4x32-10")
+    ap.add_argument("--unbound-env", action="store_true", help="env writes its own buffers; PPO.act ingests them (generic drop-in path)")
     return ap.parse_args()
 
 
@@ -59,6 +61,7 @@ def workload_config(a, world):
                         f"actor [512,256,128] critic [768,256,128] lin-vel [128,128], 2 epochs x 4 minibatches "
                         f"(BASELINE.json configs[1]); synthetic Isaac-Gym-shaped state, fused env step in the loop",
             "envs_per_gpu": a.envs, "horizon": a.horizon, "parallelism": f"env-sharded dp{world}",
+            "rng": "in-kernel Philox4x32-10 keyed by (seed, step, row) for action and observation noise; --torch-rng switches to torch.randn",
             "l2_policy": "per-iteration working set (storage 0.95 GB fp32 + 0.46 GB bf16) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -200,9 +203,11 @@ def run_ours(a):
               entropy_coef=0.001, learning_rate=1e-5, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive",
               desired_kl=0.01, device=dev)
     alg.init_storage(N, T, [705], [219], [12])
-    alg.torch_rng = not a.fast_rng
+    alg.torch_rng = a.torch_rng
     torch.manual_seed(1000 + rank)               # per-rank env / sampling streams
-    env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, pool=4, seed=rank, torch_rng_noise=not a.fast_rng)
+    env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, pool=4, seed=rank, torch_rng_noise=a.torch_rng)
+    if not a.unbound_env:
+        env.bind_storage(alg.storage)
     obs, critic_obs = env.get_observations(), env.get_privileged_observations()
     state = {"obs": obs, "critic_obs": critic_obs}
     host_pool = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in env.pool]

@@ -17,6 +17,10 @@ LIB_PATH = os.path.join(HERE, "libhgb200.so")
 BUILD_DIR = os.path.join(HERE, "csrc", "_build")
 SOURCES = ["hg_runtime.cu", "hg_gemm.cu", "hg_gae.cu", "hg_misc.cu", "hg_heads.cu", "hg_optim.cu", "hg_env.cu"]
 EXTRA_FLAGS = {"hg_env.cu": ["-fmad=false"]}
+if os.environ.get("HG_EPI_WARPS"):
+    EXTRA_FLAGS["hg_gemm.cu"] = ["-DHG_EPI_WARPS=" + os.environ["HG_EPI_WARPS"]]
+if os.environ.get("HG_GEMM_DEFS"):
+    EXTRA_FLAGS.setdefault("hg_gemm.cu", []).extend(os.environ["HG_GEMM_DEFS"].split())
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 HG_MAX_GROUP = 4
@@ -146,7 +150,9 @@ class HgEnvBuffers(C.Structure):
                  "last_contacts", "feet_height", "last_feet_z", "ref_dof_pos", "episode_length_buf", "episode_sums")] + \
                [("obs_prev", C.c_void_p), ("obs_prev_ld", C.c_int64), ("priv_prev", C.c_void_p),
                 ("priv_prev_ld", C.c_int64), ("obs_next", C.c_void_p), ("obs_next_ld", C.c_int64),
-                ("priv_next", C.c_void_p), ("priv_next_ld", C.c_int64)] + \
+                ("priv_next", C.c_void_p), ("priv_next_ld", C.c_int64),
+                ("obs16_next", C.c_void_p), ("obs16_next_ld", C.c_int64),
+                ("priv16_next", C.c_void_p), ("priv16_next_ld", C.c_int64)] + \
                [(n, C.c_void_p) for n in ("rew_buf", "reset_buf", "time_out_buf", "reward_terms")]
 
 
@@ -156,6 +162,9 @@ _SIGNATURES = {
     "hg_abi_version": (C.c_int, []),
     "hg_launch_count": (C.c_int64, []),
     "hg_gemm_grouped": (C.c_int, [C.POINTER(HgGemmProblem), C.c_int, C.c_int, C.c_int, _P]),
+    "hg_gemm_plan_create": (C.c_int, [C.POINTER(HgGemmProblem), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "hg_gemm_plan_run": (C.c_int, [C.c_void_p, _P]),
+    "hg_gemm_plan_destroy": (None, [C.c_void_p]),
     "hg_gae_returns": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
     "hg_ingest_rows": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, C.c_int64, _P, C.c_int64, _P]),
     "hg_gather_rows_bf16": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P]),

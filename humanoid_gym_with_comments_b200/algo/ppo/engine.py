@@ -139,6 +139,7 @@ class MLPEngine:
         self.flat = flat
         self.lib = _lib.load()
         self.num_sms = torch.cuda.get_device_properties(flat.device).multi_processor_count
+        self._all_plans: List[int] = []
 
     # -- helpers ----------------------------------------------------------------------------
     @staticmethod
@@ -154,11 +155,34 @@ class MLPEngine:
         arr = (HgGemmProblem * len(problems))(*problems)
         check(self.lib.hg_gemm_grouped(arr, len(problems), epi, block_n, current_stream()))
 
+    def _plan(self, problems: List[HgGemmProblem], epi: int, block_n: int) -> int:
+        arr = (HgGemmProblem * len(problems))(*problems)
+        handle = C.c_void_p()
+        check(self.lib.hg_gemm_plan_create(arr, len(problems), epi, block_n, C.byref(handle)))
+        self._all_plans.append(handle.value)
+        return handle.value
+
+    def run_plans(self, plans: List[int]) -> None:
+        st = current_stream()
+        run = self.lib.hg_gemm_plan_run
+        for h in plans:
+            if run(h, st) != 0:
+                check(-1)
+
+    def __del__(self):
+        try:
+            for h in getattr(self, "_all_plans", []):
+                self.lib.hg_gemm_plan_destroy(h)
+        except Exception:
+            pass
+
     # -- forward of all hidden layers ---------------------------------------------------------
     def forward_hidden(self, nets: Sequence[NetSpec], inputs: Dict[str, torch.Tensor], in_cols: Dict[str, int],
-                       ws: Workspace, rows: int) -> None:
+                       ws: Workspace, rows: int, make_plans: bool = False):
         """inputs[name]: bf16 [rows, ld] (ld multiple of 8; only the first in_cols[name] columns are read).
-        Fills ws.h[name][l] = elu(W_l h_{l-1} + b_l) for every hidden layer, one grouped launch per depth."""
+        Fills ws.h[name][l] = elu(W_l h_{l-1} + b_l) for every hidden layer, one grouped launch per depth.
+        With make_plans=True nothing is launched: the prepared launches are returned for `run_plans`."""
+        plans = []
         depth = max(n.num_hidden for n in nets)
         for l in range(depth):
             probs, ns = [], []
@@ -175,7 +199,11 @@ class MLPEngine:
                     M=rows, N=lin.out_features, K=k, k_splits=1, out=ptr(out), ldo=out.stride(0),
                     bias=ptr(lin.bias.data), act=0, ldact=0, colsum=0))
                 ns.append(lin.out_features)
-            self._launch(probs, EPI_BIAS_ELU_BF16, self._block_n(ns))
+            if make_plans:
+                plans.append(self._plan(probs, EPI_BIAS_ELU_BF16, self._block_n(ns)))
+            else:
+                self._launch(probs, EPI_BIAS_ELU_BF16, self._block_n(ns))
+        return plans
 
     # -- backward of all hidden layers ----------------------------------------------------------
     def backward_hidden(self, nets: Sequence[NetSpec], inputs: Dict[str, torch.Tensor], in_cols: Dict[str, int],

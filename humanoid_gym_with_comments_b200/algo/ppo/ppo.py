@@ -164,6 +164,10 @@ class PPO:
         self._perm_bufs = None
         self._lr_synced = learning_rate
         # test hooks: replay externally drawn randomness (parity tests feed the oracle's eps / permutation)
+        self._lib = _lib.load()
+        self._slot_plans, self._plans_owner, self._plans_storage = {}, None, None
+        self._seed = int(torch.initial_seed()) & (2 ** 64 - 1)
+        self._gamma_f = float(gamma)
         self.eps_override = None     # callable(step) -> [N, A] standard-normal draws
         self.perm_override = None    # int64 [num_mini_batches * mini_batch_size] permutation
 
@@ -177,55 +181,84 @@ class PPO:
         self.actor_critic.train()
 
     # ------------------------------------------------------------------ rollout
-    def act(self, obs, critic_obs):
+    def _slot_plan(self, t):
+        """Everything `act` / `process_env_step` need for storage slot t, prepared once: the grouped-GEMM plans
+        (TMA tensor maps encoded, tile schedule laid out), the head launch arguments and the slot views."""
         ac, st = self.actor_critic, self.storage
         eng = ac.engine()
-        st.check_room()
-        t, N, A = st.step, st.num_envs, ac.num_actions
+        if self._plans_owner is not eng or self._plans_storage is not st:
+            self._slot_plans = {}
+            self._plans_owner, self._plans_storage = eng, st
+        plan = self._slot_plans.get(t)
+        if plan is None:
+            N, A = st.num_envs, ac.num_actions
+            _, _, o16, p16 = st.slot(t)
+            ws = ac.workspace(N)
+            gemms = eng.forward_hidden((ac.net_actor, ac.net_critic), {"actor": o16, "critic": p16},
+                                       {"actor": st.obs_cols, "critic": st.priv_cols}, ws, N, make_plans=True)
+            la, lc = ac.net_actor.linears[-1], ac.net_critic.linears[-1]
+            ha, hc = ws.h["actor"][-1], ws.h["critic"][-1]
+            views = dict(actions=st.actions[t], values=st.values[t], log_prob=st.actions_log_prob[t].view(-1),
+                         mu=st.mu[t], sigma=st.sigma[t], rewards=st.rewards[t].view(-1))
+            head_args = (ptr(ha), ha.stride(0), ha.shape[1], ptr(la.weight.data), ptr(la.bias.data), ptr(ac.std.data),
+                         ptr(hc), hc.stride(0), hc.shape[1], ptr(lc.weight.data), ptr(lc.bias.data))
+            head_out = (N, A, ptr(st.actions[t]), ptr(st.mu[t]), ptr(st.sigma[t]), ptr(st.actions_log_prob[t]),
+                        ptr(st.values[t]))
+            store_ptrs = (ptr(st.values[t]), ptr(st.rewards[t]), ptr(st.dones[t]))
+            plan = (gemms, head_args, head_out, views, store_ptrs)
+            self._slot_plans[t] = plan
+        return plan
+
+    def act(self, obs, critic_obs):
+        ac, st = self.actor_critic, self.storage
+        t = st.step
+        if t >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
         if critic_obs is None:
             critic_obs = obs
-        o16, p16 = st.ingest(obs, critic_obs, t)
-        ws = ac.workspace(N)
-        eng.forward_hidden((ac.net_actor, ac.net_critic), {"actor": o16, "critic": p16},
-                           {"actor": st.obs_cols, "critic": st.priv_cols}, ws, N)
+        gemms, head_args, head_out, views, _ = self._slot_plan(t)
+        if not st.holds(obs, critic_obs, t):          # a bound env already wrote this slot and its bf16 shadow
+            st.ingest(obs, critic_obs, t)
+        ac._engine.run_plans(gemms)
         if self.eps_override is not None:
             eps = self.eps_override(t).to(st.actions.device).float().contiguous()
         else:
-            eps = torch.randn(N, A, device=st.actions.device) if self.torch_rng else None
-        out = dict(actions=st.actions[t], mu=st.mu[t], sigma=st.sigma[t], log_prob=st.actions_log_prob[t],
-                   values=st.values[t])
-        ac._head_rollout(ws, N, True, eps, out)
+            eps = torch.randn(head_out[0], head_out[1], device=st.actions.device) if self.torch_rng else None
+        ac._rng_counter += 1
+        check(self._lib.hg_policy_head_rollout(*head_args, ptr(eps), self._seed, ac._rng_counter, *head_out,
+                                               current_stream()))
         tr = self.transition
-        tr.actions = st.actions[t]
-        tr.values = st.values[t]
-        tr.actions_log_prob = st.actions_log_prob[t].view(-1)
-        tr.action_mean = st.mu[t]
-        tr.action_sigma = st.sigma[t]
+        tr.actions = views["actions"]
+        tr.values = views["values"]
+        tr.actions_log_prob = views["log_prob"]
+        tr.action_mean = views["mu"]
+        tr.action_sigma = views["sigma"]
         tr.observations = obs
         tr.critic_observations = critic_obs
         return tr.actions
 
     def process_env_step(self, rewards, dones, infos):
         st = self.storage
-        st.check_room()
-        t, N = st.step, st.num_envs
-        _lib.require_cuda(rewards, dones)
-        rewards = rewards.reshape(-1)
-        if rewards.dtype != torch.float32 or not rewards.is_contiguous():
-            rewards = rewards.float().contiguous()
-        d8 = dones.reshape(-1)
-        d8 = d8 if d8.dtype in (torch.bool, torch.uint8) else (d8 != 0)
-        d8 = d8.contiguous()
-        to8 = None
-        if 'time_outs' in infos:
-            to8 = infos['time_outs'].reshape(-1).to(self.device)
-            to8 = to8 if to8.dtype in (torch.bool, torch.uint8) else (to8 != 0)
-            to8 = to8.contiguous()
-        check(_lib.load().hg_store_rewards_dones(ptr(rewards), ptr(st.values[t]), ptr(to8), ptr(d8), float(self.gamma), N,
-                                                 ptr(st.rewards[t]), ptr(st.dones[t]), current_stream()))
-        self.transition.rewards = st.rewards[t].view(-1)
-        self.transition.dones = dones
-        st.step += 1
+        t = st.step
+        if t >= st.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        val_ptr, rew_ptr, done_ptr = self._slot_plan(t)[4]
+        if not (rewards.is_cuda and dones.is_cuda):
+            _lib.require_cuda(rewards, dones)
+        if rewards.dtype != torch.float32 or rewards.dim() != 1 or not rewards.is_contiguous():
+            rewards = rewards.reshape(-1).float().contiguous()
+        d8 = dones
+        if d8.dtype not in (torch.bool, torch.uint8) or d8.dim() != 1 or not d8.is_contiguous():
+            d8 = d8.reshape(-1)
+            d8 = (d8 if d8.dtype in (torch.bool, torch.uint8) else (d8 != 0)).contiguous()
+        to8 = infos.get('time_outs') if infos else None
+        if to8 is not None and (to8.dtype not in (torch.bool, torch.uint8) or to8.dim() != 1 or not to8.is_contiguous()
+                                or not to8.is_cuda):
+            to8 = to8.reshape(-1).to(self.device)
+            to8 = (to8 if to8.dtype in (torch.bool, torch.uint8) else (to8 != 0)).contiguous()
+        check(self._lib.hg_store_rewards_dones(ptr(rewards), val_ptr, ptr(to8), ptr(d8), self._gamma_f, st.num_envs,
+                                               rew_ptr, done_ptr, current_stream()))
+        st.step = t + 1
         self.transition.clear()
         self.actor_critic.reset(dones)
 
@@ -233,7 +266,11 @@ class PPO:
         ac, st = self.actor_critic, self.storage
         eng = ac.engine()
         N = last_critic_obs.shape[0]
-        c16 = ac._to_bf16(last_critic_obs, "last_critic")
+        T = st.num_transitions_per_env
+        if st._priv_all is not None and N == st.num_envs and last_critic_obs.data_ptr() == st._priv_all[T].data_ptr():
+            c16 = st.slot(T)[3]                       # written (with its shadow) by a bound env
+        else:
+            c16 = ac._to_bf16(last_critic_obs, "last_critic")
         ws = ac.workspace(N)
         eng.forward_hidden((ac.net_critic,), {"critic": c16}, {"critic": last_critic_obs.shape[1]}, ws, N)
         last_values = torch.empty(N, 1, device=st.values.device)

@@ -41,11 +41,16 @@ class RolloutStorage:
         T, N = num_transitions_per_env, num_envs
         z = lambda *s, **k: torch.zeros(*s, device=self.device, **k)
 
-        # Core
-        self.observations = z(T, N, *obs_shape)
+        # Core.  One extra slot (index T) behind the public [T, N, ...] views: an env bound with `bind_env` writes
+        # the observation of step t+1 straight into slot t+1, so slot T carries the last observation of an
+        # iteration over to the next one.
+        self._obs_all = z(T + 1, N, *obs_shape)
+        self.observations = self._obs_all[:T]
         if privileged_obs_shape[0] is not None:
-            self.privileged_observations = z(T, N, *privileged_obs_shape)
+            self._priv_all = z(T + 1, N, *privileged_obs_shape)
+            self.privileged_observations = self._priv_all[:T]
         else:
+            self._priv_all = None
             self.privileged_observations = None
         self.rewards = z(T, N, 1)
         self.actions = z(T, N, *actions_shape)
@@ -71,19 +76,34 @@ class RolloutStorage:
         # bf16 shadows for the tensor-core layers
         self.obs_cols = int(obs_shape[0])
         self.obs_ld = round_up(self.obs_cols, 8)
-        self.obs16 = z(T * N, self.obs_ld, dtype=torch.bfloat16)
+        self._obs16_all = z((T + 1) * N, self.obs_ld, dtype=torch.bfloat16)
+        self.obs16 = self._obs16_all[:T * N]
         if self.privileged_observations is not None:
             self.priv_cols = int(privileged_obs_shape[0])
             self.priv_ld = round_up(self.priv_cols, 8)
-            self.priv16 = z(T * N, self.priv_ld, dtype=torch.bfloat16)
+            self._priv16_all = z((T + 1) * N, self.priv_ld, dtype=torch.bfloat16)
+            self.priv16 = self._priv16_all[:T * N]
         else:
-            self.priv_cols, self.priv_ld, self.priv16 = self.obs_cols, self.obs_ld, self.obs16
+            self.priv_cols, self.priv_ld = self.obs_cols, self.obs_ld
+            self._priv16_all, self.priv16 = self._obs16_all, self.obs16
         self._gae_scratch = z(4, dtype=torch.float64)
 
     # ------------------------------------------------------------------ fused-path helpers (used by PPO)
     def check_room(self):
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
+
+    def slot(self, step: int):
+        """(obs fp32 [N,O], priv fp32 [N,P] or None, obs bf16 [N,ldO], priv bf16 [N,ldP]) of slot `step` in [0, T]."""
+        N = self.num_envs
+        return (self._obs_all[step], self._priv_all[step] if self._priv_all is not None else None,
+                self._obs16_all[step * N:(step + 1) * N], self._priv16_all[step * N:(step + 1) * N])
+
+    def holds(self, obs: torch.Tensor, critic_obs, step: int) -> bool:
+        """True if `obs` / `critic_obs` ARE slot `step` (written there, with their bf16 shadows, by a bound env)."""
+        if obs.data_ptr() != self._obs_all[step].data_ptr():
+            return False
+        return self._priv_all is None or critic_obs is None or critic_obs.data_ptr() == self._priv_all[step].data_ptr()
 
     def ingest(self, obs: torch.Tensor, critic_obs, step: int):
         """Copy this step's observations into slot `step` (fp32) and its bf16 shadow rows, one launch each

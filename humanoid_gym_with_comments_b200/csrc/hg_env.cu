@@ -17,7 +17,8 @@
 namespace hg {
 
 constexpr int ENV_PER_BLOCK = 32;
-constexpr int ENV_THREADS = 128;
+constexpr int ENV_THREADS = 512;       // warps 0-3: per-env math by role; warps 4-15: history streaming
+constexpr int ENV_ROLE_WARPS = 4;
 constexpr int MAX_FRAME = 160;          // >= So, Sp for D <= 32
 constexpr float TWO_PI_F = 6.2831855f;  // fp32(2*pi)
 constexpr float PI_F = 3.1415927f;
@@ -136,6 +137,35 @@ __device__ __forceinline__ BaseFrame base_frame(const HgEnvBuffers& B, int n, bo
   return f;
 }
 
+// dst[c] = clip(reset ? 0 : src[c]) for c < count, one warp, 8 independent 128-byte loads in flight per lane-iteration.
+__device__ __forceinline__ void shift_rows(const float* __restrict__ src, float* __restrict__ dst,
+                                           __nv_bfloat16* __restrict__ dst16, int count, bool reset, float clip, int lane) {
+  if (reset) {
+    for (int c = lane; c < count; c += 32) {
+      dst[c] = 0.f;
+      if (dst16) dst16[c] = __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
+  int c = lane;
+  for (; c + 7 * 32 < count; c += 8 * 32) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(src + c + u * 32);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float w = clampf(v[u], -clip, clip);
+      dst[c + u * 32] = w;
+      if (dst16) dst16[c + u * 32] = __float2bfloat16_rn(w);
+    }
+  }
+  for (; c < count; c += 32) {
+    const float w = clampf(__ldg(src + c), -clip, clip);
+    dst[c] = w;
+    if (dst16) dst16[c] = __float2bfloat16_rn(w);
+  }
+}
+
 // One thread per env for the scalar math (32 envs per block; the block's 4 warps split the work by role so the
 // dependent-latency chain per env is ~4x shorter), then all 128 threads stream the history rows.
 //   warp 0: observation frames (phase, euler, base-frame velocities, joint terms)      compute_observations :818-887
@@ -150,6 +180,8 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
   float* s_terms = s_fpriv + ENV_PER_BLOCK * Sp;      // [HG_NUM_REWARDS][ENV_PER_BLOCK]
   float* s_s2 = s_terms + HG_NUM_REWARDS * ENV_PER_BLOCK;   // [ENV_PER_BLOCK] sin of the post-reset phase
   int* s_reset = reinterpret_cast<int*>(s_s2 + ENV_PER_BLOCK);
+  int* s_ep = s_reset + ENV_PER_BLOCK;                      // episode length to store AFTER every warp has read the old one
+  int* s_tout = s_ep + ENV_PER_BLOCK;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * ENV_PER_BLOCK;
@@ -162,7 +194,23 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
   float* T = s_terms + lane;                          // T[k * ENV_PER_BLOCK]
 #define HG_TERM(k, val) T[(k) * ENV_PER_BLOCK] = (val) * C.reward_scale_dt[k]
 
-  if (ok) {
+  if (warp >= ENV_ROLE_WARPS) {
+    // ---------------------------------------------------------------- history shift (:883-887): needs only the reset flag,
+    // so these 12 warps stream the 14 old actor frames / 2 old critic frames while warps 0-3 do the per-env math.
+    if (doB) {
+      const int envs_here = min(ENV_PER_BLOCK, C.num_envs - n0);
+      for (int el = warp - ENV_ROLE_WARPS; el < envs_here; el += ENV_THREADS / 32 - ENV_ROLE_WARPS) {
+        const int ne = n0 + el;
+        const bool reset = env_base(C, B, ne, doA).reset;       // warp-uniform broadcast loads
+        __nv_bfloat16* o16 = B.obs16_next ? reinterpret_cast<__nv_bfloat16*>(B.obs16_next) + (size_t)ne * B.obs16_next_ld : nullptr;
+        __nv_bfloat16* p16 = B.priv16_next ? reinterpret_cast<__nv_bfloat16*>(B.priv16_next) + (size_t)ne * B.priv16_next_ld : nullptr;
+        shift_rows(B.obs_prev + (size_t)ne * B.obs_prev_ld + So, B.obs_next + (size_t)ne * B.obs_next_ld, o16,
+                   (C.frame_stack - 1) * So, reset, C.clip_obs, lane);
+        shift_rows(B.priv_prev + (size_t)ne * B.priv_prev_ld + Sp, B.priv_next + (size_t)ne * B.priv_next_ld, p16,
+                   (C.c_frame_stack - 1) * Sp, reset, C.clip_obs, lane);
+      }
+    }
+  } else if (ok) {
     const EnvBase e = env_base(C, B, n, doA);
     if (warp == 0) {
       // ------------------------------------------------------------ observation frames (post-reset state)
@@ -209,15 +257,12 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
         t[16] = so0; t[17] = so1;
         t[18] = e.ct0 ? 1.f : 0.f; t[19] = e.ct1 ? 1.f : 0.f;
         s_s2[lane] = s2;
-        B.episode_length_buf[n] = ep;
+        s_ep[lane] = (int)ep;
       } else {
-        B.episode_length_buf[n] = e.ep;
+        s_ep[lane] = (int)e.ep;
       }
       s_reset[lane] = e.reset ? 1 : 0;
-      if (doA) {
-        B.reset_buf[n] = e.reset ? 1 : 0;
-        B.time_out_buf[n] = e.time_out ? 1 : 0;
-      }
+      s_tout[lane] = e.time_out ? 1 : 0;
     } else if (doA && warp == 1) {
       // ------------------------------------------------------------ joint-space rewards
       float t1 = 0.f, t2 = 0.f, t3 = 0.f, jd_all = 0.f, l01 = 0.f, r01 = 0.f, acc2 = 0.f, vel2 = 0.f, tq2 = 0.f, jp2 = 0.f;
@@ -349,16 +394,27 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
 #undef HG_TERM
   __syncthreads();
 
+  if (ok && warp == 0) {       // published only now: other warps derived reset / phase from the OLD values until the barrier
+    B.episode_length_buf[n] = s_ep[lane];
+    if (doA) {
+      B.reset_buf[n] = s_reset[lane] ? 1 : 0;
+      B.time_out_buf[n] = s_tout[lane] ? 1 : 0;
+    }
+  }
   // ---------------------------------------------------------------- total reward (alphabetical order :894-898), episode sums, clip
   if (doA && ok && warp == 0) {
     const bool reset = s_reset[lane] != 0;
     float rew = 0.f;
+    float prev[HG_NUM_REWARDS];
+#pragma unroll
+    for (int k = 0; k < HG_NUM_REWARDS; ++k) prev[k] = B.episode_sums[(size_t)k * C.num_envs + n];   // 22 independent loads
+#pragma unroll
     for (int k = 0; k < HG_NUM_REWARDS; ++k) {
       if (C.reward_scale_dt[k] != 0.f) {
         const float term_k = s_terms[k * ENV_PER_BLOCK + lane];
         rew += term_k;
         const size_t idx = (size_t)k * C.num_envs + n;
-        B.episode_sums[idx] = (reset && doB) ? 0.f : B.episode_sums[idx] + term_k;   // zeroed by reset_idx (:1144)
+        B.episode_sums[idx] = (reset && doB) ? 0.f : prev[k] + term_k;               // zeroed by reset_idx (:1144)
         if (B.reward_terms) B.reward_terms[idx] = term_k;
       }
     }
@@ -400,39 +456,33 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
     B.last_root_vel[(size_t)(n0 + el) * 6 + d] = __ldg(B.root_states + (size_t)(n0 + el) * 13 + 7 + d);
   }
 
-  // ---------------------------------------------------------------- history shift + new frame + clip (:883-887, :654-657)
+  // ---------------------------------------------------------------- newest frame (+ noise :877) + clip (:654-657), all 16 warps
   for (int el = warp; el < envs_here; el += ENV_THREADS / 32) {
     const int ne = n0 + el;
-    const bool reset = s_reset[el] != 0;
     {
-      const int keep = (C.frame_stack - 1) * So, tot = C.frame_stack * So;
-      const float* prev = B.obs_prev + (size_t)ne * B.obs_prev_ld + So;
-      float* next = B.obs_next + (size_t)ne * B.obs_next_ld;
+      float* next = B.obs_next + (size_t)ne * B.obs_next_ld + (C.frame_stack - 1) * So;
       const float* fo = s_fobs + el * So;
-      for (int c = lane; c < tot; c += 32) {
-        float v;
-        if (c < keep) {
-          v = reset ? 0.f : prev[c];
-        } else {
-          const int j = c - keep;
-          v = fo[j];
-          const float nv = __ldg(B.noise_scale_vec + j);
-          if (C.noise_level != 0.f) {
-            const float e = B.noise ? __ldg(B.noise + (size_t)ne * So + j) : (nv != 0.f ? env_philox_normal(B.seed, B.counter, ne, j) : 0.f);
-            v = v + e * nv * C.noise_level;                                        // :877
-          }
+      for (int j = lane; j < So; j += 32) {
+        float v = fo[j];
+        const float nv = __ldg(B.noise_scale_vec + j);
+        if (C.noise_level != 0.f) {
+          const float e = B.noise ? __ldg(B.noise + (size_t)ne * So + j) : (nv != 0.f ? env_philox_normal(B.seed, B.counter, ne, j) : 0.f);
+          v = v + e * nv * C.noise_level;
         }
-        next[c] = clampf(v, -C.clip_obs, C.clip_obs);
+        v = clampf(v, -C.clip_obs, C.clip_obs);
+        next[j] = v;
+        if (B.obs16_next)
+          reinterpret_cast<__nv_bfloat16*>(B.obs16_next)[(size_t)ne * B.obs16_next_ld + (C.frame_stack - 1) * So + j] = __float2bfloat16_rn(v);
       }
     }
     {
-      const int keep = (C.c_frame_stack - 1) * Sp, tot = C.c_frame_stack * Sp;
-      const float* prev = B.priv_prev + (size_t)ne * B.priv_prev_ld + Sp;
-      float* next = B.priv_next + (size_t)ne * B.priv_next_ld;
+      float* next = B.priv_next + (size_t)ne * B.priv_next_ld + (C.c_frame_stack - 1) * Sp;
       const float* fp = s_fpriv + el * Sp;
-      for (int c = lane; c < tot; c += 32) {
-        const float v = c < keep ? (reset ? 0.f : prev[c]) : fp[c - keep];
-        next[c] = clampf(v, -C.clip_obs, C.clip_obs);
+      for (int j = lane; j < Sp; j += 32) {
+        const float v = clampf(fp[j], -C.clip_obs, C.clip_obs);
+        next[j] = v;
+        if (B.priv16_next)
+          reinterpret_cast<__nv_bfloat16*>(B.priv16_next)[(size_t)ne * B.priv16_next_ld + (C.c_frame_stack - 1) * Sp + j] = __float2bfloat16_rn(v);
       }
     }
   }
@@ -460,7 +510,7 @@ extern "C" int hg_env_step(const HgEnvConfig* cfg, const HgEnvBuffers* buf, void
            "hg_env_step: null buffer");
   const int blocks = (cfg->num_envs + ENV_PER_BLOCK - 1) / ENV_PER_BLOCK;
   const int So = 11 + 3 * cfg->D, Sp = 25 + 4 * cfg->D;
-  const size_t smem = (size_t)(ENV_PER_BLOCK * (So + Sp) + HG_NUM_REWARDS * ENV_PER_BLOCK + 2 * ENV_PER_BLOCK) * 4;
+  const size_t smem = (size_t)(ENV_PER_BLOCK * (So + Sp) + HG_NUM_REWARDS * ENV_PER_BLOCK + 4 * ENV_PER_BLOCK) * 4;
   env_step_kernel<<<blocks, ENV_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *buf);
   HG_LAUNCH_CHECK();
   count_launch();

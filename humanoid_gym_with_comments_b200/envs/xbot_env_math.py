@@ -177,6 +177,8 @@ class XBotEnvMath:
         c.phase_mul_reciprocal = 1 if cfg.phase_mul_reciprocal else 0
         c.phases = ENV_PHASE_ALL
         self._c = c
+        self._buf_cache = {}
+        self._lib = _lib.load()
 
     @property
     def episode_sums(self) -> Dict[str, torch.Tensor]:
@@ -187,48 +189,69 @@ class XBotEnvMath:
         for b in self._obs + self._priv:
             b.zero_()
 
+    def _buffers_for(self, sim: Dict[str, torch.Tensor]) -> HgEnvBuffers:
+        """HgEnvBuffers with every static pointer filled in, cached per set of sim tensors."""
+        key = tuple(sim[k].data_ptr() for k in _SIM_KEYS)
+        b = self._buf_cache.get(key)
+        if b is None:
+            b = HgEnvBuffers()
+            for k in _SIM_KEYS:
+                t = sim[k]
+                if not t.is_cuda:
+                    raise _lib.HgError(f"sim['{k}'] must live on the CUDA device (no CPU fallback)")
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.HgError(f"sim['{k}'] must be a contiguous float32 tensor")
+                setattr(b, k, ptr(t))
+            b.default_dof_pos, b.noise_scale_vec = ptr(self.default_dof_pos), ptr(self.noise_scale_vec)
+            for k in ("actions", "last_actions", "last_last_actions", "last_dof_vel", "last_root_vel", "feet_air_time",
+                      "last_contacts", "feet_height", "last_feet_z", "ref_dof_pos", "episode_length_buf"):
+                setattr(b, k, ptr(getattr(self, k)))
+            b.episode_sums = ptr(self.episode_sums_tensor)
+            b.rew_buf, b.reset_buf, b.time_out_buf = ptr(self.rew_buf), ptr(self.reset_buf), ptr(self.time_out_buf)
+            b.seed = self.seed
+            if len(self._buf_cache) > 64:
+                self._buf_cache.clear()
+            self._buf_cache[key] = b
+        return b
+
     def step(self, sim: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None, phases: int = ENV_PHASE_ALL,
-             obs_out: Optional[torch.Tensor] = None, priv_out: Optional[torch.Tensor] = None):
+             obs_out: Optional[torch.Tensor] = None, priv_out: Optional[torch.Tensor] = None,
+             obs16_out: Optional[torch.Tensor] = None, priv16_out: Optional[torch.Tensor] = None):
         """One fused post-physics step on the Isaac-Gym-shaped tensors in `sim` (keys: root_states, dof_state,
         contact_forces, rigid_state, commands, torques, rand_push_force, rand_push_torque, env_frictions, body_mass;
         optional `actions` [N,D] = the actions applied this step, copied into `self.actions` first).
         `noise`: N(0,1) draws [N, num_single_obs] (the reference's `randn_like`, :877) or None for in-kernel Philox.
-        `obs_out` / `priv_out`: optional destinations (e.g. the learner's storage slot) instead of the internal
-        double buffer.  Returns (obs_buf, privileged_obs_buf, rew_buf, reset_buf, time_out_buf)."""
-        _lib.require_cuda(*[v for v in sim.values() if torch.is_tensor(v)])
-        if "actions" in sim and sim["actions"] is not None:
-            self.actions.copy_(sim["actions"])
+        `obs_out` / `priv_out` (+ optional bf16 shadows `obs16_out` / `priv16_out`): destinations, e.g. the learner's
+        next storage slot, instead of the internal double buffer.
+        Returns (obs_buf, privileged_obs_buf, rew_buf, reset_buf, time_out_buf)."""
+        acts = sim.get("actions")
+        if acts is not None:
+            self.actions.copy_(acts)
         nxt = 1 - self._cur
         obs_next = obs_out if obs_out is not None else self._obs[nxt]
         priv_next = priv_out if priv_out is not None else self._priv[nxt]
-        b = HgEnvBuffers()
-        for k in ("root_states", "dof_state", "contact_forces", "rigid_state", "commands", "torques",
-                  "rand_push_force", "rand_push_torque", "env_frictions", "body_mass"):
-            t = sim[k]
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                raise _lib.HgError(f"sim['{k}'] must be a contiguous float32 tensor")
-            setattr(b, k, ptr(t))
-        b.default_dof_pos, b.noise_scale_vec = ptr(self.default_dof_pos), ptr(self.noise_scale_vec)
+        b = self._buffers_for(sim)
         b.noise = ptr(noise)
         self.step_counter += 1
-        b.seed, b.counter = self.seed, self.step_counter
-        for k in ("actions", "last_actions", "last_last_actions", "last_dof_vel", "last_root_vel", "feet_air_time",
-                  "last_contacts", "feet_height", "last_feet_z", "ref_dof_pos", "episode_length_buf"):
-            setattr(b, k, ptr(getattr(self, k)))
-        b.episode_sums = ptr(self.episode_sums_tensor)
+        b.counter = self.step_counter
         b.obs_prev, b.obs_prev_ld = ptr(self.obs_buf), self.obs_buf.stride(0)
         b.priv_prev, b.priv_prev_ld = ptr(self.privileged_obs_buf), self.privileged_obs_buf.stride(0)
         b.obs_next, b.obs_next_ld = ptr(obs_next), obs_next.stride(0)
         b.priv_next, b.priv_next_ld = ptr(priv_next), priv_next.stride(0)
-        b.rew_buf, b.reset_buf, b.time_out_buf = ptr(self.rew_buf), ptr(self.reset_buf), ptr(self.time_out_buf)
+        b.obs16_next, b.obs16_next_ld = (ptr(obs16_out), obs16_out.stride(0)) if obs16_out is not None else (0, 0)
+        b.priv16_next, b.priv16_next_ld = (ptr(priv16_out), priv16_out.stride(0)) if priv16_out is not None else (0, 0)
         b.reward_terms = ptr(self.reward_terms)
         self._c.phases = phases
-        check(_lib.load().hg_env_step(C.byref(self._c), C.byref(b), current_stream()))
+        check(self._lib.hg_env_step(C.byref(self._c), C.byref(b), current_stream()))
         if phases & 2:
             self.obs_buf, self.privileged_obs_buf = obs_next, priv_next
             if obs_out is None:
                 self._cur = nxt
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.time_out_buf
+
+
+_SIM_KEYS = ("root_states", "dof_state", "contact_forces", "rigid_state", "commands", "torques", "rand_push_force",
+             "rand_push_torque", "env_frictions", "body_mass")
 
 
 def synthetic_sim_state(cfg: XBotMathConfig, gen: torch.Generator, device, upright: bool = True,
@@ -274,6 +297,7 @@ class SyntheticXBotEnv:
         self.torch_rng_noise = torch_rng_noise
         self.extras = {}
         self._i = 0
+        self._storage = None
         self.obs_buf, self.privileged_obs_buf = self.math.obs_buf, self.math.privileged_obs_buf
         self.rew_buf, self.reset_buf = self.math.rew_buf, self.math.reset_buf
         self.episode_length_buf = self.math.episode_length_buf
@@ -281,6 +305,12 @@ class SyntheticXBotEnv:
     def set_host_pool(self, host_pool):
         """Optional: pinned-host copies of the state pool, for end-to-end timing with H2D copies per step."""
         self._host_pool = host_pool
+
+    def bind_storage(self, storage):
+        """Let `step()` write the next observations (fp32 + bf16 shadow) straight into the learner's next storage
+        slot: `PPO.act` then finds them in place and launches no ingest / copy (replaces, together with the env
+        kernel, rollout_storage.py:90-91).  Pass None to unbind."""
+        self._storage = storage
 
     def get_observations(self):
         return self.obs_buf
@@ -298,6 +328,12 @@ class SyntheticXBotEnv:
         torch.clamp(actions, -clip, clip, out=self.math.actions)    # stand-in for the pre-physics action path (:624-635)
         noise = torch.randn(self.num_envs, self.cfg.num_single_obs, device=self.device) if (
             self.torch_rng_noise and self.cfg.add_noise) else None
-        self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, to = self.math.step(sim, noise)
+        st = self._storage
+        if st is not None and st.step + 1 <= st.num_transitions_per_env:
+            o, p, o16, p16 = st.slot(st.step + 1)
+            out = self.math.step(sim, noise, obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16)
+        else:
+            out = self.math.step(sim, noise)
+        self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, to = out
         self.extras["time_outs"] = to
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras

@@ -68,6 +68,14 @@ typedef struct HgGemmProblem {
 /* block_n: 128 or 256 (UMMA N of one accumulator tile). */
 int hg_gemm_grouped(const HgGemmProblem* problems_host, int num_problems, int epilogue, int block_n, void* stream);
 
+/* The same launch with the host-side preparation (argument checks, TMA tensor-map encoding, tile schedule) done
+ * once: the rollout issues the identical three launches for every storage slot on every iteration, so the host
+ * keeps one plan per (slot, depth) and replays it with a single cheap call. */
+typedef struct HgGemmPlan HgGemmPlan;
+int hg_gemm_plan_create(const HgGemmProblem* problems_host, int num_problems, int epilogue, int block_n, HgGemmPlan** out);
+int hg_gemm_plan_run(const HgGemmPlan* plan, void* stream);
+void hg_gemm_plan_destroy(HgGemmPlan* plan);
+
 /* ------------------------------------------------------------------------------------------
  * GAE: replaces RolloutStorage.compute_returns (humanoid/algo/ppo/rollout_storage.py:122-143).
  * rewards/values/returns/advantages are [T,N] fp32, dones [T,N] uint8, last_values [N].
@@ -274,6 +282,10 @@ typedef struct HgEnvBuffers {
   const float* priv_prev; int64_t priv_prev_ld; /* [N, Fc*Sp] */
   float* obs_next; int64_t obs_next_ld;
   float* priv_next; int64_t priv_next_ld;
+  /* optional bf16 shadows of obs_next / priv_next (same values, row stride in elements): lets the env write the
+   * learner's next storage slot AND its tensor-core shadow directly, so PPO.act needs no ingest launch */
+  void* obs16_next; int64_t obs16_next_ld;
+  void* priv16_next; int64_t priv16_next_ld;
   /* outputs */
   float* rew_buf;               /* [N] */
   uint8_t* reset_buf;           /* [N] */

@@ -213,6 +213,37 @@ def test_runner_style_loop_and_api_surface():
     assert torch.equal(batches[5][0], alg.storage.observations.flatten(0, 1)[perm[N * T // 4: N * T // 2]])
 
 
+def test_bound_env_writes_storage_slots_identically():
+    """`SyntheticXBotEnv.bind_storage`: the env kernel writes obs (fp32 + bf16 shadow) straight into the next storage
+    slot.  Must be bit-identical to the generic path (env buffer -> ingest kernel) over two iterations."""
+    N, T = 256, 6
+    outs = []
+    for bound in (False, True):
+        torch.manual_seed(7)
+        env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), DEV, seed=3)
+        alg, cfg = make_alg(N, T)
+        if bound:
+            env.bind_storage(alg.storage)
+        torch.manual_seed(11)
+        obs, critic_obs = env.get_observations(), env.get_privileged_observations()
+        res = []
+        for it in range(2):
+            with torch.inference_mode():
+                for i in range(T):
+                    actions = alg.act(obs, critic_obs)
+                    obs, critic_obs, rewards, dones, infos = env.step(actions)
+                    alg.process_env_step(rewards, dones, infos)
+                alg.compute_returns(critic_obs)
+            st = alg.storage
+            res.append([t.clone() for t in (st.observations, st.privileged_observations, st.obs16, st.priv16, st.actions,
+                                            st.values, st.rewards, st.dones, st.returns, st.advantages)])
+            res.append(list(alg.update()))
+        outs.append(res)
+    for a, b in zip(outs[0], outs[1]):
+        for x, y in zip(a, b):
+            assert (torch.equal(x, y) if torch.is_tensor(x) else x == y)
+
+
 def test_checkpoint_roundtrip_and_export():
     """OnPolicyRunner.save/load (on_policy_runner.py:293-310) and export_policy_as_jit (utils/helpers.py:242-254)."""
     N, T = 64, 4
