@@ -161,8 +161,8 @@ _SIGNATURES = {
     "hg_last_error": (C.c_char_p, []),
     "hg_abi_version": (C.c_int, []),
     "hg_launch_count": (C.c_int64, []),
-    "hg_gemm_grouped": (C.c_int, [C.POINTER(HgGemmProblem), C.c_int, C.c_int, C.c_int, _P]),
-    "hg_gemm_plan_create": (C.c_int, [C.POINTER(HgGemmProblem), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "hg_gemm_grouped": (C.c_int, [C.POINTER(HgGemmProblem), C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "hg_gemm_plan_create": (C.c_int, [C.POINTER(HgGemmProblem), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "hg_gemm_plan_run": (C.c_int, [C.c_void_p, _P]),
     "hg_gemm_plan_destroy": (None, [C.c_void_p]),
     "hg_gae_returns": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
@@ -197,7 +197,7 @@ def load(auto_build: bool = True) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.hg_abi_version() != 1:
+    if lib.hg_abi_version() != 2:
         raise HgError("libhgb200.so ABI mismatch")
     _lib = lib
     return lib

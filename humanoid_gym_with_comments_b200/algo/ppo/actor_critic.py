@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ..._lib import check, current_stream, ptr
-from .engine import FlatParams, MLPEngine, NetSpec, Workspace, round_up
+from .engine import LD_ALIGN, FlatParams, MLPEngine, NetSpec, Workspace, round_up
 
 
 class ActorCritic(nn.Module):
@@ -97,14 +97,14 @@ class ActorCritic(nn.Module):
         return ws
 
     def _to_bf16(self, x: torch.Tensor, tag: str) -> torch.Tensor:
-        """fp32 [rows, cols] -> cached bf16 [rows, round_up(cols,8)] through the ingest kernel."""
+        """fp32 [rows, cols] -> cached bf16 [rows, round_up(cols,64)] through the ingest kernel."""
         _lib.require_cuda(x)
         if x.dtype != torch.float32 or x.dim() != 2:
             raise _lib.HgError("observations must be float32 [rows, features]")
         if x.stride(1) != 1:
             x = x.contiguous()
         rows, cols = x.shape
-        ld = round_up(cols, 8)
+        ld = round_up(cols, LD_ALIGN)
         buf = self._x16.get((tag, rows, ld))
         if buf is None:
             buf = torch.empty(rows, ld, dtype=torch.bfloat16, device=x.device)

@@ -24,6 +24,12 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+# Row pitch of every bf16 operand, in elements: a multiple of 64 (128 bytes) so that each 128-byte row of a TMA box
+# is exactly one L2 line.  With a merely 16-byte-aligned pitch (712 for 705 columns) the rows straddle lines and the
+# first-layer GEMMs lose ~25 % (tools/bench_gemm_ld.py).
+LD_ALIGN = 64
+
+
 class NetSpec:
     """One MLP: list of (weight, bias) Parameters, hidden layers first, output layer last."""
 
@@ -87,7 +93,7 @@ class FlatParams:
         for net in self.nets:
             for lin in net.linears[:-1]:
                 w = lin.weight
-                ld = round_up(w.shape[1], 8)
+                ld = round_up(w.shape[1], LD_ALIGN)
                 sh = torch.zeros(w.shape[0], ld, dtype=torch.bfloat16, device=dev)
                 self.w16[id(w)] = sh
                 self._shadow_list.append(HgBf16Shadow(self.offsets[id(w)], w.shape[0], w.shape[1], sh.data_ptr(), ld))
@@ -140,6 +146,8 @@ class MLPEngine:
         self.lib = _lib.load()
         self.num_sms = torch.cuda.get_device_properties(flat.device).multi_processor_count
         self._all_plans: List[int] = []
+        import os
+        self.cta_group_override = int(os.environ.get("HG_CTA_GROUP", "0"))
 
     # -- helpers ----------------------------------------------------------------------------
     @staticmethod
@@ -151,14 +159,24 @@ class MLPEngine:
             return 128
         return 256 if max(ns) >= 256 else 128
 
+    def _cta_group(self, problems: List[HgGemmProblem], epi: int = EPI_BIAS_ELU_BF16) -> int:
+        """CTA pairs (tcgen05.mma.cta_group::2, 256-row tiles) for the forward and weight-gradient launches once
+        there are enough rows to fill the machine; the dX launches (K <= 256, epilogue-bound) keep single CTAs
+        (tools/bench_gemm.py)."""
+        if self.cta_group_override:
+            return self.cta_group_override
+        if epi == EPI_DELU_BF16:
+            return 1
+        return 2 if max(p.M for p in problems) >= 8192 or max(p.K for p in problems) >= 8192 else 1
+
     def _launch(self, problems: List[HgGemmProblem], epi: int, block_n: int) -> None:
         arr = (HgGemmProblem * len(problems))(*problems)
-        check(self.lib.hg_gemm_grouped(arr, len(problems), epi, block_n, current_stream()))
+        check(self.lib.hg_gemm_grouped(arr, len(problems), epi, block_n, self._cta_group(problems, epi), current_stream()))
 
     def _plan(self, problems: List[HgGemmProblem], epi: int, block_n: int) -> int:
         arr = (HgGemmProblem * len(problems))(*problems)
         handle = C.c_void_p()
-        check(self.lib.hg_gemm_plan_create(arr, len(problems), epi, block_n, C.byref(handle)))
+        check(self.lib.hg_gemm_plan_create(arr, len(problems), epi, block_n, self._cta_group(problems, epi), C.byref(handle)))
         self._all_plans.append(handle.value)
         return handle.value
 
@@ -241,8 +259,9 @@ class MLPEngine:
                     dx_n.append(k_in)
             if dw:
                 bn = self._block_n(dw_n, "dw")
-                tiles = sum(((p.M + 127) // 128) * ((p.N + bn - 1) // bn) for p in dw)
-                splits = max(1, min((rows + 63) // 64, self.num_sms // max(tiles, 1)))
+                cg = self._cta_group(dw, EPI_ATOMIC_F32)
+                tiles = sum(((p.M + 128 * cg - 1) // (128 * cg)) * ((p.N + bn - 1) // bn) for p in dw)
+                splits = max(1, min((rows + 63) // 64, (self.num_sms // cg) // max(tiles, 1)))
                 for p in dw:
                     p.k_splits = splits
                 self._launch(dw, EPI_ATOMIC_F32, bn)

@@ -2,7 +2,7 @@
 (reference: humanoid/algo/ppo/rollout_storage.py:35-191), GAE on a CUDA scan kernel.
 
 Public tensors keep the reference's names, dtypes and [T, N, ...] shapes.  In addition the storage owns bf16,
-16-byte-row-aligned shadows of the observations (`obs16`, `priv16`: [T*N, round_up(width, 8)]) which are what
+128-byte-row-aligned shadows of the observations (`obs16`, `priv16`: [T*N, round_up(width, 64)]) which are what
 the tensor-core layers read; they are written by the same ingest kernel that fills the fp32 slot.
 """
 from __future__ import annotations
@@ -11,7 +11,7 @@ import torch
 
 from ... import _lib
 from ..._lib import check, current_stream, ptr
-from .engine import round_up
+from .engine import LD_ALIGN, round_up
 
 
 class RolloutStorage:
@@ -75,12 +75,12 @@ class RolloutStorage:
 
         # bf16 shadows for the tensor-core layers
         self.obs_cols = int(obs_shape[0])
-        self.obs_ld = round_up(self.obs_cols, 8)
+        self.obs_ld = round_up(self.obs_cols, LD_ALIGN)
         self._obs16_all = z((T + 1) * N, self.obs_ld, dtype=torch.bfloat16)
         self.obs16 = self._obs16_all[:T * N]
         if self.privileged_observations is not None:
             self.priv_cols = int(privileged_obs_shape[0])
-            self.priv_ld = round_up(self.priv_cols, 8)
+            self.priv_ld = round_up(self.priv_cols, LD_ALIGN)
             self._priv16_all = z((T + 1) * N, self.priv_ld, dtype=torch.bfloat16)
             self.priv16 = self._priv16_all[:T * N]
         else:

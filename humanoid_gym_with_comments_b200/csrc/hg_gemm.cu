@@ -28,7 +28,7 @@ constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
 #ifndef HG_EPI_WARPS
-#define HG_EPI_WARPS 16
+#define HG_EPI_WARPS 8
 #endif
 constexpr int NUM_EPI_WARPS = HG_EPI_WARPS;          // 8 or 16: 2 or 4 epilogue warps per scheduler
 constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
@@ -36,12 +36,12 @@ constexpr int EPI_COL_SPLIT = NUM_EPI_WARPS / 4;      // column slices per tile
 constexpr int EPI_TILE_FLOATS = 32 * 33;      // per-warp transpose tile of the split-K epilogue
 constexpr int MN_ATOM_BYTES = BLOCK_K * 128;  // 8192: one [64 x 64] bf16 atom
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CG>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KB
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;                 // 16 / 32 KB
+  static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;          // 8 / 16 / 32 KB (per CTA)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = (EPI == HG_EPI_ATOMIC_F32) ? NUM_EPI_WARPS * EPI_TILE_FLOATS * 4 : 0;
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_TILE_FLOATS * 4;   // per-warp transpose tiles of the epilogues
   static constexpr int STAGES = (SMEM_BUDGET - EPI_BYTES) / STAGE_BYTES;  // 3..7 deep TMA ring
   static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
   static_assert(STAGES >= 3, "pipeline too shallow");
@@ -89,6 +89,14 @@ __device__ __forceinline__ Tile decode_tile(const GroupParams& P, int t) {
   return ti;
 }
 
+// N of the MMA instruction for this tile = its valid columns rounded up to 32: a ragged last tile (N=705 -> 193,
+// the 128-wide lin-vel layer in a 256-wide tile) does not pay for columns that are all zero padding.
+template <int BLOCK_N>
+__device__ __forceinline__ int tile_n_mma(const DevProblem& q, const Tile& ti) {
+  const int n_left = q.N - ti.n_blk * BLOCK_N;
+  return n_left >= BLOCK_N ? BLOCK_N : ((n_left + 31) & ~31);
+}
+
 __device__ __forceinline__ uint64_t desc_base() {
   // version=1 (bits 46-47), layout SWIZZLE_128B=2 (bits 61-63), SBO = 1024 B (bits 32-45, >>4)
   return (uint64_t(1) << 46) | (uint64_t(2) << 61) | (uint64_t(1024 >> 4) << 32);
@@ -121,6 +129,35 @@ __device__ __forceinline__ float exp2f_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+constexpr int EPI_ROW_PITCH = 80;   // bytes per staged row: 64 B of bf16 + 16 B pad (conflict-free 16-byte accesses)
+
+// Write the warp's 32 rows x 32 columns (one row per lane, fp32 in registers) as bf16 with COALESCED global stores:
+// each lane parks its 64-byte row in the warp's shared tile, then 4 lanes cooperate on each row segment, so one
+// store instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.
+__device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* tile, int lane, __nv_bfloat16* out_col0,
+                                                long long ldo, int row_base, int M) {
+  uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const uint4 w = make_uint4(pack_bf16x2(z[j], z[j + 1]), pack_bf16x2(z[j + 2], z[j + 3]),
+                               pack_bf16x2(z[j + 4], z[j + 5]), pack_bf16x2(z[j + 6], z[j + 7]));
+    *reinterpret_cast<uint4*>(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16) = w;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), piece = lane & 3;
+    const uint4 w = *reinterpret_cast<const uint4*>(tb + r * EPI_ROW_PITCH + piece * 16);
+#ifdef HG_DBG_NOSTORE
+    if (row_base + r < M && w.x == 0x12345678u)
+#else
+    if (row_base + r < M)
+#endif
+      *(reinterpret_cast<uint4*>(out_col0 + (long long)(row_base + r) * ldo) + piece) = w;
+  }
+  __syncwarp();
 }
 
 template <int EPI>
@@ -164,53 +201,50 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float t = __uint_as_float(v[j]) + bv[j];
-      // ELU with MUFU.EX2: |err| ~ 1e-7 absolute, far below the bf16 rounding of the stored activation
 #ifdef HG_DBG_NOEXP
       z[j] = t;
 #else
+      // ELU with MUFU.EX2: |err| ~ 1e-7 absolute, far below the bf16 rounding of the stored activation
       z[j] = (EPI == HG_EPI_BIAS_ELU_BF16) ? (t > 0.f ? t : exp2f_fast(t * 1.4426950408889634f) - 1.f) : t;
 #endif
     }
-#ifdef HG_DBG_NOSTORE
-    if (row_ok && z[0] == 12345.678f) {
-#else
-    if (row_ok) {
-#endif
-      if (full) {
+    if (full) {
+      store_rows_bf16(z, tile, lane, reinterpret_cast<__nv_bfloat16*>(q.out) + n0, q.ldo, row - lane, q.M);
+    } else if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 w = make_uint4(pack_bf16x2(z[j], z[j + 1]), pack_bf16x2(z[j + 2], z[j + 3]),
-                               pack_bf16x2(z[j + 4], z[j + 5]), pack_bf16x2(z[j + 6], z[j + 7]));
-          *reinterpret_cast<uint4*>(o + j) = w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < q.N) o[j] = __float2bfloat16_rn(z[j]);
-      }
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < q.N) o[j] = __float2bfloat16_rn(z[j]);
     }
   } else if constexpr (EPI == HG_EPI_DELU_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(q.out) + (long long)row * q.ldo + n0;
     const __nv_bfloat16* a = q.act + (long long)row * q.ldact + n0;
     float d[32];
-    if (row_ok && full) {
+    if (full) {
+      // activation rows of the layer below: coalesced global -> shared (4 lanes per 64-byte row segment), then each
+      // lane reads back its own row
+      uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+      const int row_base = row - lane;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2), piece = lane & 3;
+        uint4 hv = make_uint4(0, 0, 0, 0);
+        if (row_base + r < q.M) hv = __ldg(reinterpret_cast<const uint4*>(q.act + (long long)(row_base + r) * q.ldact + n0) + piece);
+        *reinterpret_cast<uint4*>(tb + r * EPI_ROW_PITCH + piece * 16) = hv;
+      }
+      __syncwarp();
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        uint4 hw = *reinterpret_cast<const uint4*>(a + j);
-        uint32_t hv[4] = {hw.x, hw.y, hw.z, hw.w};
+        const uint4 hw = *reinterpret_cast<const uint4*>(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16);
+        const uint32_t hv[4] = {hw.x, hw.y, hw.z, hw.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float2 h = unpack_bf16x2(hv[k]);
-          d[j + 2 * k] = __uint_as_float(v[j + 2 * k]) * (h.x > 0.f ? 1.f : h.x + 1.f);
-          d[j + 2 * k + 1] = __uint_as_float(v[j + 2 * k + 1]) * (h.y > 0.f ? 1.f : h.y + 1.f);
+          const float2 h = unpack_bf16x2(hv[k]);
+          d[j + 2 * k] = row_ok ? __uint_as_float(v[j + 2 * k]) * (h.x > 0.f ? 1.f : h.x + 1.f) : 0.f;
+          d[j + 2 * k + 1] = row_ok ? __uint_as_float(v[j + 2 * k + 1]) * (h.y > 0.f ? 1.f : h.y + 1.f) : 0.f;
         }
       }
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 w = make_uint4(pack_bf16x2(d[j], d[j + 1]), pack_bf16x2(d[j + 2], d[j + 3]),
-                             pack_bf16x2(d[j + 4], d[j + 5]), pack_bf16x2(d[j + 6], d[j + 7]));
-        *reinterpret_cast<uint4*>(o + j) = w;
-      }
+      __syncwarp();
+      store_rows_bf16(d, tile, lane, reinterpret_cast<__nv_bfloat16*>(q.out) + n0, q.ldo, row_base, q.M);
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -232,26 +266,101 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
   }
 }
 
+// ------------------------------------------------------------------------------------------ cta_group helpers
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-pair rank bit of a shared::cluster address -> leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_cg(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  if constexpr (CG == 1) {
+    tma_load_2d(dst, tmap, bar, c0, c1);
+  } else {
+    // executed by both CTAs of the pair; the transaction bytes land on the LEADER's barrier (peer bit cleared)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_bf16_cg(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrive (once all earlier MMAs of this thread retired) on the barrier at the same offset in EVERY CTA of the group
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
+  if constexpr (CG == 1) {
+    umma_commit(bar);
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)0x3)
+                 : "memory");
+  }
+}
+template <int CG, int kCols>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t smem_dst) {
+  if constexpr (CG == 1) {
+    tmem_alloc<kCols>(smem_dst);
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG, int kCols>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr) {
+  if constexpr (CG == 1) {
+    tmem_dealloc<kCols>(taddr);
+  } else {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ kernel
-template <int BLOCK_N, int EPI>
+// CG = 1: one CTA per 128 x BLOCK_N tile.
+// CG = 2: a CTA pair (cluster of 2, `tcgen05.mma.cta_group::2`) per 256 x BLOCK_N tile: CTA r owns rows
+//         [128 r, 128 r + 128) of A and of the accumulator and loads only columns [r BLOCK_N/2, (r+1) BLOCK_N/2) of B;
+//         the leader CTA issues the MMAs for both, each tensor core reads the other half of B from its peer's
+//         shared memory.  Operand fill per SM drops from 16 + 32 KB to 16 + 16 KB per 128x256x64 MMA block.
+template <int BLOCK_N, int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ GroupParams P) {
-  using K = Cfg<BLOCK_N, EPI>;
+  using K = Cfg<BLOCK_N, EPI, CG>;
   constexpr int A_BYTES = K::A_BYTES, STAGE_BYTES = K::STAGE_BYTES, STAGES = K::STAGES;
+  constexpr int B_ROWS = BLOCK_N / CG;                      // rows (K-major) / columns (MN-major) of B this CTA loads
   constexpr int TMEM_COLS = 2 * BLOCK_N;                    // 256 / 512
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* full_bar = bars;                 // [STAGES]   (CG=2: only the leader's are used)
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]  (CG=2: only the leader's are used)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* epi_tiles = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const int group_id = blockIdx.x / CG;
+  const int num_groups = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < P.num_problems; ++g) {
@@ -266,64 +375,78 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), NUM_EPI_WARPS);
+      mbar_init(smem_u32(&tempty_bar[a]), CG * NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == 2) tmem_alloc_cg<CG, TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================================================================ TMA producer
+    // ================================================================ TMA producer (every CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      for (int t = group_id; t < P.total_tiles; t += num_groups) {
         const Tile ti = decode_tile(P, t);
         const DevProblem& q = P.p[ti.g];
         const void* ta = &P.tma_a[ti.g];
         const void* tb = &P.tma_b[ti.g];
+        const int m0 = (ti.m_blk * CG + rank) * BLOCK_M;
+        // CTA `rank` of a pair supplies columns [rank * n_mma/2, (rank+1) * n_mma/2) of the tile's B operand
+        const int nb0 = ti.n_blk * BLOCK_N + rank * (tile_n_mma<BLOCK_N>(q, ti) / CG);
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(fb, STAGE_BYTES);
+          if (rank == 0) mbar_arrive_expect_tx(fb, CG * STAGE_BYTES);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
           if (!q.a_mn) {
-            tma_load_2d(sa, ta, fb, kb * BLOCK_K, ti.m_blk * BLOCK_M);
+            tma_load_2d_cg<CG>(sa, ta, fb, kb * BLOCK_K, m0);
           } else {
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_2d(sa + j * MN_ATOM_BYTES, ta, fb, ti.m_blk * BLOCK_M + j * 64, kb * BLOCK_K);
+              tma_load_2d_cg<CG>(sa + j * MN_ATOM_BYTES, ta, fb, m0 + j * 64, kb * BLOCK_K);
           }
           if (!q.b_mn) {
-            tma_load_2d(sb, tb, fb, kb * BLOCK_K, ti.n_blk * BLOCK_N);
+            tma_load_2d_cg<CG>(sb, tb, fb, kb * BLOCK_K, nb0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * MN_ATOM_BYTES, tb, fb, ti.n_blk * BLOCK_N + j * 64, kb * BLOCK_K);
+            for (int j = 0; j < B_ROWS / 64; ++j)
+              tma_load_2d_cg<CG>(sb + j * MN_ATOM_BYTES, tb, fb, nb0 + j * 64, kb * BLOCK_K);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
+    // ================================================================ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      for (int t = group_id; t < P.total_tiles; t += num_groups) {
         const Tile ti = decode_tile(P, t);
         const DevProblem& q = P.p[ti.g];
         // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), majors, N>>3 at 17, M>>4 at 24
+        const int n_mma = tile_n_mma<BLOCK_N>(q, ti);
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(q.a_mn) << 15) |
-                               (uint32_t(q.b_mn) << 16) | (uint32_t(BLOCK_N >> 3) << 17) |
-                               (uint32_t(BLOCK_M >> 4) << 24);
+                               (uint32_t(q.b_mn) << 16) | (uint32_t(n_mma >> 3) << 17) |
+                               (uint32_t((BLOCK_M * CG) >> 4) << 24);
+        // Descriptors are built with 32-bit arithmetic only: the high word (SBO, version, swizzle) is a constant and the
+        // low word is (LBO << 16) | (address >> 4), advanced by a constant per 16-wide K slice -- the single issuing
+        // thread must stay far ahead of the tensor core (a 128x128x16 MMA retires in 64 clocks).
+        const uint32_t desc_hi = (uint32_t)(desc_base() >> 32);
+        const uint32_t a_lo0 = q.a_mn ? (uint32_t(MN_ATOM_BYTES >> 4) << 16) : (1u << 16);
+        const uint32_t b_lo0 = q.b_mn ? (uint32_t(MN_ATOM_BYTES >> 4) << 16) : (1u << 16);
+        const uint32_t a_step = q.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;   // MN-major: 16 k-rows; K-major: 32 B
+        const uint32_t b_step = q.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+        const int K_total = q.K;
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -332,25 +455,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
-          const int k_left = q.K - kb * BLOCK_K;
-          const int nk = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
-          for (int k = 0; k < nk; ++k) {
-            // K-major: +32 B per 16 bf16 inside the 128 B swizzle span; MN-major: +16 k-rows * 128 B
-            const uint64_t ad = q.a_mn ? desc_mnmajor(sa + k * (UMMA_K * 128)) : desc_kmajor(sa + k * (UMMA_K * 2));
-            const uint64_t bd = q.b_mn ? desc_mnmajor(sb + k * (UMMA_K * 128)) : desc_kmajor(sb + k * (UMMA_K * 2));
-            umma_bf16(d_tmem, ad, bd, idesc, accumulate);
-            accumulate = 1;
+          const uint32_t a_lo = a_lo0 | ((sa & 0x3FFFFu) >> 4);
+          const uint32_t b_lo = b_lo0 | (((sa + A_BYTES) & 0x3FFFFu) >> 4);
+          const int k_left = K_total - kb * BLOCK_K;
+          if (k_left >= BLOCK_K) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t ad = (uint64_t(desc_hi) << 32) | (a_lo + k * a_step);
+              const uint64_t bd = (uint64_t(desc_hi) << 32) | (b_lo + k * b_step);
+              umma_bf16_cg<CG>(d_tmem, ad, bd, idesc, k == 0 ? accumulate : 1u);
+            }
+          } else {
+            const int nk = (k_left + UMMA_K - 1) / UMMA_K;
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t ad = (uint64_t(desc_hi) << 32) | (a_lo + k * a_step);
+              const uint64_t bd = (uint64_t(desc_hi) << 32) | (b_lo + k * b_step);
+              umma_bf16_cg<CG>(d_tmem, ad, bd, idesc, k == 0 ? accumulate : 1u);
+            }
           }
-          umma_commit(smem_u32(&empty_bar[stage]));   // smem slot free once these MMAs retire
+          accumulate = 1;
+          umma_commit_cg<CG>(smem_u32(&empty_bar[stage]));   // smem slot free (in every CTA of the group) once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));        // accumulator complete -> epilogue
+        umma_commit_cg<CG>(smem_u32(&tfull_bar[acc]));        // accumulator complete -> epilogues
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ================================================================ epilogue: warps 4..11
+    // ================================================================ epilogue: warps 4..(4+NUM_EPI_WARPS)
     const int quad = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;          // which column slice of the tile
     constexpr int SLICE = BLOCK_N / EPI_COL_SPLIT;
@@ -358,12 +490,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     float* tile = epi_tiles + (warp - 4) * EPI_TILE_FLOATS;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+    for (int t = group_id; t < P.total_tiles; t += num_groups) {
       const Tile ti = decode_tile(P, t);
       const DevProblem& q = P.p[ti.g];
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
-      const int row = ti.m_blk * BLOCK_M + quad * 32 + lane;
+      const int row = (ti.m_blk * CG + rank) * BLOCK_M + quad * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + half * SLICE;
 #pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
@@ -376,16 +508,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (lane == 0) {
+        if constexpr (CG == 1) {
+          mbar_arrive(smem_u32(&tempty_bar[acc]));
+        } else {   // the leader's MMA thread waits for the epilogues of BOTH CTAs
+          asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];"
+                       ::"r"(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK) : "memory");
+        }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // nobody leaves while the peer may still read its shared memory / barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    tmem_dealloc_cg<CG, TMEM_COLS>(tmem_base);
   }
 }
 
@@ -424,39 +564,62 @@ static int make_tmap(CUtensorMap* m, const void* base, long long inner, long lon
   return HG_OK;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CG>
 static int launch(const GroupParams& gp, cudaStream_t stream) {
-  const int smem = Cfg<BLOCK_N, EPI>::SMEM_TOTAL;
+  const int smem = Cfg<BLOCK_N, EPI, CG>::SMEM_TOTAL;
   static bool configured = false;
   if (!configured) {
-    HG_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HG_CUDA(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int grid = gp.total_tiles < num_sms() ? gp.total_tiles : num_sms();
-  gemm_kernel<BLOCK_N, EPI><<<grid, NUM_THREADS, smem, stream>>>(gp);
+  const int max_groups = num_sms() / CG;
+  const int groups = gp.total_tiles < max_groups ? gp.total_tiles : max_groups;
+  if constexpr (CG == 1) {
+    gemm_kernel<BLOCK_N, EPI, 1><<<groups, NUM_THREADS, smem, stream>>>(gp);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(groups * CG);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HG_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, EPI, CG>, gp));
+  }
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 static int dispatch_epi(const GroupParams& gp, int epi, cudaStream_t s) {
   switch (epi) {
-    case HG_EPI_STORE_F32: return launch<BLOCK_N, HG_EPI_STORE_F32>(gp, s);
-    case HG_EPI_BIAS_ELU_BF16: return launch<BLOCK_N, HG_EPI_BIAS_ELU_BF16>(gp, s);
-    case HG_EPI_DELU_BF16: return launch<BLOCK_N, HG_EPI_DELU_BF16>(gp, s);
-    case HG_EPI_ATOMIC_F32: return launch<BLOCK_N, HG_EPI_ATOMIC_F32>(gp, s);
-    case HG_EPI_BIAS_BF16: return launch<BLOCK_N, HG_EPI_BIAS_BF16>(gp, s);
+    case HG_EPI_STORE_F32: return launch<BLOCK_N, HG_EPI_STORE_F32, CG>(gp, s);
+    case HG_EPI_BIAS_ELU_BF16: return launch<BLOCK_N, HG_EPI_BIAS_ELU_BF16, CG>(gp, s);
+    case HG_EPI_DELU_BF16: return launch<BLOCK_N, HG_EPI_DELU_BF16, CG>(gp, s);
+    case HG_EPI_ATOMIC_F32: return launch<BLOCK_N, HG_EPI_ATOMIC_F32, CG>(gp, s);
+    case HG_EPI_BIAS_BF16: return launch<BLOCK_N, HG_EPI_BIAS_BF16, CG>(gp, s);
   }
   set_error("unknown epilogue %d", epi);
   return HG_ERR_INVALID;
+}
+
+static int dispatch(const GroupParams& gp, int epi, int block_n, int cg, cudaStream_t s) {
+  if (cg == 2) return block_n == 128 ? dispatch_epi<128, 2>(gp, epi, s) : dispatch_epi<256, 2>(gp, epi, s);
+  return block_n == 128 ? dispatch_epi<128, 1>(gp, epi, s) : dispatch_epi<256, 1>(gp, epi, s);
 }
 
 }  // namespace hg
 
 namespace hg {
 // Validate the problems, encode the TMA tensor maps and lay out the tile schedule (host side, ~1 us per tensor map).
-static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_n, GroupParams& gp) {
+static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_n, int cg, GroupParams& gp) {
+  HG_CHECK(cg == 1 || cg == 2, "cta_group must be 1 or 2");
   HG_CHECK(pr != nullptr && n >= 1 && n <= HG_MAX_GROUP, "num_problems must be in [1,%d]", HG_MAX_GROUP);
   HG_CHECK(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
   HG_CHECK(epilogue >= HG_EPI_STORE_F32 && epilogue <= HG_EPI_BIAS_BF16, "unknown epilogue %d", epilogue);
@@ -478,7 +641,7 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
     int ks = h.k_splits < q.num_kb ? h.k_splits : q.num_kb;
     q.kb_per_split = (q.num_kb + ks - 1) / ks;
     q.k_splits = (q.num_kb + q.kb_per_split - 1) / q.kb_per_split;   // no empty split
-    q.tiles_m = (h.M + BLOCK_M - 1) / BLOCK_M;
+    q.tiles_m = (h.M + BLOCK_M * cg - 1) / (BLOCK_M * cg);
     q.tiles_n = (h.N + block_n - 1) / block_n;
     q.tile_begin = tiles;
     tiles += q.tiles_m * q.tiles_n * q.k_splits;
@@ -493,7 +656,7 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
     if (!q.a_mn) rc = make_tmap(&gp.tma_a[g], h.A, h.K, h.M, h.lda, BLOCK_M);
     else rc = make_tmap(&gp.tma_a[g], h.A, h.M, h.K, h.lda, BLOCK_K);
     if (rc != HG_OK) return rc;
-    if (!q.b_mn) rc = make_tmap(&gp.tma_b[g], h.B, h.K, h.N, h.ldb, block_n);
+    if (!q.b_mn) rc = make_tmap(&gp.tma_b[g], h.B, h.K, h.N, h.ldb, block_n / cg);
     else rc = make_tmap(&gp.tma_b[g], h.B, h.N, h.K, h.ldb, BLOCK_K);
     if (rc != HG_OK) return rc;
   }
@@ -504,29 +667,29 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
 
 struct HgGemmPlan {
   hg::GroupParams gp;
-  int epilogue, block_n;
+  int epilogue, block_n, cta_group;
 };
 
-extern "C" int hg_gemm_grouped(const HgGemmProblem* pr, int n, int epilogue, int block_n, void* stream) {
+extern "C" int hg_gemm_grouped(const HgGemmProblem* pr, int n, int epilogue, int block_n, int cta_group, void* stream) {
   using namespace hg;
   GroupParams gp;
-  int rc = build_params(pr, n, epilogue, block_n, gp);
+  int rc = build_params(pr, n, epilogue, block_n, cta_group, gp);
   if (rc != HG_OK) return rc;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return block_n == 128 ? dispatch_epi<128>(gp, epilogue, s) : dispatch_epi<256>(gp, epilogue, s);
+  return dispatch(gp, epilogue, block_n, cta_group, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int hg_gemm_plan_create(const HgGemmProblem* pr, int n, int epilogue, int block_n, HgGemmPlan** out) {
+extern "C" int hg_gemm_plan_create(const HgGemmProblem* pr, int n, int epilogue, int block_n, int cta_group, HgGemmPlan** out) {
   using namespace hg;
   HG_CHECK(out != nullptr, "hg_gemm_plan_create: null output");
   HgGemmPlan* plan = new HgGemmPlan();
-  int rc = build_params(pr, n, epilogue, block_n, plan->gp);
+  int rc = build_params(pr, n, epilogue, block_n, cta_group, plan->gp);
   if (rc != HG_OK) {
     delete plan;
     return rc;
   }
   plan->epilogue = epilogue;
   plan->block_n = block_n;
+  plan->cta_group = cta_group;
   *out = plan;
   return HG_OK;
 }
@@ -534,8 +697,7 @@ extern "C" int hg_gemm_plan_create(const HgGemmProblem* pr, int n, int epilogue,
 extern "C" int hg_gemm_plan_run(const HgGemmPlan* plan, void* stream) {
   using namespace hg;
   HG_CHECK(plan != nullptr, "hg_gemm_plan_run: null plan");
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return plan->block_n == 128 ? dispatch_epi<128>(plan->gp, plan->epilogue, s) : dispatch_epi<256>(plan->gp, plan->epilogue, s);
+  return dispatch(plan->gp, plan->epilogue, plan->block_n, plan->cta_group, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" void hg_gemm_plan_destroy(HgGemmPlan* plan) { delete plan; }

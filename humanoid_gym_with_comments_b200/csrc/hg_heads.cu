@@ -64,9 +64,10 @@ __device__ __forceinline__ void stage_f32(const float* __restrict__ src, int n, 
 
 // Partial dot products of one staged row with n_out weight rows, for the k-chunks owned by `sub` of `nsub`
 // cooperating lanes; reduced over the nsub lanes (nsub is a power of two <= 32, lanes are adjacent).
-template <int MAX_OUT>
+template <int MAX_OUT, bool EXACT = false>
 __device__ __forceinline__ void head_forward_row(const __nv_bfloat16* hrow, int H, const float* W, const float* b,
                                                  int n_out, int sub, int nsub, float (&out)[MAX_OUT]) {
+  // EXACT: n_out == MAX_OUT is known at compile time, so no per-output predication is generated
 #pragma unroll
   for (int a = 0; a < MAX_OUT; ++a) out[a] = 0.f;
   for (int c = sub; c < (H >> 3); c += nsub) {
@@ -81,7 +82,7 @@ __device__ __forceinline__ void head_forward_row(const __nv_bfloat16* hrow, int 
     }
 #pragma unroll
     for (int a = 0; a < MAX_OUT; ++a) {
-      if (a < n_out) {
+      if (EXACT || a < n_out) {
         const float4 w0 = *reinterpret_cast<const float4*>(W + a * H + c * 8);
         const float4 w1 = *reinterpret_cast<const float4*>(W + a * H + c * 8 + 4);
         out[a] += hf[0] * w0.x + hf[1] * w0.y + hf[2] * w0.z + hf[3] * w0.w + hf[4] * w1.x + hf[5] * w1.y +
@@ -91,7 +92,7 @@ __device__ __forceinline__ void head_forward_row(const __nv_bfloat16* hrow, int 
   }
 #pragma unroll
   for (int a = 0; a < MAX_OUT; ++a) {
-    if (a < n_out) {
+    if (EXACT || a < n_out) {
       for (int o = nsub >> 1; o > 0; o >>= 1) out[a] += __shfl_xor_sync(0xffffffffu, out[a], o);
       out[a] += b[a];
     }
@@ -196,9 +197,9 @@ struct NetSmem {
 
 // Backward of one head for the block's rows: column-parallel over the hidden index k.
 //   dH[r,k] = sum_a dOut[r,a] W[a,k];  dZ = dH * elu'(h);  gW[a,k] += dOut[r,a] h[r,k];  gb_hidden[k] += dZ[r,k]
-template <int NO>
+template <int NO, bool EXACT>
 __device__ __forceinline__ void head_backward(const HgHeadNet& net, const NetSmem& s, int row0, int valid, float* red) {
-  const int H = net.H, n_out = net.n_out, pitch = H + 8;
+  const int H = net.H, n_out = EXACT ? NO : net.n_out, pitch = H + 8;
   const int grp = threadIdx.x / 128;
   for (int k0 = 0; k0 < H; k0 += 128) {            // uniform trip count: the loop body holds block barriers
     const int k = k0 + (threadIdx.x % 128);
@@ -207,20 +208,28 @@ __device__ __forceinline__ void head_backward(const HgHeadNet& net, const NetSme
 #pragma unroll
     for (int a = 0; a < NO; ++a) {
       gw[a] = 0.f;
-      w[a] = (k_ok && a < n_out) ? s.W[a * H + k] : 0.f;
+      w[a] = (k_ok && (EXACT || a < n_out)) ? s.W[a * H + k] : 0.f;
     }
     float gbh = 0.f;
     if (k_ok) {
       for (int r = grp; r < valid; r += LH_GROUPS) {
         const float h = __bfloat162float(s.h[r * pitch + k]);
+        float dd[NO];
+        if constexpr (EXACT && (NO % 4 == 0)) {      // the row of output gradients as broadcast 16-byte loads
+#pragma unroll
+          for (int a = 0; a < NO; a += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(s.dOut + r * NO + a);
+            dd[a] = v.x; dd[a + 1] = v.y; dd[a + 2] = v.z; dd[a + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int a = 0; a < NO; ++a) dd[a] = (EXACT || a < n_out) ? s.dOut[r * n_out + a] : 0.f;
+        }
         float dh = 0.f;
 #pragma unroll
         for (int a = 0; a < NO; ++a) {
-          if (a < n_out) {
-            const float d = s.dOut[r * n_out + a];
-            dh += d * w[a];
-            gw[a] += d * h;
-          }
+          dh += dd[a] * w[a];
+          gw[a] += dd[a] * h;
         }
         const float dz = dh * (h > 0.f ? 1.f : h + 1.f);
         reinterpret_cast<__nv_bfloat16*>(net.dZ)[(long long)(row0 + r) * net.ld_dz + k] = __float2bfloat16_rn(dz);
@@ -244,17 +253,17 @@ __device__ __forceinline__ void head_backward(const HgHeadNet& net, const NetSme
       }
 #pragma unroll
       for (int a = 0; a < NO; ++a)
-        if (a < n_out) atomicAdd(net.gW + a * H + k, gw[a]);
+        if (EXACT || a < n_out) atomicAdd(net.gW + a * H + k, gw[a]);
       atomicAdd(net.gb_hidden + k, gbh);
     }
     __syncthreads();
   }
 }
 
-template <int AT>
+template <int AT, bool EXACT>
 __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_constant__ HgLossArgs L) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int A = L.A;
+  const int A = EXACT ? AT : L.A;
   const int RS = 3 * A + 8;            // per-row gathered record: actions[A] old_mu[A] old_sigma[A] logp adv ret v tgt[3] pad
   // ---- carve shared memory
   uint8_t* p = smem;
@@ -306,9 +315,9 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
   // ---- forward of the three heads + losses, LH_SUB lanes per row
   const int r = threadIdx.x / LH_SUB, sub = threadIdx.x % LH_SUB;
   float m[AT], v1[1], lv[3];
-  head_forward_row<AT>(sa.h + r * (L.actor.H + 8), L.actor.H, sa.W, sa.b, A, sub, LH_SUB, m);
-  head_forward_row<1>(sc.h + r * (L.critic.H + 8), L.critic.H, sc.W, sc.b, 1, sub, LH_SUB, v1);
-  head_forward_row<3>(sl.h + r * (L.linvel.H + 8), L.linvel.H, sl.W, sl.b, 3, sub, LH_SUB, lv);
+  head_forward_row<AT, EXACT>(sa.h + r * (L.actor.H + 8), L.actor.H, sa.W, sa.b, A, sub, LH_SUB, m);
+  head_forward_row<1, true>(sc.h + r * (L.critic.H + 8), L.critic.H, sc.W, sc.b, 1, sub, LH_SUB, v1);
+  head_forward_row<3, true>(sl.h + r * (L.linvel.H + 8), L.linvel.H, sl.W, sl.b, 3, sub, LH_SUB, lv);
 
   float st_v = 0.f, st_s = 0.f, st_l = 0.f, st_k = 0.f, st_e = 0.f;
   if (sub == 0) {
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
       float logp = 0.f, ent = 0.f, kl = 0.f;
 #pragma unroll
       for (int a = 0; a < AT; ++a) {
-        if (a < A) {
+        if (EXACT || a < A) {
           const float sd = s_std[a];
           const float d = rec[a] - m[a];
           logp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
       // -- gradients wrt mean and std
 #pragma unroll
       for (int a = 0; a < AT; ++a) {
-        if (a < A) {
+        if (EXACT || a < A) {
           const float sd = s_std[a];
           const float d = rec[a] - m[a];
           sa.dOut[r * A + a] = g_logp * d / (sd * sd);
@@ -409,9 +418,9 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
   }
 
   // ---- backward through the three output layers and the ELU below them
-  head_backward<AT>(L.actor, sa, row0, valid, s_red);
-  head_backward<1>(L.critic, sc, row0, valid, s_red);
-  head_backward<3>(L.linvel, sl, row0, valid, s_red);
+  head_backward<AT, EXACT>(L.actor, sa, row0, valid, s_red);
+  head_backward<1, true>(L.critic, sc, row0, valid, s_red);
+  head_backward<3, true>(L.linvel, sl, row0, valid, s_red);
 }
 
 static size_t loss_smem_bytes(const HgLossArgs& L, int AT) {
@@ -427,15 +436,15 @@ static size_t loss_smem_bytes(const HgLossArgs& L, int AT) {
   return t;
 }
 
-template <int AT>
+template <int AT, bool EXACT>
 static int launch_loss(const HgLossArgs& L, cudaStream_t s) {
   const size_t smem = loss_smem_bytes(L, AT);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    HG_CUDA(cudaFuncSetAttribute(ppo_head_loss_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HG_CUDA(cudaFuncSetAttribute(ppo_head_loss_kernel<AT, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  ppo_head_loss_kernel<AT><<<(L.rows + LH_ROWS - 1) / LH_ROWS, LH_THREADS, smem, s>>>(L);
+  ppo_head_loss_kernel<AT, EXACT><<<(L.rows + LH_ROWS - 1) / LH_ROWS, LH_THREADS, smem, s>>>(L);
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;
@@ -528,7 +537,9 @@ extern "C" int hg_ppo_head_loss(const HgLossArgs* L, void* stream) {
   HG_CHECK(L->actions && L->old_mu && L->old_sigma && L->old_log_prob && L->advantages && L->returns && L->old_values &&
                L->critic_obs && L->std && L->g_std && L->stats, "hg_ppo_head_loss: null pointer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (L->A <= 12) return launch_loss<12>(*L, s);
-  if (L->A <= 20) return launch_loss<20>(*L, s);
-  return launch_loss<32>(*L, s);
+  if (L->A == 12) return launch_loss<12, true>(*L, s);     // XBot-L: 12 actions
+  if (L->A == 20) return launch_loss<20, true>(*L, s);
+  if (L->A <= 12) return launch_loss<12, false>(*L, s);
+  if (L->A <= 20) return launch_loss<20, false>(*L, s);    // 18-DOF fork
+  return launch_loss<32, false>(*L, s);
 }

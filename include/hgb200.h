@@ -21,7 +21,7 @@ extern "C" {
 #define HG_ERR_INVALID (-1)
 #define HG_ERR_CUDA (-2)
 
-#define HG_ABI_VERSION 1
+#define HG_ABI_VERSION 2
 
 const char* hg_last_error(void);
 int hg_abi_version(void);
@@ -65,14 +65,18 @@ typedef struct HgGemmProblem {
   float* colsum;      /* [N] or NULL (HG_EPI_DELU_BF16) */
 } HgGemmProblem;
 
-/* block_n: 128 or 256 (UMMA N of one accumulator tile). */
-int hg_gemm_grouped(const HgGemmProblem* problems_host, int num_problems, int epilogue, int block_n, void* stream);
+/* block_n: 128 or 256 (UMMA N of one accumulator tile).
+ * cta_group: 1 = one CTA per 128 x block_n tile; 2 = a CTA pair per 256 x block_n tile (tcgen05.mma.cta_group::2:
+ * each CTA loads half of B, the pair shares it through distributed shared memory). */
+int hg_gemm_grouped(const HgGemmProblem* problems_host, int num_problems, int epilogue, int block_n, int cta_group,
+                    void* stream);
 
 /* The same launch with the host-side preparation (argument checks, TMA tensor-map encoding, tile schedule) done
  * once: the rollout issues the identical three launches for every storage slot on every iteration, so the host
  * keeps one plan per (slot, depth) and replays it with a single cheap call. */
 typedef struct HgGemmPlan HgGemmPlan;
-int hg_gemm_plan_create(const HgGemmProblem* problems_host, int num_problems, int epilogue, int block_n, HgGemmPlan** out);
+int hg_gemm_plan_create(const HgGemmProblem* problems_host, int num_problems, int epilogue, int block_n, int cta_group,
+                        HgGemmPlan** out);
 int hg_gemm_plan_run(const HgGemmPlan* plan, void* stream);
 void hg_gemm_plan_destroy(HgGemmPlan* plan);
 

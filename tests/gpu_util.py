@@ -19,9 +19,9 @@ def make_problem(A, B, out, M, N, K, a_mn=0, b_mn=0, k_splits=1, bias=None, act=
                          act=ptr(act), ldact=act.stride(0) if act is not None else 0, colsum=ptr(colsum))
 
 
-def gemm(problems, epi, block_n):
+def gemm(problems, epi, block_n, cg=1):
     arr = (HgGemmProblem * len(problems))(*problems)
-    check(_lib.load().hg_gemm_grouped(arr, len(problems), epi, block_n, current_stream()))
+    check(_lib.load().hg_gemm_grouped(arr, len(problems), epi, block_n, cg, current_stream()))
     torch.cuda.synchronize()
 
 

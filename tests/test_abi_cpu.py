@@ -30,7 +30,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hgb200.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes prototypes and header disagree"
-    assert lib.hg_abi_version() == 1
+    assert lib.hg_abi_version() == 2
     assert lib.hg_launch_count() == 0            # nothing launched on a CPU box
 
 
@@ -59,7 +59,7 @@ def test_struct_layouts_match_header_sizes():
 
 def test_argument_validation_without_gpu():
     lib = _lib.load()
-    assert lib.hg_gemm_grouped(None, 0, 0, 128, None) == -1
+    assert lib.hg_gemm_grouped(None, 0, 0, 128, 1, None) == -1
     assert b"num_problems" in lib.hg_last_error()
     assert lib.hg_gae_returns(None, None, None, None, 0.9, 0.9, 1, 1, None, None, None, None) == -1
 

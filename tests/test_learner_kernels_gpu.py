@@ -17,7 +17,7 @@ lib = _lib.load
 
 def test_ingest_and_gather():
     g = torch.Generator(device=DEV).manual_seed(0)
-    rows, cols, ld = 300, 705, 712
+    rows, cols, ld = 300, 705, 768
     src = torch.randn(rows, cols, device=DEV, generator=g)
     dst = torch.zeros(rows, cols, device=DEV)
     d16 = torch.full((rows, ld), float("nan"), dtype=torch.bfloat16, device=DEV)
@@ -160,8 +160,8 @@ def test_clip_adam_matches_torch():
         v.copy_(0.1 * torch.randn(v.shape, device=DEV, generator=g))
     ref_params = [torch.nn.Parameter(v.clone()) for v in views]
     opt = torch.optim.Adam(ref_params, lr=1e-3)
-    sh = torch.zeros(512, 712, dtype=torch.bfloat16, device=DEV)
-    shadows = (HgBf16Shadow * 1)(HgBf16Shadow(offs[1], 512, 705, sh.data_ptr(), 712))
+    sh = torch.zeros(512, 768, dtype=torch.bfloat16, device=DEV)
+    shadows = (HgBf16Shadow * 1)(HgBf16Shadow(offs[1], 512, 705, sh.data_ptr(), 768))
     opt_state = torch.zeros(8, dtype=torch.float64, device=DEV)
     opt_state[0] = 1e-3
     log = torch.zeros(3, 8, dtype=torch.float64, device=DEV)

@@ -7,6 +7,7 @@ from gpu_util import DEV, gemm, make_problem
 from humanoid_gym_with_comments_b200 import _lib
 
 M = int(os.environ.get("HG_M", 61440))
+CG = int(os.environ.get("HG_CG", 1))
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
 
 
@@ -27,7 +28,8 @@ def timeit(fn, reps=5):
 def fwd(specs, bn, m=M):
     probs, keep, fl = [], [], 0
     for N, K in specs:
-        ld = (K + 7) // 8 * 8
+        al = int(os.environ.get('HG_LD_ALIGN', 8))
+        ld = (K + al - 1) // al * al
         A, W = bf(m, ld), bf(N, ld, 0.05)
         out = torch.empty(m, N, dtype=torch.bfloat16, device=DEV)
         bias = torch.zeros(N, device=DEV)
@@ -59,11 +61,11 @@ def dw(specs, bn, splits, m=M):
 def gemm_nosync(problems, epi, bn):
     from humanoid_gym_with_comments_b200._lib import HgGemmProblem, check, current_stream
     arr = (HgGemmProblem * len(problems))(*problems)
-    check(_lib.load().hg_gemm_grouped(arr, len(problems), epi, bn, current_stream()))
+    check(_lib.load().hg_gemm_grouped(arr, len(problems), epi, bn, CG, current_stream()))
 
 
 def show(name, ms, fl):
-    print(f"{name:55s} {ms*1e3:9.1f} us  {fl/ms/1e9:8.1f} TFLOP/s", flush=True)
+    print(f"cg{CG} {name:55s} {ms*1e3:9.1f} us  {fl/ms/1e9:8.1f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":
