@@ -144,7 +144,7 @@ class HgEnvBuffers(C.Structure):
                 ("root_states", "dof_state", "contact_forces", "rigid_state", "commands", "torques",
                  "rand_push_force", "rand_push_torque", "env_frictions", "body_mass", "default_dof_pos",
                  "noise_scale_vec", "noise")] + \
-               [("seed", C.c_uint64), ("counter", C.c_uint64)] + \
+               [("seed", C.c_uint64), ("counter", C.c_uint64), ("actions_in", C.c_void_p), ("clip_actions", C.c_float)] + \
                [(n, C.c_void_p) for n in
                 ("actions", "last_actions", "last_last_actions", "last_dof_vel", "last_root_vel", "feet_air_time",
                  "last_contacts", "feet_height", "last_feet_z", "ref_dof_pos", "episode_length_buf", "episode_sums")] + \

@@ -151,12 +151,12 @@ class MLPEngine:
 
     # -- helpers ----------------------------------------------------------------------------
     @staticmethod
-    def _block_n(ns: Sequence[int], kind: str = "fwd") -> int:
+    def _block_n(ns: Sequence[int], kind: str = "fwd", rows: int = 1 << 30) -> int:
         """UMMA N of the accumulator tile, from tools/bench_gemm.py on B200: 256-wide tiles win whenever some
         problem of the group is at least 256 wide (less shared-memory traffic per MMA), except for the dX launches
         whose K is tiny and whose epilogue (ELU' + column sums) is the bound."""
-        if kind == "dx":
-            return 128
+        if kind == "dx" or rows <= 8192:
+            return 128       # rollout-sized launches: more, smaller tiles fill the 148 SMs better
         return 256 if max(ns) >= 256 else 128
 
     def _cta_group(self, problems: List[HgGemmProblem], epi: int = EPI_BIAS_ELU_BF16) -> int:
@@ -218,9 +218,9 @@ class MLPEngine:
                     bias=ptr(lin.bias.data), act=0, ldact=0, colsum=0))
                 ns.append(lin.out_features)
             if make_plans:
-                plans.append(self._plan(probs, EPI_BIAS_ELU_BF16, self._block_n(ns)))
+                plans.append(self._plan(probs, EPI_BIAS_ELU_BF16, self._block_n(ns, "fwd", rows)))
             else:
-                self._launch(probs, EPI_BIAS_ELU_BF16, self._block_n(ns))
+                self._launch(probs, EPI_BIAS_ELU_BF16, self._block_n(ns, "fwd", rows))
         return plans
 
     # -- backward of all hidden layers ----------------------------------------------------------

@@ -16,7 +16,7 @@
 
 namespace hg {
 
-constexpr int ENV_PER_BLOCK = 32;
+constexpr int ENV_PER_BLOCK = 16;       // 16 envs per block -> 256 blocks at 4096 envs (two per SM): twice the loads in flight
 constexpr int ENV_THREADS = 512;       // warps 0-3: per-env math by role; warps 4-15: history streaming
 constexpr int ENV_ROLE_WARPS = 4;
 constexpr int MAX_FRAME = 160;          // >= So, Sp for D <= 32
@@ -121,6 +121,11 @@ __device__ __forceinline__ EnvBase env_base(const HgEnvConfig& C, const HgEnvBuf
   return e;
 }
 
+// this step's applied action: either already in `actions`, or the policy's raw output clipped here
+__device__ __forceinline__ float load_action(const HgEnvBuffers& B, size_t k) {
+  return B.actions_in ? clampf(__ldg(B.actions_in + k), -B.clip_actions, B.clip_actions) : B.actions[k];
+}
+
 struct BaseFrame { Vec3 blv, bav, pg, eul; Vec3 lin, ang; float root_z; };
 
 __device__ __forceinline__ BaseFrame base_frame(const HgEnvBuffers& B, int n, bool need_euler) {
@@ -137,7 +142,7 @@ __device__ __forceinline__ BaseFrame base_frame(const HgEnvBuffers& B, int n, bo
   return f;
 }
 
-// dst[c] = clip(reset ? 0 : src[c]) for c < count, one warp, 8 independent 128-byte loads in flight per lane-iteration.
+// dst[c] = clip(reset ? 0 : src[c]) for c < count, one warp, 16 independent 128-byte loads in flight per lane-iteration.
 __device__ __forceinline__ void shift_rows(const float* __restrict__ src, float* __restrict__ dst,
                                            __nv_bfloat16* __restrict__ dst16, int count, bool reset, float clip, int lane) {
   if (reset) {
@@ -148,12 +153,23 @@ __device__ __forceinline__ void shift_rows(const float* __restrict__ src, float*
     return;
   }
   int c = lane;
-  for (; c + 7 * 32 < count; c += 8 * 32) {
-    float v[8];
+  for (; c + 15 * 32 < count; c += 16 * 32) {
+    float v[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(src + c + u * 32);
+    for (int u = 0; u < 16; ++u) v[u] = __ldg(src + c + u * 32);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 16; ++u) {
+      const float w = clampf(v[u], -clip, clip);
+      dst[c + u * 32] = w;
+      if (dst16) dst16[c + u * 32] = __float2bfloat16_rn(w);
+    }
+  }
+  for (; c + 3 * 32 < count; c += 4 * 32) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(src + c + u * 32);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
       const float w = clampf(v[u], -clip, clip);
       dst[c + u * 32] = w;
       if (dst16) dst16[c + u * 32] = __float2bfloat16_rn(w);
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * ENV_PER_BLOCK;
   const int n = n0 + lane;
-  const bool ok = n < C.num_envs;
+  const bool ok = lane < ENV_PER_BLOCK && n < C.num_envs;
   const bool doA = (C.phases & HG_ENV_PHASE_REWARD) != 0, doB = (C.phases & HG_ENV_PHASE_OBS) != 0;
   const float* cf = B.contact_forces + (size_t)n * NB * 3;
   const float* rg = B.rigid_state + (size_t)n * NB * 13;
@@ -232,7 +248,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
         for (int i = 0; i < D; ++i) {
           const float2 pv = *reinterpret_cast<const float2*>(dof + 2 * i);
           const float dflt = __ldg(B.default_dof_pos + i);
-          const float a = e.reset ? 0.f : B.actions[(size_t)n * D + i];
+          const float a = e.reset ? 0.f : load_action(B, (size_t)n * D + i);
           const int j = i - off;
           float ref = 0.f;
           if (j == 2 || j == 4) ref = sl * sc1;
@@ -269,7 +285,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
       for (int i = 0; i < D; ++i) {
         const float2 pv = *reinterpret_cast<const float2*>(dof + 2 * i);
         const size_t k = (size_t)n * D + i;
-        const float a = B.actions[k], la = B.last_actions[k], lla = B.last_last_actions[k];
+        const float a = load_action(B, k), la = B.last_actions[k], lla = B.last_last_actions[k];
         const float d1 = la - a, d2 = a + lla - 2.0f * la;
         t1 += d1 * d1; t2 += d2 * d2; t3 += fabsf(a);                           // action_smoothness :1427-1437
         const float jd = pv.x - __ldg(B.default_dof_pos + i);                    // default_joint_pos :1259-1269
@@ -433,11 +449,11 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
     const int el = i / D, d = i - el * D;
     const size_t k = (size_t)(n0 + el) * D + d;
     const bool reset = s_reset[el] != 0;
-    const float a = reset ? 0.f : B.actions[k];
+    const float a = reset ? 0.f : load_action(B, k);
     const float la = reset ? 0.f : B.last_actions[k];
     B.last_last_actions[k] = la;
     B.last_actions[k] = a;
-    if (reset) B.actions[k] = 0.f;
+    if (reset || B.actions_in) B.actions[k] = a;
     B.last_dof_vel[k] = B.dof_state[k * 2 + 1];
     const float s2 = s_s2[el];
     const float sl = s2 > 0.f ? 0.f : s2, sr = s2 < 0.f ? 0.f : s2;

@@ -51,15 +51,45 @@ __device__ __forceinline__ void stage_h(const __nv_bfloat16* __restrict__ h, lon
                                         int rows, __nv_bfloat16* sh) {
   const int chunks = H >> 3;
   const int pitch = H + 8;
-  for (int i = threadIdx.x; i < rows * chunks; i += blockDim.x) {
-    const int r = i / chunks, c = i - r * chunks;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < valid) v = __ldg(reinterpret_cast<const uint4*>(h + (long long)(row0 + r) * ld) + c);
-    *reinterpret_cast<uint4*>(sh + r * pitch + c * 8) = v;
+  const int total = rows * chunks;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {      // 4 independent 16-byte loads in flight per thread
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (i < total) {
+        const int r = i / chunks, c = i - r * chunks;
+        if (r < valid) v[u] = __ldg(reinterpret_cast<const uint4*>(h + (long long)(row0 + r) * ld) + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total) {
+        const int r = i / chunks, c = i - r * chunks;
+        *reinterpret_cast<uint4*>(sh + r * pitch + c * 8) = v[u];
+      }
+    }
   }
 }
 __device__ __forceinline__ void stage_f32(const float* __restrict__ src, int n, float* dst) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+  // 16-byte loads, all issued before the first store (independent -> one memory round trip), scalar tail
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const int n4 = n >> 2;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * blockDim.x < n4) v[u] = __ldg(reinterpret_cast<const float4*>(src) + i0 + u * blockDim.x);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * blockDim.x < n4) reinterpret_cast<float4*>(dst)[i0 + u * blockDim.x] = v[u];
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
 }
 
 // Partial dot products of one staged row with n_out weight rows, for the k-chunks owned by `sub` of `nsub`
@@ -278,6 +308,7 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
     ss[i]->dOut = reinterpret_cast<float*>(carve((size_t)LH_ROWS * nets[i]->n_out * 4));
   }
   float* s_std = reinterpret_cast<float*>(carve(MAX_A * 4));
+  float* s_c = reinterpret_cast<float*>(carve(3 * MAX_A * 4));     // [1/(2 sigma^2) | log sigma | 1/sigma] per action
   float* s_rec = reinterpret_cast<float*>(carve((size_t)LH_ROWS * RS * 4));
   float* s_gs = reinterpret_cast<float*>(carve((size_t)LH_ROWS * A * 4));          // per-row d loss / d std[a]
   float* s_stat = reinterpret_cast<float*>(carve((size_t)(LH_THREADS / 32) * 8 * 4));
@@ -294,6 +325,12 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
     stage_f32(nets[i]->b, nets[i]->n_out, ss[i]->b);
   }
   stage_f32(L.std, A, s_std);
+  if (threadIdx.x < A) {
+    const float sd = __ldg(L.std + threadIdx.x);
+    s_c[threadIdx.x] = 1.f / (2.f * sd * sd);
+    s_c[MAX_A + threadIdx.x] = logf(sd);
+    s_c[2 * MAX_A + threadIdx.x] = 1.f / sd;
+  }
   __syncthreads();
   // ---- cooperative gather of the rows' old-policy records (all loads independent -> full memory-level parallelism)
   for (int i = threadIdx.x; i < valid * RS; i += LH_THREADS) {
@@ -320,70 +357,88 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
   head_forward_row<3, true>(sl.h + r * (L.linvel.H + 8), L.linvel.H, sl.W, sl.b, 3, sub, LH_SUB, lv);
 
   float st_v = 0.f, st_s = 0.f, st_l = 0.f, st_k = 0.f, st_e = 0.f;
-  if (sub == 0) {
-    if (r < valid) {
-      const float* rec = s_rec + r * RS;
-      const float inv_rows = L.inv_world / (float)L.rows;      // 1 / (rows over all ranks)
-      // -- Gaussian log-prob, entropy, KL(old || new)   (actor_critic.py:123-138, ppo.py:165-166)
-      float logp = 0.f, ent = 0.f, kl = 0.f;
+  {
+    // The row's LH_SUB lanes split the actions (a = sub, sub+4, ...): Gaussian log-prob, entropy, KL(old || new)
+    // (actor_critic.py:123-138, ppo.py:165-166), then a 2-step shuffle reduction; lane 0 of the row finishes the
+    // scalar losses.  Per-action constants (1/(2 sigma^2), log sigma, ...) come from shared memory: no divisions
+    // by sigma in the per-row path.
+    const bool row_ok = r < valid;
+    const float* rec = s_rec + r * RS;
+    const float inv_rows = L.inv_world / (float)L.rows;      // 1 / (rows over all ranks)
+    float logp = 0.f, ent = 0.f, kl = 0.f;
 #pragma unroll
-      for (int a = 0; a < AT; ++a) {
-        if (EXACT || a < A) {
-          const float sd = s_std[a];
-          const float d = rec[a] - m[a];
-          logp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;
-          ent += HALF_LOG_2PI_PLUS_HALF + logf(sd);
-          const float osd = rec[2 * A + a];
-          const float dm = rec[A + a] - m[a];
-          kl += logf(sd / osd + 1.e-5f) + (osd * osd + dm * dm) / (2.f * sd * sd) - 0.5f;
-        }
+    for (int a = 0; a < AT; ++a) {
+      if ((EXACT || a < A) && (a % LH_SUB) == sub && row_ok) {
+        const float sd = s_std[a], i2v = s_c[a], lsd = s_c[MAX_A + a];
+        const float d = rec[a] - m[a];
+        logp += -(d * d) * i2v - lsd - LOG_SQRT_2PI;
+        ent += HALF_LOG_2PI_PLUS_HALF + lsd;
+        const float osd = rec[2 * A + a];
+        const float dm = rec[A + a] - m[a];
+        kl += logf(sd * __frcp_rn(osd) + 1.e-5f) + (osd * osd + dm * dm) * i2v - 0.5f;
       }
-      // -- clipped surrogate (ppo.py:178-184)
+    }
+#pragma unroll
+    for (int o = LH_SUB >> 1; o > 0; o >>= 1) {
+      logp += __shfl_xor_sync(0xffffffffu, logp, o);
+      ent += __shfl_xor_sync(0xffffffffu, ent, o);
+      kl += __shfl_xor_sync(0xffffffffu, kl, o);
+    }
+    float g_logp = 0.f;
+    if (row_ok) {
+      // -- clipped surrogate (ppo.py:178-184); every lane of the row computes it (needed for its actions' gradients)
       const float adv = rec[3 * A + 1];
       const float ratio = expf(logp - rec[3 * A]);
       const float s1 = -adv * ratio;
       const float s2 = -adv * fminf(fmaxf(ratio, 1.f - L.clip_param), 1.f + L.clip_param);
-      const float surr = fmaxf(s1, s2);
-      const float g_logp = (s1 >= s2 ? s1 : 0.f) * inv_rows;   // d surr / d logp  (ties: clamp passes gradient)
-      // -- value loss (ppo.py:187-194)
-      const float R = rec[3 * A + 2], v = v1[0];
-      float vl, g_v;
-      if (L.use_clipped_value_loss) {
-        const float vo = rec[3 * A + 3];
-        const float dv = v - vo;
-        const float vc = vo + fminf(fmaxf(dv, -L.clip_param), L.clip_param);
-        const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
-        const float pass = (dv >= -L.clip_param && dv <= L.clip_param) ? 1.f : 0.f;
-        vl = fmaxf(l1, l2);
-        g_v = l1 > l2 ? 2.f * (v - R) : (l1 < l2 ? 2.f * (vc - R) * pass : (v - R) + (vc - R) * pass);
-      } else {
-        vl = (R - v) * (R - v);
-        g_v = 2.f * (v - R);
-      }
-      sc.dOut[r] = L.value_loss_coef * g_v * inv_rows;
-      // -- lin-vel regression (ppo.py:205; target = critic_obs[:, 53:56], rollout_storage.py:164)
-      float lsq = 0.f;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float e = lv[j] - rec[3 * A + 4 + j];
-        lsq += e * e;
-        sl.dOut[r * 3 + j] = L.lin_vel_coef * 2.f * e * inv_rows * (1.f / 3.f);
-      }
-      // -- gradients wrt mean and std
-#pragma unroll
-      for (int a = 0; a < AT; ++a) {
-        if (EXACT || a < A) {
-          const float sd = s_std[a];
-          const float d = rec[a] - m[a];
-          sa.dOut[r * A + a] = g_logp * d / (sd * sd);
-          s_gs[r * A + a] = g_logp * (d * d / (sd * sd * sd) - 1.f / sd) - L.entropy_coef * inv_rows / sd;
+      g_logp = (s1 >= s2 ? s1 : 0.f) * inv_rows;             // d surr / d logp  (ties: clamp passes gradient)
+      if (sub == 0) {
+        st_s = fmaxf(s1, s2); st_k = kl; st_e = ent;
+        // -- value loss (ppo.py:187-194)
+        const float R = rec[3 * A + 2], v = v1[0];
+        float vl, g_v;
+        if (L.use_clipped_value_loss) {
+          const float vo = rec[3 * A + 3];
+          const float dv = v - vo;
+          const float vc = vo + fminf(fmaxf(dv, -L.clip_param), L.clip_param);
+          const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+          const float pass = (dv >= -L.clip_param && dv <= L.clip_param) ? 1.f : 0.f;
+          vl = fmaxf(l1, l2);
+          g_v = l1 > l2 ? 2.f * (v - R) : (l1 < l2 ? 2.f * (vc - R) * pass : (v - R) + (vc - R) * pass);
+        } else {
+          vl = (R - v) * (R - v);
+          g_v = 2.f * (v - R);
         }
+        st_v = vl;
+        sc.dOut[r] = L.value_loss_coef * g_v * inv_rows;
+        // -- lin-vel regression (ppo.py:205; target = critic_obs[:, 53:56], rollout_storage.py:164)
+        float lsq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float e = lv[j] - rec[3 * A + 4 + j];
+          lsq += e * e;
+          sl.dOut[r * 3 + j] = L.lin_vel_coef * 2.f * e * inv_rows * (1.f / 3.f);
+        }
+        st_l = lsq;
       }
-      st_v = vl; st_s = surr; st_l = lsq; st_k = kl; st_e = ent;
-    } else {
+    } else if (sub == 0) {
       sc.dOut[r] = 0.f;
       for (int j = 0; j < 3; ++j) sl.dOut[r * 3 + j] = 0.f;
-      for (int a = 0; a < A; ++a) { sa.dOut[r * A + a] = 0.f; s_gs[r * A + a] = 0.f; }
+    }
+    // -- gradients wrt mean and std for this lane's actions
+#pragma unroll
+    for (int a = 0; a < AT; ++a) {
+      if ((EXACT || a < A) && (a % LH_SUB) == sub) {
+        float gm = 0.f, gs = 0.f;
+        if (row_ok) {
+          const float isd = s_c[2 * MAX_A + a], ivar = 2.f * s_c[a];
+          const float d = rec[a] - m[a];
+          gm = g_logp * d * ivar;
+          gs = g_logp * (d * d * ivar * isd - isd) - L.entropy_coef * inv_rows * isd;
+        }
+        sa.dOut[r * A + a] = gm;
+        s_gs[r * A + a] = gs;
+      }
     }
   }
   // statistics: warp shuffle reduction, then one partial per warp in shared memory
@@ -431,7 +486,7 @@ static size_t loss_smem_bytes(const HgLossArgs& L, int AT) {
     t += al((size_t)LH_ROWS * (nets[i]->H + 8) * 2) + al((size_t)nets[i]->n_out * nets[i]->H * 4) +
          al((size_t)nets[i]->n_out * 4) + al((size_t)LH_ROWS * nets[i]->n_out * 4);
   }
-  t += al(MAX_A * 4) + al((size_t)LH_ROWS * (3 * L.A + 8) * 4) + al((size_t)LH_ROWS * L.A * 4) +
+  t += al(MAX_A * 4) + al(3 * MAX_A * 4) + al((size_t)LH_ROWS * (3 * L.A + 8) * 4) + al((size_t)LH_ROWS * L.A * 4) +
        al((size_t)(LH_THREADS / 32) * 8 * 4) + al((size_t)LH_ROWS * 8) + al((size_t)(LH_GROUPS - 1) * 128 * (AT + 1) * 4 + 16);
   return t;
 }

@@ -216,7 +216,8 @@ class XBotEnvMath:
 
     def step(self, sim: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None, phases: int = ENV_PHASE_ALL,
              obs_out: Optional[torch.Tensor] = None, priv_out: Optional[torch.Tensor] = None,
-             obs16_out: Optional[torch.Tensor] = None, priv16_out: Optional[torch.Tensor] = None):
+             obs16_out: Optional[torch.Tensor] = None, priv16_out: Optional[torch.Tensor] = None,
+             raw_actions: Optional[torch.Tensor] = None, clip_actions: float = 18.0):
         """One fused post-physics step on the Isaac-Gym-shaped tensors in `sim` (keys: root_states, dof_state,
         contact_forces, rigid_state, commands, torques, rand_push_force, rand_push_torque, env_frictions, body_mass;
         optional `actions` [N,D] = the actions applied this step, copied into `self.actions` first).
@@ -232,6 +233,7 @@ class XBotEnvMath:
         priv_next = priv_out if priv_out is not None else self._priv[nxt]
         b = self._buffers_for(sim)
         b.noise = ptr(noise)
+        b.actions_in, b.clip_actions = ptr(raw_actions), clip_actions   # fused clip of step() (:633-635)
         self.step_counter += 1
         b.counter = self.step_counter
         b.obs_prev, b.obs_prev_ld = ptr(self.obs_buf), self.obs_buf.stride(0)
@@ -324,16 +326,16 @@ class SyntheticXBotEnv:
     def step(self, actions):
         sim = self.pool[self._i % len(self.pool)]
         self._i += 1
-        clip = 18.0
-        torch.clamp(actions, -clip, clip, out=self.math.actions)    # stand-in for the pre-physics action path (:624-635)
+        if not (actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()):
+            actions = actions.to(self.device).float().contiguous()
         noise = torch.randn(self.num_envs, self.cfg.num_single_obs, device=self.device) if (
             self.torch_rng_noise and self.cfg.add_noise) else None
         st = self._storage
         if st is not None and st.step + 1 <= st.num_transitions_per_env:
             o, p, o16, p16 = st.slot(st.step + 1)
-            out = self.math.step(sim, noise, obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16)
+            out = self.math.step(sim, noise, obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16, raw_actions=actions)
         else:
-            out = self.math.step(sim, noise)
+            out = self.math.step(sim, noise, raw_actions=actions)   # clip(+-18) of step() (:633-635) fused in the kernel
         self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, to = out
         self.extras["time_outs"] = to
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras

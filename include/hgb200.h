@@ -269,6 +269,10 @@ typedef struct HgEnvBuffers {
   const float* noise_scale_vec; /* [So] */
   const float* noise;           /* [N,So] N(0,1) draws, or NULL -> Philox(seed, counter) */
   uint64_t seed, counter;
+  /* optional: the policy's raw actions [N,D]; when set, the kernel applies clip(+-clip_actions) itself (the clip
+   * of step(), humanoid_env.py:633-635) and stores the result in `actions` */
+  const float* actions_in;
+  float clip_actions;
   /* persistent state, updated in place */
   float* actions;               /* [N,D] in: this step's applied actions; zeroed on reset */
   float* last_actions; float* last_last_actions;   /* [N,D] */
