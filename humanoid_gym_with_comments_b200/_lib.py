@@ -156,6 +156,14 @@ class HgEnvBuffers(C.Structure):
                [(n, C.c_void_p) for n in ("rew_buf", "reset_buf", "time_out_buf", "reward_terms")]
 
 
+class HgActionArgs(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("D", C.c_int32), ("raw_actions", C.c_void_p), ("delay", C.c_void_p),
+                ("noise", C.c_void_p), ("seed", C.c_uint64), ("counter", C.c_uint64), ("dyn_rand", C.c_float),
+                ("clip_actions", C.c_float), ("action_scale", C.c_float), ("actions", C.c_void_p),
+                ("dof_state", C.c_void_p), ("p_gains", C.c_void_p), ("d_gains", C.c_void_p),
+                ("default_dof_pos", C.c_void_p), ("torque_limits", C.c_void_p), ("torques", C.c_void_p)]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     "hg_last_error": (C.c_char_p, []),
@@ -177,6 +185,7 @@ _SIGNATURES = {
     "hg_clip_adam_step": (C.c_int, [C.POINTER(HgAdamArgs), _P]),
     "hg_cast_weight_bf16": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "hg_env_step": (C.c_int, [C.POINTER(HgEnvConfig), C.POINTER(HgEnvBuffers), _P]),
+    "hg_action_torque": (C.c_int, [C.POINTER(HgActionArgs), _P]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
 
@@ -219,6 +228,15 @@ def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+_raw_stream = None
+
+
 def current_stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (fast path: one C call)."""
+    global _raw_stream
     import torch
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", False)
+    if _raw_stream:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream

@@ -87,6 +87,7 @@ class RolloutStorage:
             self.priv_cols, self.priv_ld = self.obs_cols, self.obs_ld
             self._priv16_all, self.priv16 = self._obs16_all, self.obs16
         self._gae_scratch = z(4, dtype=torch.float64)
+        self._slots = {}
 
     # ------------------------------------------------------------------ fused-path helpers (used by PPO)
     def check_room(self):
@@ -95,15 +96,20 @@ class RolloutStorage:
 
     def slot(self, step: int):
         """(obs fp32 [N,O], priv fp32 [N,P] or None, obs bf16 [N,ldO], priv bf16 [N,ldP]) of slot `step` in [0, T]."""
-        N = self.num_envs
-        return (self._obs_all[step], self._priv_all[step] if self._priv_all is not None else None,
-                self._obs16_all[step * N:(step + 1) * N], self._priv16_all[step * N:(step + 1) * N])
+        cached = self._slots.get(step)
+        if cached is None:
+            N = self.num_envs
+            cached = (self._obs_all[step], self._priv_all[step] if self._priv_all is not None else None,
+                      self._obs16_all[step * N:(step + 1) * N], self._priv16_all[step * N:(step + 1) * N])
+            self._slots[step] = cached
+        return cached
 
     def holds(self, obs: torch.Tensor, critic_obs, step: int) -> bool:
         """True if `obs` / `critic_obs` ARE slot `step` (written there, with their bf16 shadows, by a bound env)."""
-        if obs.data_ptr() != self._obs_all[step].data_ptr():
+        o, p, _, _ = self.slot(step)
+        if obs is not o and obs.data_ptr() != o.data_ptr():
             return False
-        return self._priv_all is None or critic_obs is None or critic_obs.data_ptr() == self._priv_all[step].data_ptr()
+        return p is None or critic_obs is None or critic_obs is p or critic_obs.data_ptr() == p.data_ptr()
 
     def ingest(self, obs: torch.Tensor, critic_obs, step: int):
         """Copy this step's observations into slot `step` (fp32) and its bf16 shadow rows, one launch each

@@ -87,6 +87,20 @@ __device__ __forceinline__ float env_philox_normal(uint64_t seed, uint64_t count
   return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 
+__device__ __forceinline__ float env_philox_uniform(uint64_t seed, uint64_t counter, uint32_t row) {
+  uint4 ctr = make_uint4(row, 0x0DE1A7u, (uint32_t)counter, (uint32_t)(counter >> 32));
+  uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return (ctr.x >> 8) * 5.9604644775390625e-8f;   // [0,1) with 24 bits, like torch.rand
+}
+
 // Per-env quantities every role needs (cheap, recomputed by each role's warp instead of being exchanged).
 struct EnvBase {
   long long ep;        // episode length after the increment of :780 (REWARD phase) or as stored (OBS-only launch)
@@ -504,7 +518,43 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
   }
 }
 
+__global__ void action_torque_kernel(const __grid_constant__ HgActionArgs P) {
+  const long long total = (long long)P.num_envs * P.D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / P.D), d = (int)(i - (long long)n * P.D);
+    float a = P.actions[i];
+    if (P.raw_actions) {
+      const float delay = P.delay ? __ldg(P.delay + n) : env_philox_uniform(P.seed, P.counter, (uint32_t)n);
+      a = (1.0f - delay) * __ldg(P.raw_actions + i) + delay * a;                          // :629
+      const float e = P.noise ? __ldg(P.noise + i) : env_philox_normal(P.seed, P.counter ^ 0xAC710ull, (uint32_t)n, (uint32_t)d);
+      a = a + P.dyn_rand * e * a;                                                           // :633
+      a = clampf(a, -P.clip_actions, P.clip_actions);                                       // :636
+      P.actions[i] = a;
+    }
+    if (P.torques) {
+      const float2 pv = *reinterpret_cast<const float2*>(P.dof_state + 2 * i);
+      const float lim = __ldg(P.torque_limits + d);
+      const float t = __ldg(P.p_gains + i) * (a * P.action_scale + __ldg(P.default_dof_pos + d) - pv.x) - __ldg(P.d_gains + i) * pv.y;
+      P.torques[i] = clampf(t, -lim, lim);                                                  // :921-925
+    }
+  }
+}
+
 }  // namespace hg
+
+extern "C" int hg_action_torque(const HgActionArgs* a, void* stream) {
+  using namespace hg;
+  HG_CHECK(a && a->num_envs > 0 && a->D > 0 && a->actions, "hg_action_torque: bad arguments");
+  HG_CHECK(!a->torques || (a->dof_state && a->p_gains && a->d_gains && a->default_dof_pos && a->torque_limits),
+           "hg_action_torque: the torque law needs dof_state, gains, default_dof_pos and torque_limits");
+  const long long total = (long long)a->num_envs * a->D;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  action_torque_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
+}
 
 extern "C" int hg_env_step(const HgEnvConfig* cfg, const HgEnvBuffers* buf, void* stream) {
   using namespace hg;

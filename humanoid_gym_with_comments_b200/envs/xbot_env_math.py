@@ -20,7 +20,8 @@ from typing import Dict, Optional
 import torch
 
 from .. import _lib
-from .._lib import (ENV_PHASE_ALL, HG_NUM_REWARDS, REWARD_NAMES, HgEnvBuffers, HgEnvConfig, check, current_stream, ptr)
+from .._lib import (ENV_PHASE_ALL, HG_NUM_REWARDS, REWARD_NAMES, HgActionArgs, HgEnvBuffers, HgEnvConfig, check,
+                    current_stream, ptr)
 
 # humanoid_config.py:395-430 (XBotLCfg.rewards.scales)
 XBOT_REWARD_SCALES = dict(
@@ -189,6 +190,28 @@ class XBotEnvMath:
         for b in self._obs + self._priv:
             b.zero_()
 
+    def pre_physics(self, raw_actions: Optional[torch.Tensor], dof_state: Optional[torch.Tensor] = None,
+                    p_gains: Optional[torch.Tensor] = None, d_gains: Optional[torch.Tensor] = None,
+                    torque_limits: Optional[torch.Tensor] = None, torques: Optional[torch.Tensor] = None,
+                    delay: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                    dyn_rand: float = 0.02, clip_actions: float = 18.0, action_scale: float = 0.25):
+        """The tensor math in front of the physics step, one launch: action delay mix +
+        multiplicative noise + clip into `self.actions` (`step`, humanoid_env.py:624-636) and, if `torques` is given,
+        the PD law of `_compute_torques` (:910-925).  `raw_actions=None` re-evaluates only the torques (what a real env
+        does on each of its physics sub-steps).  `delay` [N] / `noise` [N,D]: torch draws, or None for Philox."""
+        a = HgActionArgs()
+        a.num_envs, a.D = self.num_envs, self.num_dof
+        a.raw_actions, a.delay, a.noise = ptr(raw_actions), ptr(delay), ptr(noise)
+        self.step_counter += 1
+        a.seed, a.counter = self.seed, self.step_counter
+        a.dyn_rand, a.clip_actions, a.action_scale = dyn_rand, clip_actions, action_scale
+        a.actions = ptr(self.actions)
+        a.dof_state, a.p_gains, a.d_gains = ptr(dof_state), ptr(p_gains), ptr(d_gains)
+        a.default_dof_pos, a.torque_limits, a.torques = ptr(self.default_dof_pos), ptr(torque_limits), ptr(torques)
+        _lib.require_cuda(raw_actions, dof_state, p_gains, d_gains, torque_limits, torques, delay, noise)
+        check(self._lib.hg_action_torque(C.byref(a), current_stream()))
+        return self.actions, torques
+
     def _buffers_for(self, sim: Dict[str, torch.Tensor]) -> HgEnvBuffers:
         """HgEnvBuffers with every static pointer filled in, cached per set of sim tensors."""
         key = tuple(sim[k].data_ptr() for k in _SIM_KEYS)
@@ -238,10 +261,16 @@ class XBotEnvMath:
         b.counter = self.step_counter
         b.obs_prev, b.obs_prev_ld = ptr(self.obs_buf), self.obs_buf.stride(0)
         b.priv_prev, b.priv_prev_ld = ptr(self.privileged_obs_buf), self.privileged_obs_buf.stride(0)
-        b.obs_next, b.obs_next_ld = ptr(obs_next), obs_next.stride(0)
-        b.priv_next, b.priv_next_ld = ptr(priv_next), priv_next.stride(0)
-        b.obs16_next, b.obs16_next_ld = (ptr(obs16_out), obs16_out.stride(0)) if obs16_out is not None else (0, 0)
-        b.priv16_next, b.priv16_next_ld = (ptr(priv16_out), priv16_out.stride(0)) if priv16_out is not None else (0, 0)
+        b.obs_next, b.obs_next_ld = obs_next.data_ptr(), obs_next.stride(0)
+        b.priv_next, b.priv_next_ld = priv_next.data_ptr(), priv_next.stride(0)
+        if obs16_out is not None:
+            b.obs16_next, b.obs16_next_ld = obs16_out.data_ptr(), obs16_out.stride(0)
+        else:
+            b.obs16_next = 0
+        if priv16_out is not None:
+            b.priv16_next, b.priv16_next_ld = priv16_out.data_ptr(), priv16_out.stride(0)
+        else:
+            b.priv16_next = 0
         b.reward_terms = ptr(self.reward_terms)
         self._c.phases = phases
         check(self._lib.hg_env_step(C.byref(self._c), C.byref(b), current_stream()))

@@ -303,6 +303,32 @@ typedef struct HgEnvBuffers {
 
 int hg_env_step(const HgEnvConfig* cfg_host, const HgEnvBuffers* buf_host, void* stream);
 
+/* Pre-physics tensor math of XBotLFreeEnv.step (humanoid_env.py:624-635) and the PD law of _compute_torques
+ * (:910-925), the step immediately in front of the hot path, one launch:
+ *   a   = (1 - delay[n]) * raw[n,d] + delay[n] * actions[n,d]          (action delay mix, :629)
+ *   a  += dyn_rand * noise[n,d] * a                                     (multiplicative noise, :633)
+ *   actions[n,d] = clip(a, +-clip_actions)                              (:636)
+ *   torques[n,d] = clip(p_gains*(actions*action_scale + default_dof_pos[d] - dof_pos) - d_gains*dof_vel, +-torque_limits[d])
+ * delay [N] ~ U[0,1) and noise [N,D] ~ N(0,1) are given, or NULL -> in-kernel Philox4x32-10 (seed, counter).
+ * raw_actions NULL skips the action part (a real env re-evaluates only the torque law on each of its 10 physics
+ * sub-steps, :639-649).  torques NULL skips the torque part. */
+typedef struct HgActionArgs {
+  int32_t num_envs, D;
+  const float* raw_actions;    /* [N,D] policy output or NULL */
+  const float* delay;          /* [N] or NULL */
+  const float* noise;          /* [N,D] or NULL */
+  uint64_t seed, counter;
+  float dyn_rand, clip_actions, action_scale;
+  float* actions;              /* [N,D] in: previous applied actions, out: this step's */
+  const float* dof_state;      /* [N*D,2] interleaved pos, vel */
+  const float* p_gains;        /* [N,D] */
+  const float* d_gains;        /* [N,D] */
+  const float* default_dof_pos;/* [D] */
+  const float* torque_limits;  /* [D] */
+  float* torques;              /* [N,D] or NULL */
+} HgActionArgs;
+int hg_action_torque(const HgActionArgs* args_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -372,3 +372,22 @@ def synthetic_sim_state(spec: EnvSpec, N: int, gen: torch.Generator, upright: bo
         rand_push_force=0.2 * rn(N, 3), rand_push_torque=0.4 * rn(N, 3),
         env_frictions=0.1 + 1.9 * torch.rand(N, 1, generator=gen),
         body_mass=20.0 + 10.0 * torch.rand(N, 1, generator=gen))
+
+
+# ----------------------------------------------------------------------------- pre-physics math
+def mix_actions(raw_actions: torch.Tensor, prev_actions: torch.Tensor, delay: torch.Tensor, noise: torch.Tensor,
+                dyn_rand: float = 0.02, clip_actions: float = 18.0) -> torch.Tensor:
+    """`XBotLFreeEnv.step` :624-636: action delay mix with delay ~ U[0,1) [N,1], multiplicative noise with
+    noise ~ N(0,1) [N,D] (`dynamic_randomization`, humanoid_config.py domain_rand), clip.  Returns the new self.actions."""
+    actions = (1 - delay) * raw_actions + delay * prev_actions
+    actions = actions + dyn_rand * noise * actions
+    return torch.clip(actions, -clip_actions, clip_actions)
+
+
+def compute_torques(actions: torch.Tensor, dof_pos: torch.Tensor, dof_vel: torch.Tensor, p_gains: torch.Tensor,
+                    d_gains: torch.Tensor, default_dof_pos: torch.Tensor, torque_limits: torch.Tensor,
+                    action_scale: float = 0.25) -> torch.Tensor:
+    """`_compute_torques` :910-925 (PD law + clip)."""
+    actions_scaled = actions * action_scale
+    torques = p_gains * (actions_scaled + default_dof_pos - dof_pos) - d_gains * dof_vel
+    return torch.clip(torques, -torque_limits, torque_limits)

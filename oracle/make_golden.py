@@ -12,6 +12,7 @@ RNG reproducibility across machines):
                       (inputs regenerated from the seeds by `oracle.ppo_oracle.synthetic_rollout`).
   env_d12.npz / env_d18.npz   N=16, 20 consecutive steps with resets/time-outs of the reference env
                       math under the stub isaacgym: all sim inputs, noise, and obs/priv/rew/reset.
+  pre_physics_d12.npz   action delay/noise/clip (oracle) + PD torques of the reference's `_compute_torques`.
   onnx_actor_probe.npz  layer shapes + weight statistics of the reference's trained actor
                       (`humanoid/OnnxTest.onnx`), parsed with a tiny protobuf walker.
 """
@@ -265,6 +266,35 @@ def onnx_initializers(path):
     return tensors
 
 
+def torque_case(D=12, N=32, seed=9):
+    """`_compute_torques` of the reference (humanoid_env.py:910-925) bound to synthetic tensors; the action mix
+    (:624-636) is inline in `step()` and cannot run without Isaac Gym, so only its oracle restatement is stored."""
+    import types
+    cls, Cfg = rh.load_env_class(D)
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    e = types.SimpleNamespace()
+    e.cfg = Cfg()
+    e.p_gains, e.d_gains = 50 + 150 * torch.rand(N, D, generator=g), 1 + 7 * torch.rand(N, D, generator=g)
+    e.default_dof_pos = 0.3 * rn(1, D)
+    e.dof_pos, e.dof_vel = 0.5 * rn(N, D), 3.0 * rn(N, D)
+    e.torque_limits = 20 + 80 * torch.rand(D, generator=g)
+    raw, prev = 3.0 * rn(N, D), 3.0 * rn(N, D)
+    delay, noise = torch.rand(N, 1, generator=g), rn(N, D)
+    actions = eo.mix_actions(raw, prev, delay, noise, e.cfg.domain_rand.dynamic_randomization, e.cfg.normalization.clip_actions)
+    want = cls._compute_torques(e, actions)
+    got = eo.compute_torques(actions, e.dof_pos, e.dof_vel, e.p_gains, e.d_gains, e.default_dof_pos, e.torque_limits,
+                             e.cfg.control.action_scale)
+    assert torch.equal(want, got)
+    assert float((want.abs() == e.torque_limits).float().mean()) > 0.01      # the clip is exercised
+    out = dict(D=D, N=N, raw=_np(raw), prev=_np(prev), delay=_np(delay), noise=_np(noise), actions=_np(actions),
+               p_gains=_np(e.p_gains), d_gains=_np(e.d_gains), default_dof_pos=_np(e.default_dof_pos), dof_pos=_np(e.dof_pos),
+               dof_vel=_np(e.dof_vel), torque_limits=_np(e.torque_limits), torques=_np(want),
+               dyn_rand=np.array(e.cfg.domain_rand.dynamic_randomization), clip_actions=np.array(e.cfg.normalization.clip_actions),
+               action_scale=np.array(e.cfg.control.action_scale))
+    return out, dict(clipped_fraction=float((want.abs() == e.torque_limits).float().mean()))
+
+
 def onnx_probe():
     path = os.path.join(rh.REF_ROOT, "humanoid", "OnnxTest.onnx")
     ts = onnx_initializers(path)
@@ -296,6 +326,8 @@ def main():
     for D in (12, 18):
         d, rep = env_case(D)
         save(f"env_d{D}.npz", d, rep)
+    d, rep = torque_case()
+    save("pre_physics_d12.npz", d, rep)
     d, rep = onnx_probe()
     save("onnx_actor_probe.npz", d, rep)
     json.dump(manifest, open(os.path.join(GOLD, "MANIFEST.json"), "w"), indent=1, sort_keys=True)

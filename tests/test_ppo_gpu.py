@@ -171,6 +171,35 @@ def test_config2_iteration_vs_oracle():
     assert alg.learning_rate == pytest.approx(olr, rel=1e-12)
 
 
+def test_shipped_18dof_layout_update_vs_oracle():
+    """The shipped fork's shapes: 18 actions, obs 975 = 15x65, priv 291 = 3x97; the lin-vel target is still
+    the hard-coded critic_obs[:, 53:56] (rollout_storage.py:164).  One update on an identical rollout buffer."""
+    N, T, O, P, A = 32, 16, 975, 291, 18
+    alg, cfg = make_alg(N, T, num_obs=O, num_priv=P, A=A)
+    torch.manual_seed(0)
+    p = po.init_params(O, P, A, NETS["actor_hidden_dims"], NETS["critic_hidden_dims"], (128, 128), 1.0)
+    sd = alg.actor_critic.state_dict()
+    assert all(torch.equal(sd[k].cpu(), p[k]) for k in sd)
+    gen = torch.Generator().manual_seed(3)
+    ro, last_c, _ = po.synthetic_rollout(p, N, T, O, P, A, cfg, gen)
+    st = alg.storage
+    for t in range(T):
+        st.ingest(ro.observations[t].to(DEV), ro.privileged_observations[t].to(DEV), t)
+    for name in ("actions", "rewards", "dones", "values", "actions_log_prob", "mu", "sigma", "returns", "advantages"):
+        getattr(st, name).copy_(getattr(ro, name).to(DEV))
+    perm = torch.randperm(N * T, generator=gen)
+    alg.perm_override = perm.to(DEV)
+    rec = []
+    ov, os_, olv, olr = po.ppo_update(p, po.AdamState(), ro, perm, cfg, cfg.learning_rate, record=rec)
+    v, s, _, lv = alg.update()
+    log = alg.last_update_log.numpy()
+    for i, r in enumerate(rec):
+        assert rel(log[i, 0], r["value"]) <= 3e-3 and rel(log[i, 2], r["lin_vel"]) <= 3e-3, (i, log[i], r)
+        assert abs(log[i, 1] - r["surrogate"]) <= 3e-3 and rel(log[i, 4], r["entropy"]) <= 1e-5
+        assert log[i, 5] == pytest.approx(r["lr"], rel=1e-12)
+    assert rel(v, ov) <= 2e-3 and rel(lv, olv) <= 2e-3 and abs(s - os_) <= 3e-3
+
+
 def test_runner_style_loop_and_api_surface():
     """The call pattern of OnPolicyRunner.learn (on_policy_runner.py:125-168) against a synthetic VecEnv."""
     N, T = 512, 8

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi.txt 2>&1
 files="$@"
-[ -z "$files" ] && files="tests/test_gemm_gpu.py tests/test_gae_gpu.py tests/test_env_gpu.py tests/test_learner_kernels_gpu.py tests/test_ppo_gpu.py"
+[ -z "$files" ] && files="tests/test_gemm_gpu.py tests/test_gae_gpu.py tests/test_env_gpu.py tests/test_learner_kernels_gpu.py tests/test_pre_physics.py tests/test_ppo_gpu.py"
 rc_all=0
 for f in $files; do
   log=gpurun_out/$(basename $f .py).log
