@@ -329,13 +329,58 @@ class SyntheticXBotEnv:
         self.extras = {}
         self._i = 0
         self._storage = None
+        self._host_pool = None
         self.obs_buf, self.privileged_obs_buf = self.math.obs_buf, self.math.privileged_obs_buf
         self.rew_buf, self.reset_buf = self.math.rew_buf, self.math.reset_buf
         self.episode_length_buf = self.math.episode_length_buf
 
-    def set_host_pool(self, host_pool):
-        """Optional: pinned-host copies of the state pool, for end-to-end timing with H2D copies per step."""
-        self._host_pool = host_pool
+    def stream_states_from_host(self, enable: bool = True, depth: int = 64):
+        """End-to-end mode: the Isaac-Gym-shaped state of EVERY step arrives from pinned host memory (as it would from
+        an external simulator).  Copies run on a side stream up to `depth` steps ahead of the consumer (a ring of
+        `depth` device staging sets, 4.4 MB each at 4096 envs), so they also overlap the learner's update;
+        `step()` waits on its set's copy event before launching the env kernel."""
+        if not enable:
+            if self._host_pool is not None:
+                torch.cuda.current_stream().wait_stream(self._copy_stream)
+            self._host_pool = None
+            return
+        # every state set is ONE packed buffer (tensors are 256-byte aligned views into it): one copy per step
+        keys = list(self.pool[0].keys())
+        offs, total = {}, 0
+        for k in keys:
+            offs[k] = total
+            total += (self.pool[0][k].numel() + 63) // 64 * 64
+        self._packed_floats = total
+
+        def views(buf):
+            return {k: buf[offs[k]:offs[k] + self.pool[0][k].numel()].view(self.pool[0][k].shape) for k in keys}
+
+        self._host_pool = []
+        for s_ in self.pool:
+            hb = torch.empty(total, dtype=torch.float32).pin_memory()
+            for k, v in views(hb).items():
+                v.copy_(s_[k])
+            self._host_pool.append(hb)
+        self._depth = depth
+        self._stage_buf = [torch.empty(total, dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self._stage = [views(b) for b in self._stage_buf]
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._copy_done = [torch.cuda.Event() for _ in range(depth)]
+        self._consumed = [torch.cuda.Event() for _ in range(depth)]
+        self.h2d_bytes_per_step = total * 4
+        self._next_prefetch = self._i
+        self._prefetch_upto(self._i + depth)
+
+    def _prefetch_upto(self, end):
+        with torch.cuda.stream(self._copy_stream):
+            while self._next_prefetch < end:
+                i = self._next_prefetch
+                slot = i % self._depth
+                src = self._host_pool[i % len(self._host_pool)]
+                self._copy_stream.wait_event(self._consumed[slot])  # the env kernel that last read this set has finished
+                self._stage_buf[slot].copy_(src, non_blocking=True)
+                self._copy_done[slot].record(self._copy_stream)
+                self._next_prefetch += 1
 
     def bind_storage(self, storage):
         """Let `step()` write the next observations (fp32 + bf16 shadow) straight into the learner's next storage
@@ -353,7 +398,13 @@ class SyntheticXBotEnv:
         return self.obs_buf, self.privileged_obs_buf
 
     def step(self, actions):
-        sim = self.pool[self._i % len(self.pool)]
+        if getattr(self, "_host_pool", None) is not None:
+            slot = self._i % self._depth
+            torch.cuda.current_stream().wait_event(self._copy_done[slot])
+            sim = self._stage[slot]
+        else:
+            slot = None
+            sim = self.pool[self._i % len(self.pool)]
         self._i += 1
         if not (actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()):
             actions = actions.to(self.device).float().contiguous()
@@ -365,6 +416,9 @@ class SyntheticXBotEnv:
             out = self.math.step(sim, noise, obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16, raw_actions=actions)
         else:
             out = self.math.step(sim, noise, raw_actions=actions)   # clip(+-18) of step() (:633-635) fused in the kernel
+        if slot is not None:
+            self._consumed[slot].record(torch.cuda.current_stream())
+            self._prefetch_upto(self._i + self._depth)      # refill the set just consumed (one step, far ahead)
         self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, to = out
         self.extras["time_outs"] = to
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras
