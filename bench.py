@@ -75,6 +75,8 @@ class ClockSampler:
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
+        if os.environ.get("HG_NO_CLOCK_SAMPLER"):      # experiments only: never set for a reported number
+            return
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libhgb200.so")
+LIB_PATH = os.environ.get("HG_LIB_PATH") or os.path.join(HERE, "libhgb200.so")   # HG_LIB_PATH: kernel-variant experiments (tools/build_variant.sh)
 BUILD_DIR = os.path.join(HERE, "csrc", "_build")
 SOURCES = ["hg_runtime.cu", "hg_gemm.cu", "hg_gae.cu", "hg_misc.cu", "hg_heads.cu", "hg_optim.cu", "hg_env.cu"]
 EXTRA_FLAGS = {"hg_env.cu": ["-fmad=false"]}

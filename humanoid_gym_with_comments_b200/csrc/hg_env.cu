@@ -203,6 +203,8 @@ __device__ __forceinline__ void shift_rows(const float* __restrict__ src, float*
 __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_constant__ HgEnvConfig C,
                                                                const __grid_constant__ HgEnvBuffers B) {
   extern __shared__ __align__(16) float s_env[];
+  pdl_trigger();
+  pdl_wait();
   const int D = C.D, NB = C.num_bodies, off = C.leg_offset;
   const int So = 11 + 3 * D, Sp = 25 + 4 * D;
   float* s_fobs = s_env;                              // [ENV_PER_BLOCK][So]
@@ -519,6 +521,8 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
 }
 
 __global__ void action_torque_kernel(const __grid_constant__ HgActionArgs P) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)P.num_envs * P.D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i / P.D), d = (int)(i - (long long)n * P.D);
@@ -550,7 +554,7 @@ extern "C" int hg_action_torque(const HgActionArgs* a, void* stream) {
   const long long total = (long long)a->num_envs * a->D;
   int blocks = (int)((total + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  action_torque_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+  HG_CUDA(launch_kernel(action_torque_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, *a));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;
@@ -577,7 +581,7 @@ extern "C" int hg_env_step(const HgEnvConfig* cfg, const HgEnvBuffers* buf, void
   const int blocks = (cfg->num_envs + ENV_PER_BLOCK - 1) / ENV_PER_BLOCK;
   const int So = 11 + 3 * cfg->D, Sp = 25 + 4 * cfg->D;
   const size_t smem = (size_t)(ENV_PER_BLOCK * (So + Sp) + HG_NUM_REWARDS * ENV_PER_BLOCK + 4 * ENV_PER_BLOCK) * 4;
-  env_step_kernel<<<blocks, ENV_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *buf);
+  HG_CUDA(launch_kernel(env_step_kernel, dim3(blocks), dim3(ENV_THREADS), smem, reinterpret_cast<cudaStream_t>(stream), 1, *cfg, *buf));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;

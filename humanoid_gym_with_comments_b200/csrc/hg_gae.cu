@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(GAE_THREADS) gae_scan_kernel(const float* __re
                                                                const float* __restrict__ last_values, float gamma,
                                                                float lam, int T, int N, float* __restrict__ returns,
                                                                float* __restrict__ adv_raw, double* scratch) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_r[GAE_CHUNK][GAE_THREADS];
   __shared__ float s_v[GAE_CHUNK][GAE_THREADS];
   __shared__ uint8_t s_d[GAE_CHUNK][GAE_THREADS];
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__(GAE_THREADS) gae_scan_kernel(const float* __re
 }
 
 __global__ void gae_normalise_kernel(float* __restrict__ adv, long long count, const double* __restrict__ scratch) {
+  pdl_trigger();
+  pdl_wait();
   const double n = (double)count;
   const double mean_d = scratch[0] / n;
   double var = (scratch[1] - scratch[0] * mean_d) / (n - 1.0);   // unbiased (torch.std default)
@@ -120,15 +124,14 @@ extern "C" int hg_gae_returns(const float* rewards, const float* values, const u
   HG_CHECK((reinterpret_cast<uintptr_t>(advantages) & 15) == 0, "advantages must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   HG_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), s));
-  gae_scan_kernel<<<(N + GAE_THREADS - 1) / GAE_THREADS, GAE_THREADS, 0, s>>>(rewards, values, dones, last_values, gamma,
-                                                                               lam, T, N, returns, advantages, scratch);
+  HG_CUDA(launch_kernel(gae_scan_kernel, dim3((N + GAE_THREADS - 1) / GAE_THREADS), dim3(GAE_THREADS), 0, s, 1, rewards, values, dones, last_values, gamma, lam, T, N, returns, advantages, scratch));
   HG_LAUNCH_CHECK();
   const long long count = (long long)T * N;
   long long blocks = (count / 4 + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  gae_normalise_kernel<<<(int)blocks, 256, 0, s>>>(advantages, count, scratch);
+  HG_CUDA(launch_kernel(gae_normalise_kernel, dim3((int)blocks), dim3(256), 0, s, 1, advantages, count, scratch));
   HG_LAUNCH_CHECK();
   count_launch(2);
   return HG_OK;

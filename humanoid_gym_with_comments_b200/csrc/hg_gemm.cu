@@ -160,8 +160,21 @@ __device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* til
   __syncwarp();
 }
 
+// Activation rows of the layer below for one 32x32 chunk, in the coalesced pattern of store_rows_bf16 (4 lanes per
+// 64-byte row segment).  Issued BEFORE the accumulator barrier so the HBM latency hides behind the tile's main loop.
+__device__ __forceinline__ void prefetch_act(const DevProblem& q, int row_base, int n0, int lane, uint4 (&pre)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), piece = lane & 3;
+    pre[i] = make_uint4(0, 0, 0, 0);
+    if (n0 + 32 <= q.N && row_base + r < q.M)
+      pre[i] = __ldg(reinterpret_cast<const uint4*>(q.act + (long long)(row_base + r) * q.ldact + n0) + piece);
+  }
+}
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int n0, uint32_t (&v)[32], int lane, float* tile) {
+__device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int n0, uint32_t (&v)[32], int lane, float* tile,
+                                               const uint4 (&pre)[4]) {
   const bool row_ok = row < q.M;
   const bool full = (n0 + 32 <= q.N);
   if constexpr (EPI == HG_EPI_STORE_F32) {
@@ -227,9 +240,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + (lane >> 2), piece = lane & 3;
-        uint4 hv = make_uint4(0, 0, 0, 0);
-        if (row_base + r < q.M) hv = __ldg(reinterpret_cast<const uint4*>(q.act + (long long)(row_base + r) * q.ldact + n0) + piece);
-        *reinterpret_cast<uint4*>(tb + r * EPI_ROW_PITCH + piece * 16) = hv;
+        *reinterpret_cast<uint4*>(tb + r * EPI_ROW_PITCH + piece * 16) = pre[i];
       }
       __syncwarp();
 #pragma unroll
@@ -356,6 +367,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* epi_tiles = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
@@ -381,6 +393,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   }
   if (warp == 2) tmem_alloc_cg<CG, TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before();
+  pdl_wait();          // everything above is on-chip set-up; operands, bias, act and outputs are touched only below
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();   // peer's barriers are initialised before anything signals them
   tc_fence_after();
@@ -493,18 +506,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     for (int t = group_id; t < P.total_tiles; t += num_groups) {
       const Tile ti = decode_tile(P, t);
       const DevProblem& q = P.p[ti.g];
+      const int row = (ti.m_blk * CG + rank) * BLOCK_M + quad * 32 + lane;
+      uint4 pre[EPI == HG_EPI_DELU_BF16 ? CHUNKS : 1][4];
+      if constexpr (EPI == HG_EPI_DELU_BF16) {
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c)
+          prefetch_act(q, row - lane, ti.n_blk * BLOCK_N + half * SLICE + c * 32, lane, pre[c]);
+      }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
-      const int row = (ti.m_blk * CG + rank) * BLOCK_M + quad * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + half * SLICE;
 #pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
         const int n0 = ti.n_blk * BLOCK_N + half * SLICE + c * 32;
         if (n0 >= q.N) break;
         uint32_t v[32];
+#ifdef HG_DBG_EPI_NOLD
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0;
+#else
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(q, row, n0, v, lane, tile);
+#endif
+#ifdef HG_DBG_EPI_NONE
+#pragma unroll
+        for (int j = 0; j < 32; ++j) asm volatile("" ::"r"(v[j]));
+#else
+        epilogue_chunk<EPI>(q, row, n0, v, lane, tile, pre[EPI == HG_EPI_DELU_BF16 ? c : 0]);
+#endif
       }
       tc_fence_before();
       __syncwarp();
@@ -574,23 +603,7 @@ static int launch(const GroupParams& gp, cudaStream_t stream) {
   }
   const int max_groups = num_sms() / CG;
   const int groups = gp.total_tiles < max_groups ? gp.total_tiles : max_groups;
-  if constexpr (CG == 1) {
-    gemm_kernel<BLOCK_N, EPI, 1><<<groups, NUM_THREADS, smem, stream>>>(gp);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(groups * CG);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    HG_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, EPI, CG>, gp));
-  }
+  HG_CUDA(launch_kernel(gemm_kernel<BLOCK_N, EPI, CG>, dim3(groups * CG), dim3(NUM_THREADS), smem, stream, CG, gp));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;

@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(RH_ROWS* RH_SUB)
                                const float* __restrict__ eps, uint64_t seed, uint64_t counter, int n, int A,
                                float* __restrict__ actions, float* __restrict__ mu, float* __restrict__ sigma,
                                float* __restrict__ log_prob, float* __restrict__ values) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   float* sWa = reinterpret_cast<float*>(smem);                 // [A][H_a]
   float* sWc = sWa + A * H_a;                                  // [H_c]
@@ -192,6 +194,8 @@ __global__ void __launch_bounds__(RH_ROWS* RH_SUB)
 __global__ void __launch_bounds__(RH_ROWS* RH_SUB)
     head_forward_kernel(const __nv_bfloat16* __restrict__ h, long long ld_h, int H, const float* __restrict__ W,
                         const float* __restrict__ b, int n_out, int n, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   float* sW = reinterpret_cast<float*>(smem);                  // [n_out][H]
   float* sb = sW + n_out * H;                                  // [MAX_A]
@@ -292,6 +296,8 @@ __device__ __forceinline__ void head_backward(const HgHeadNet& net, const NetSme
 
 template <int AT, bool EXACT>
 __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_constant__ HgLossArgs L) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   const int A = EXACT ? AT : L.A;
   const int RS = 3 * A + 8;            // per-row gathered record: actions[A] old_mu[A] old_sigma[A] logp adv ret v tgt[3] pad
@@ -499,7 +505,7 @@ static int launch_loss(const HgLossArgs& L, cudaStream_t s) {
     HG_CUDA(cudaFuncSetAttribute(ppo_head_loss_kernel<AT, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  ppo_head_loss_kernel<AT, EXACT><<<(L.rows + LH_ROWS - 1) / LH_ROWS, LH_THREADS, smem, s>>>(L);
+  HG_CUDA(launch_kernel(ppo_head_loss_kernel<AT, EXACT>, dim3((L.rows + LH_ROWS - 1) / LH_ROWS), dim3(LH_THREADS), smem, s, 1, L));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;
@@ -516,10 +522,7 @@ static int launch_rollout(const void* h_actor, int64_t ld_ha, int H_a, const flo
     HG_CUDA(cudaFuncSetAttribute(policy_head_rollout_kernel<AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  policy_head_rollout_kernel<AT><<<(n + RH_ROWS - 1) / RH_ROWS, RH_ROWS * RH_SUB, smem, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(h_actor), ld_ha, H_a, W_a, b_a, std,
-      reinterpret_cast<const __nv_bfloat16*>(h_critic), ld_hc, H_c, W_c, b_c, eps, seed, counter, n, A, actions, mu,
-      sigma, log_prob, values);
+  HG_CUDA(launch_kernel(policy_head_rollout_kernel<AT>, dim3((n + RH_ROWS - 1) / RH_ROWS), dim3(RH_ROWS * RH_SUB), smem, s, 1, reinterpret_cast<const __nv_bfloat16*>(h_actor), ld_ha, H_a, W_a, b_a, std, reinterpret_cast<const __nv_bfloat16*>(h_critic), ld_hc, H_c, W_c, b_c, eps, seed, counter, n, A, actions, mu, sigma, log_prob, values));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;
@@ -571,8 +574,7 @@ extern "C" int hg_head_forward(const void* h, int64_t ld_h, int H, const float* 
     HG_CUDA(cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  head_forward_kernel<<<(n + RH_ROWS - 1) / RH_ROWS, RH_ROWS * RH_SUB, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(h), ld_h, H, W, b, n_out, n, out);
+  HG_CUDA(launch_kernel(head_forward_kernel, dim3((n + RH_ROWS - 1) / RH_ROWS), dim3(RH_ROWS * RH_SUB), smem, reinterpret_cast<cudaStream_t>(stream), 1, reinterpret_cast<const __nv_bfloat16*>(h), ld_h, H, W, b, n_out, n, out));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;

@@ -9,6 +9,8 @@ namespace hg {
 __global__ void ingest_rows_kernel(const float* __restrict__ src, long long src_ld, int rows, int cols,
                                    float* __restrict__ dst, long long dst_ld, __nv_bfloat16* __restrict__ dst16,
                                    long long ld16) {
+  pdl_trigger();
+  pdl_wait();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
@@ -30,6 +32,8 @@ __global__ void ingest_rows_kernel(const float* __restrict__ src, long long src_
 // One warp per destination row, 16-byte chunks.
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, int chunks_per_row, const long long* __restrict__ idx,
                                    int rows, uint4* __restrict__ dst) {
+  pdl_trigger();
+  pdl_wait();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
@@ -41,6 +45,8 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ src, int chunks_per
 
 __global__ void cast_weight_kernel(const float* __restrict__ src, int rows, int cols, __nv_bfloat16* __restrict__ dst,
                                    long long ld) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)rows * ld;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / ld), c = (int)(i % ld);
@@ -52,6 +58,8 @@ __global__ void cast_weight_kernel(const float* __restrict__ src, int rows, int 
 __global__ void store_rewards_dones_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                                            const uint8_t* __restrict__ time_outs, const uint8_t* __restrict__ dones,
                                            float gamma, int n, float* __restrict__ out_r, uint8_t* __restrict__ out_d) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float r = rewards[i];
@@ -74,8 +82,7 @@ extern "C" int hg_ingest_rows(const float* src, int64_t src_ld, int rows, int co
   HG_CHECK(src && dst_bf16 && rows > 0 && cols > 0, "hg_ingest_rows: bad arguments");
   HG_CHECK(ld16 >= cols && ld16 % 8 == 0, "hg_ingest_rows: ld16 must be >= cols and a multiple of 8");
   HG_CHECK((reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0, "hg_ingest_rows: bf16 destination alignment");
-  ingest_rows_kernel<<<row_grid(rows, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, src_ld, rows, cols, dst_f32, dst_ld, reinterpret_cast<__nv_bfloat16*>(dst_bf16), ld16);
+  HG_CUDA(launch_kernel(ingest_rows_kernel, dim3(row_grid(rows, 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, src, src_ld, rows, cols, dst_f32, dst_ld, reinterpret_cast<__nv_bfloat16*>(dst_bf16), ld16));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;
@@ -86,9 +93,7 @@ extern "C" int hg_gather_rows_bf16(const void* src, int64_t ld, const int64_t* i
   HG_CHECK(src && idx && dst && rows > 0, "hg_gather_rows_bf16: bad arguments");
   HG_CHECK(ld % 8 == 0, "hg_gather_rows_bf16: ld must be a multiple of 8");
   HG_CHECK(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "hg_gather_rows_bf16: alignment");
-  gather_rows_kernel<<<row_grid(rows, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const uint4*>(src), (int)(ld / 8), reinterpret_cast<const long long*>(idx), rows,
-      reinterpret_cast<uint4*>(dst));
+  HG_CUDA(launch_kernel(gather_rows_kernel, dim3(row_grid(rows, 8)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, reinterpret_cast<const uint4*>(src), (int)(ld / 8), reinterpret_cast<const long long*>(idx), rows, reinterpret_cast<uint4*>(dst)));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;
@@ -100,8 +105,7 @@ extern "C" int hg_cast_weight_bf16(const float* src, int rows, int cols, void* d
   const long long total = (long long)rows * ld;
   int blocks = (int)((total + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  cast_weight_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, rows, cols, reinterpret_cast<__nv_bfloat16*>(dst), ld);
+  HG_CUDA(launch_kernel(cast_weight_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, src, rows, cols, reinterpret_cast<__nv_bfloat16*>(dst), ld));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;
@@ -112,8 +116,7 @@ extern "C" int hg_store_rewards_dones(const float* rewards, const float* values,
                                       void* stream) {
   using namespace hg;
   HG_CHECK(rewards && values && dones && out_rewards && out_dones && n > 0, "hg_store_rewards_dones: bad arguments");
-  store_rewards_dones_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      rewards, values, time_outs, dones, gamma, n, out_rewards, out_dones);
+  HG_CUDA(launch_kernel(store_rewards_dones_kernel, dim3((n + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, rewards, values, time_outs, dones, gamma, n, out_rewards, out_dones));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;

@@ -13,6 +13,8 @@ struct ShadowTable {
 };
 
 __global__ void grad_sumsq_kernel(const float* __restrict__ g, long long count, double* opt_state) {
+  pdl_trigger();
+  pdl_wait();
   double acc = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
@@ -33,6 +35,8 @@ __global__ void grad_sumsq_kernel(const float* __restrict__ g, long long count, 
 
 // One thread: everything the reference does on the host between backward() and optimizer.step().
 __global__ void opt_scalars_kernel(HgAdamArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const float* stats = a.grads + a.count;
   const double rows = (double)a.rows_global;
   double lr = a.opt_state[0];
@@ -68,6 +72,8 @@ __global__ void opt_scalars_kernel(HgAdamArgs a) {
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(HgAdamArgs a, const __grid_constant__ ShadowTable tab) {
+  pdl_trigger();
+  pdl_wait();
   const float coef = (float)a.opt_state[3];
   const float step_size = (float)a.opt_state[4];
   const float bc2_sqrt = (float)a.opt_state[5];
@@ -119,11 +125,11 @@ extern "C" int hg_clip_adam_step(const HgAdamArgs* a, void* stream) {
   int blocks = (int)((a->count + 256 * 4 - 1) / (256 * 4));
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
   if (blocks < 1) blocks = 1;
-  grad_sumsq_kernel<<<blocks, 256, 0, s>>>(a->grads, a->count, a->opt_state);
+  HG_CUDA(launch_kernel(grad_sumsq_kernel, dim3(blocks), dim3(256), 0, s, 1, a->grads, a->count, a->opt_state));
   HG_LAUNCH_CHECK();
-  opt_scalars_kernel<<<1, 1, 0, s>>>(dev);
+  HG_CUDA(launch_kernel(opt_scalars_kernel, dim3(1), dim3(1), 0, s, 1, dev));
   HG_LAUNCH_CHECK();
-  adam_kernel<<<blocks, 256, 0, s>>>(dev, tab);
+  HG_CUDA(launch_kernel(adam_kernel, dim3(blocks), dim3(256), 0, s, 1, dev, tab));
   HG_LAUNCH_CHECK();
   count_launch(3);
   return HG_OK;

@@ -1,5 +1,6 @@
 // Library-level plumbing: error text, launch counter, device attributes.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -18,6 +19,15 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("HG_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 int num_sms() {
   static int n = 0;

@@ -23,7 +23,8 @@ def fwd_like(specs, bn, m=bg.M):   # same shapes through the forward epilogue (n
     ms = bg.timeit(lambda: bg.gemm_nosync(probs, _lib.EPI_BIAS_ELU_BF16, bn))
     return ms, fl
 
-for bn in (128, 256):
+if __name__ == '__main__':
+  for bn in (128, 256):
     bg.show(f"dx L2 group bn{bn} colsum", *dx([(256, 512), (256, 768)], bn, True))
     bg.show(f"dx L2 group bn{bn} NO colsum", *dx([(256, 512), (256, 768)], bn, False))
     bg.show(f"dx-shaped L2 group bn{bn} fwd epilogue", *fwd_like([(256, 512), (256, 768)], bn))
