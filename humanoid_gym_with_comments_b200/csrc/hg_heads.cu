@@ -8,6 +8,8 @@
 //             through the ELU of the last hidden layer (dZ, bias gradient), + d/d std.
 // Keeping the output layer in fp32 also keeps the policy mean's response to small Adam steps exact,
 // which the PPO ratio is sensitive to ("numerics").
+#include <stdlib.h>
+
 #include "hg_common.cuh"
 
 namespace hg {
@@ -484,6 +486,449 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
   head_backward<3, true>(L.linvel, sl, row0, valid, s_red);
 }
 
+// ------------------------------------------------------------------------------------------ update head on tensor cores
+// Same operator as ppo_head_loss_kernel for the common shape (three heads of equal hidden width H <= 128, H % 16 == 0,
+// A <= 16): the three tiny GEMMs per row tile run on the tensor cores (warp-level mma.sync m16n8k16 bf16 -> fp32,
+// operands through ldmatrix) and the blocks are PERSISTENT, so the weight gradients live in accumulator registers for
+// the whole launch and are added to global memory once per block instead of once per 64 rows.
+//   forward : out = h W^T with W = W_hi + W_mid + W_lo (three bf16 terms = all 24 mantissa bits; h is bf16, every
+//             product is exact in fp32), so the means match the fp32 rollout head to accumulation-order rounding --
+//             the PPO ratio is sensitive to exactly that.
+//   backward: dH = dOut W and gW = dOut^T h with dOut = hi + lo (16 mantissa bits), W = hi + mid.
+// The critic (1 output) and lin-vel (3 outputs) heads share one 16-row weight tile: row 0 = critic, rows 1..3 = lin-vel.
+namespace mh {
+constexpr int ROWS = 64;             // rows per tile
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int SUB = THREADS / ROWS;  // lanes per row in the loss phase
+constexpr int NO = 16;               // padded outputs per head (two n8 mma tiles)
+constexpr int DP = NO + 8;           // row pitch of the gradient tiles (48 B: conflict-free ldmatrix)
+constexpr int MAXP = 3;              // (net, 16-column tile) pairs per warp: 3 nets * (128/16) / 8 warps
+constexpr int HMAX = 128;
+constexpr int AJ = NO / SUB;         // actions per lane
+constexpr int MAXCH = ROWS * (HMAX / 8) / THREADS;   // 16-byte chunks of one activation tile per thread
+
+struct Layout {
+  size_t sh, wm, out, dO, bias, cst, total;
+  __host__ __device__ explicit Layout(int H) {
+    const size_t HP = H + 8;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t q = o; o += (b + 127) & ~size_t(127); return q; };
+    sh = take(3 * ROWS * HP * 2);
+    wm = take(2 * 3 * NO * HP * 2);
+    out = take(3 * ROWS * NO * 4);
+    dO = take(3 * 2 * ROWS * DP * 2);
+    bias = take(3 * NO * 4);
+    cst = take(4 * NO * 4);
+    total = o;
+  }
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+// D[16x8] += A[16x16] B[16x8]  (bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, bool valid) {
+  const int sz = valid ? 16 : 0;      // src-size 0 -> the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+}
+}  // namespace mh
+
+__global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const __grid_constant__ HgLossArgs L) {
+  using namespace mh;
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int H = L.actor.H, HP = H + 8, A = L.A, NT = H >> 4, P = 3 * NT;
+  const Layout lay(H);
+  __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(smem + lay.sh);          // [3][ROWS][HP]
+  __nv_bfloat16* wm = reinterpret_cast<__nv_bfloat16*>(smem + lay.wm);          // [2][3][NO][HP]
+  float* s_out = reinterpret_cast<float*>(smem + lay.out);                      // [3][ROWS][NO]
+  __nv_bfloat16* s_dO = reinterpret_cast<__nv_bfloat16*>(smem + lay.dO);        // [3][2][ROWS][DP]
+  float* s_bias = reinterpret_cast<float*>(smem + lay.bias);                    // [3][NO]
+  float* s_c = reinterpret_cast<float*>(smem + lay.cst);                        // [std | 1/(2 s^2) | log s | 1/s][NO]
+  const uint32_t sh_u = smem_u32(sh), wm_u = smem_u32(wm), dO_u = smem_u32(s_dO);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g8 = lane >> 2, t4 = lane & 3;           // mma fragment coordinates
+  const int mi = lane >> 3, rr = lane & 7;           // ldmatrix: this lane addresses row rr of 8x8 matrix mi
+
+  // ---- once per block: weights as three bf16 terms, biases, per-action constants, zeroed gradient tiles
+  for (int i = tid; i < 2 * NO * H; i += THREADS) {
+    const int mat = i / (NO * H), rem = i - mat * NO * H, n = rem / H, k = rem - n * H;
+    float w = 0.f;
+    if (mat == 0) {
+      if (n < A) w = __ldg(L.actor.W + n * H + k);
+    } else if (n == 0) {
+      w = __ldg(L.critic.W + k);
+    } else if (n < 4) {
+      w = __ldg(L.linvel.W + (n - 1) * H + k);
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const float r1 = w - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    __nv_bfloat16* d = wm + (size_t)(mat * 3) * NO * HP + n * HP + k;
+    d[0] = hi;
+    d[(size_t)NO * HP] = mid;
+    d[(size_t)2 * NO * HP] = lo;
+  }
+  for (int i = tid; i < 3 * 2 * ROWS * DP / 2; i += THREADS) reinterpret_cast<uint32_t*>(s_dO)[i] = 0u;
+  if (tid < 3 * NO) {
+    const int net = tid / NO, n = tid - net * NO;
+    float b = 0.f;
+    if (net == 0) { if (n < A) b = __ldg(L.actor.b + n); }
+    else if (net == 1) { if (n == 0) b = __ldg(L.critic.b); }
+    else if (n >= 1 && n < 4) b = __ldg(L.linvel.b + n - 1);
+    s_bias[tid] = b;
+  }
+  if (tid < NO) {
+    const float sd = tid < A ? __ldg(L.std + tid) : 1.f;
+    s_c[tid] = sd;
+    s_c[NO + tid] = 1.f / (2.f * sd * sd);
+    s_c[2 * NO + tid] = logf(sd);
+    s_c[3 * NO + tid] = 1.f / sd;
+  }
+  // activation staging map of this thread (tile independent): chunk u -> (row, 16-byte column chunk)
+  const int chunks = H >> 3;
+  int st_row[MAXCH], st_col[MAXCH];
+#pragma unroll
+  for (int u = 0; u < MAXCH; ++u) {
+    const int i = tid + u * THREADS;
+    st_row[u] = i / chunks;                      // >= ROWS when this thread has no chunk u
+    st_col[u] = (i - st_row[u] * chunks) * 8;
+  }
+  const __nv_bfloat16* h_g[3] = {reinterpret_cast<const __nv_bfloat16*>(L.actor.h), reinterpret_cast<const __nv_bfloat16*>(L.critic.h),
+                                 reinterpret_cast<const __nv_bfloat16*>(L.linvel.h)};
+  const long long h_ld[3] = {L.actor.ld_h, L.critic.ld_h, L.linvel.ld_h};
+  __nv_bfloat16* dz_g[3] = {reinterpret_cast<__nv_bfloat16*>(L.actor.dZ), reinterpret_cast<__nv_bfloat16*>(L.critic.dZ),
+                            reinterpret_cast<__nv_bfloat16*>(L.linvel.dZ)};
+  const long long dz_ld[3] = {L.actor.ld_dz, L.critic.ld_dz, L.linvel.ld_dz};
+  __syncthreads();
+
+  // ---- accumulators that live for the whole launch
+  float gWf[MAXP][2][4];      // [pair][n8 tile][fragment]: rows = outputs g8 / g8+8, cols = 2 t4, 2 t4 + 1
+  float gbh[MAXP][4];         // column sums of dZ: cols {2 t4, 2 t4 + 1} of the two n8 tiles
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gWf[j][0][i] = gWf[j][1][i] = gbh[j][i] = 0.f;
+  }
+  float st_v = 0.f, st_s = 0.f, st_l = 0.f, st_k = 0.f, st_e = 0.f;
+  float gb_a[AJ], gs_a[AJ], gb_c = 0.f, gb_l[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < AJ; ++j) gb_a[j] = gs_a[j] = 0.f;
+
+  const int r = tid / SUB, sub = tid % SUB;
+  const float inv_rows = L.inv_world / (float)L.rows;      // 1 / (rows over all ranks)
+  const int ntiles = (L.rows + ROWS - 1) / ROWS;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * ROWS;
+    const int valid = min(ROWS, L.rows - row0);
+    const bool row_ok = r < valid;
+    // -- activations: global -> shared with cp.async (rows beyond `valid` zero-filled)
+#pragma unroll
+    for (int net = 0; net < 3; ++net) {
+#pragma unroll
+      for (int u = 0; u < MAXCH; ++u) {
+        if (st_row[u] < ROWS) {
+          const bool ok = st_row[u] < valid;
+          cp_async16(sh_u + (uint32_t)((net * ROWS + st_row[u]) * HP + st_col[u]) * 2,
+                     h_g[net] + (long long)(row0 + (ok ? st_row[u] : 0)) * h_ld[net] + st_col[u], ok);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // -- the row's old-policy record, straight into registers (independent loads, consumed after the forward GEMMs)
+    const long long src = row_ok ? (L.idx ? __ldg(L.idx + row0 + r) : (long long)(row0 + r)) : 0;
+    float r_act[AJ], r_mu[AJ], r_sd[AJ];
+#pragma unroll
+    for (int j = 0; j < AJ; ++j) {
+      const int a = sub + SUB * j;
+      const bool ok = row_ok && a < A;
+      r_act[j] = ok ? __ldg(L.actions + src * A + a) : 0.f;
+      r_mu[j] = ok ? __ldg(L.old_mu + src * A + a) : 0.f;
+      r_sd[j] = ok ? __ldg(L.old_sigma + src * A + a) : 1.f;
+    }
+    const float r_logp = row_ok ? __ldg(L.old_log_prob + src) : 0.f;
+    const float r_adv = row_ok ? __ldg(L.advantages + src) : 0.f;
+    float r_ret = 0.f, r_vold = 0.f, r_tgt[3] = {0.f, 0.f, 0.f};
+    if (row_ok && sub == 0) {
+      r_ret = __ldg(L.returns + src);
+      r_vold = __ldg(L.old_values + src);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) r_tgt[j] = __ldg(L.critic_obs + src * L.ld_cobs + L.lv_col + j);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // -- forward: out[net][64][16] = h W^T, one (net, 16-row group) job per warp pass
+    for (int job = warp; job < 3 * (ROWS / 16); job += WARPS) {
+      const int net = job / (ROWS / 16), rg = job - net * (ROWS / 16);
+      // A: rows rg*16.., matrices {rows 0-7 | 8-15} x {k 0-7 | 8-15};  B: W[n][k], matrices {n 0-7 | 8-15} x {k 0-7 | 8-15}
+      const uint32_t a_addr = sh_u + (uint32_t)((net * ROWS + rg * 16 + (mi & 1) * 8 + rr) * HP + (mi >> 1) * 8) * 2;
+      const uint32_t b_addr = wm_u + (uint32_t)(((net == 0 ? 0 : 3) * NO + (mi >> 1) * 8 + rr) * HP + (mi & 1) * 8) * 2;
+      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      for (int k0 = 0; k0 < H; k0 += 16) {
+        uint32_t a[4];
+        ldsm_x4(a, a_addr + k0 * 2);
+#pragma unroll
+        for (int sp = 2; sp >= 0; --sp) {               // smallest term first
+          uint32_t b[4];
+          ldsm_x4(b, b_addr + (uint32_t)(sp * NO * HP + k0) * 2);
+          mma16816(c[0], a, b[0], b[1]);
+          mma16816(c[1], a, b[2], b[3]);
+        }
+      }
+      float* o = s_out + (size_t)(net * ROWS + rg * 16) * NO;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        *reinterpret_cast<float2*>(o + g8 * NO + nt * 8 + 2 * t4) = make_float2(c[nt][0], c[nt][1]);
+        *reinterpret_cast<float2*>(o + (g8 + 8) * NO + nt * 8 + 2 * t4) = make_float2(c[nt][2], c[nt][3]);
+      }
+    }
+    __syncthreads();
+
+    // -- losses and d loss / d outputs (same math as ppo_head_loss_kernel; SUB lanes per row split the actions)
+    {
+      float logp = 0.f, ent = 0.f, kl = 0.f;
+      float m[AJ];
+#pragma unroll
+      for (int j = 0; j < AJ; ++j) {
+        const int a = sub + SUB * j;
+        m[j] = 0.f;
+        if (a < A && row_ok) {
+          m[j] = s_out[r * NO + a] + s_bias[a];
+          const float sd = s_c[a], i2v = s_c[NO + a], lsd = s_c[2 * NO + a];
+          const float d = r_act[j] - m[j];
+          logp += -(d * d) * i2v - lsd - LOG_SQRT_2PI;
+          ent += HALF_LOG_2PI_PLUS_HALF + lsd;
+          const float osd = r_sd[j];
+          const float dm = r_mu[j] - m[j];
+          kl += logf(sd * __frcp_rn(osd) + 1.e-5f) + (osd * osd + dm * dm) * i2v - 0.5f;
+        }
+      }
+#pragma unroll
+      for (int o = SUB >> 1; o > 0; o >>= 1) {
+        logp += __shfl_xor_sync(0xffffffffu, logp, o);
+        ent += __shfl_xor_sync(0xffffffffu, ent, o);
+        kl += __shfl_xor_sync(0xffffffffu, kl, o);
+      }
+      float g_logp = 0.f;
+      __nv_bfloat16* dOa = s_dO;                                 // actor   [2][ROWS][DP]
+      __nv_bfloat16* dOc = s_dO + (size_t)2 * ROWS * DP;         // critic
+      __nv_bfloat16* dOl = s_dO + (size_t)4 * ROWS * DP;         // lin-vel
+      auto put = [&](__nv_bfloat16* base, int col, float g) {    // gradient as hi + lo bf16 terms
+        const __nv_bfloat16 hi = __float2bfloat16_rn(g);
+        base[r * DP + col] = hi;
+        base[ROWS * DP + r * DP + col] = __float2bfloat16_rn(g - __bfloat162float(hi));
+      };
+      if (row_ok) {
+        const float ratio = expf(logp - r_logp);
+        const float s1 = -r_adv * ratio;
+        const float s2 = -r_adv * fminf(fmaxf(ratio, 1.f - L.clip_param), 1.f + L.clip_param);
+        g_logp = (s1 >= s2 ? s1 : 0.f) * inv_rows;               // d surr / d logp  (ties: clamp passes gradient)
+        if (sub == 0) {
+          st_s += fmaxf(s1, s2); st_k += kl; st_e += ent;
+          const float R = r_ret, v = s_out[ROWS * NO + r * NO] + s_bias[NO];
+          float vl, g_v;
+          if (L.use_clipped_value_loss) {
+            const float vo = r_vold;
+            const float dv = v - vo;
+            const float vc = vo + fminf(fmaxf(dv, -L.clip_param), L.clip_param);
+            const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+            const float pass = (dv >= -L.clip_param && dv <= L.clip_param) ? 1.f : 0.f;
+            vl = fmaxf(l1, l2);
+            g_v = l1 > l2 ? 2.f * (v - R) : (l1 < l2 ? 2.f * (vc - R) * pass : (v - R) + (vc - R) * pass);
+          } else {
+            vl = (R - v) * (R - v);
+            g_v = 2.f * (v - R);
+          }
+          st_v += vl;
+          const float gv = L.value_loss_coef * g_v * inv_rows;
+          put(dOc, 0, gv);
+          gb_c += gv;
+          float lsq = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float e = s_out[2 * ROWS * NO + r * NO + 1 + j] + s_bias[2 * NO + 1 + j] - r_tgt[j];
+            lsq += e * e;
+            const float gl = L.lin_vel_coef * 2.f * e * inv_rows * (1.f / 3.f);
+            put(dOl, 1 + j, gl);
+            gb_l[j] += gl;
+          }
+          st_l += lsq;
+        }
+      } else if (sub == 0) {
+        put(dOc, 0, 0.f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) put(dOl, 1 + j, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < AJ; ++j) {
+        const int a = sub + SUB * j;
+        if (a < A) {
+          float gm = 0.f;
+          if (row_ok) {
+            const float isd = s_c[3 * NO + a], ivar = 2.f * s_c[NO + a];
+            const float d = r_act[j] - m[j];
+            gm = g_logp * d * ivar;
+            gs_a[j] += g_logp * (d * d * ivar * isd - isd) - L.entropy_coef * inv_rows * isd;
+          }
+          put(dOa, a, gm);
+          gb_a[j] += gm;
+        }
+      }
+    }
+    __syncthreads();
+
+    // -- backward: each warp owns up to MAXP (net, 16-column tile) pairs for the whole launch
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+      const int p = warp + WARPS * j;
+      if (p < P) {
+        const int net = p / NT, n0 = (p - net * NT) * 16;
+        const uint32_t h_u = sh_u + (uint32_t)(net * ROWS * HP) * 2;
+        const uint32_t d_u = dO_u + (uint32_t)(net * 2 * ROWS * DP) * 2;
+        const uint32_t w_u = wm_u + (uint32_t)((net == 0 ? 0 : 3) * NO * HP) * 2;
+        // gW[16 outputs x 16 cols] += dOut^T[16 x 64 rows] h[64 rows x 16 cols]:
+        //   A(m = output, k = row) is dOut[row][output]  -> transposed 8x8 loads, matrices {k 0-7 | 8-15} x {m 0-7 | 8-15}
+        //   B(k = row, n = col)    is h[row][col]        -> transposed 8x8 loads
+        for (int k0 = 0; k0 < ROWS; k0 += 16) {
+          uint32_t b[4], ah[4], al[4];
+          ldsm_x4_t(b, h_u + (uint32_t)((k0 + (mi & 1) * 8 + rr) * HP + n0 + (mi >> 1) * 8) * 2);
+          const uint32_t a_off = (uint32_t)((k0 + (mi >> 1) * 8 + rr) * DP + (mi & 1) * 8) * 2;
+          ldsm_x4_t(ah, d_u + a_off);
+          ldsm_x4_t(al, d_u + (uint32_t)(ROWS * DP) * 2 + a_off);
+          mma16816(gWf[j][0], al, b[0], b[1]);
+          mma16816(gWf[j][1], al, b[2], b[3]);
+          mma16816(gWf[j][0], ah, b[0], b[1]);
+          mma16816(gWf[j][1], ah, b[2], b[3]);
+        }
+        // dH[16 rows x 16 cols] = dOut[16 x 16 outputs] W[16 outputs x 16 cols] per 16-row group (B: transposed loads of
+        // W[output][col]), then the ELU derivative, the dZ store and the bias-gradient column sums -- all in fragments
+        uint32_t bh[4], bm[4];
+        const uint32_t w_off = (uint32_t)(((mi & 1) * 8 + rr) * HP + n0 + (mi >> 1) * 8) * 2;
+        ldsm_x4_t(bh, w_u + w_off);
+        ldsm_x4_t(bm, w_u + (uint32_t)(NO * HP) * 2 + w_off);
+        for (int rg = 0; rg < ROWS / 16; ++rg) {
+          uint32_t ah[4], al[4];
+          const uint32_t a_off = (uint32_t)((rg * 16 + (mi & 1) * 8 + rr) * DP + (mi >> 1) * 8) * 2;
+          ldsm_x4(ah, d_u + a_off);
+          ldsm_x4(al, d_u + (uint32_t)(ROWS * DP) * 2 + a_off);
+          float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          mma16816(c[0], ah, bm[0], bm[1]);
+          mma16816(c[1], ah, bm[2], bm[3]);
+          mma16816(c[0], al, bh[0], bh[1]);
+          mma16816(c[1], al, bh[2], bh[3]);
+          mma16816(c[0], ah, bh[0], bh[1]);
+          mma16816(c[1], ah, bh[2], bh[3]);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {             // rows g8 and g8 + 8
+              const int row = rg * 16 + g8 + hf * 8, col = n0 + nt * 8 + 2 * t4;
+              const float2 h2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sh + (size_t)(net * ROWS + row) * HP + col));
+              const float z0 = c[nt][2 * hf] * (h2.x > 0.f ? 1.f : h2.x + 1.f);
+              const float z1 = c[nt][2 * hf + 1] * (h2.y > 0.f ? 1.f : h2.y + 1.f);
+              gbh[j][2 * nt] += z0;
+              gbh[j][2 * nt + 1] += z1;
+              if (row < valid)
+                *reinterpret_cast<uint32_t*>(dz_g[net] + (long long)(row0 + row) * dz_ld[net] + col) = pack_bf16x2(z0, z1);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();       // the next tile overwrites sh / s_out / s_dO
+  }
+
+  // ---- once per block: flush everything that was accumulated in registers
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) {
+    const int p = warp + WARPS * j;
+    if (p < P) {
+      const int net = p / NT, n0 = (p - net * NT) * 16;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int a = g8 + (i >> 1) * 8, col = n0 + nt * 8 + 2 * t4 + (i & 1);
+          const float g = gWf[j][nt][i];
+          if (net == 0) { if (a < A) atomicAdd(L.actor.gW + a * H + col, g); }
+          else if (net == 1) { if (a == 0) atomicAdd(L.critic.gW + col, g); }
+          else if (a >= 1 && a < 4) atomicAdd(L.linvel.gW + (a - 1) * H + col, g);
+        }
+      }
+      float* gbh_g = net == 0 ? L.actor.gb_hidden : net == 1 ? L.critic.gb_hidden : L.linvel.gb_hidden;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = gbh[j][i];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (g8 == 0) atomicAdd(gbh_g + n0 + (i >> 1) * 8 + 2 * t4 + (i & 1), v);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < AJ; ++j) {
+    float g = gb_a[j], gs = gs_a[j];
+#pragma unroll
+    for (int o = SUB; o < 32; o <<= 1) {
+      g += __shfl_xor_sync(0xffffffffu, g, o);
+      gs += __shfl_xor_sync(0xffffffffu, gs, o);
+    }
+    const int a = lane + SUB * j;
+    if (lane < SUB && a < A) {
+      atomicAdd(L.actor.gb + a, g);
+      atomicAdd(L.g_std + a, gs);
+    }
+  }
+  gb_c = warp_sum(gb_c);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) gb_l[j] = warp_sum(gb_l[j]);
+  st_v = warp_sum(st_v); st_s = warp_sum(st_s); st_l = warp_sum(st_l); st_k = warp_sum(st_k); st_e = warp_sum(st_e);
+  if (lane == 0) {
+    atomicAdd(L.critic.gb, gb_c);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) atomicAdd(L.linvel.gb + j, gb_l[j]);
+    atomicAdd(L.stats + 0, st_v);
+    atomicAdd(L.stats + 1, st_s);
+    atomicAdd(L.stats + 2, st_l);
+    atomicAdd(L.stats + 3, st_k);
+    atomicAdd(L.stats + 4, st_e);
+  }
+}
+
+static bool loss_mma_eligible(const HgLossArgs& L) {
+  const int H = L.actor.H;
+  return H == L.critic.H && H == L.linvel.H && H % 16 == 0 && H >= 16 && H <= mh::HMAX && L.A <= mh::NO;
+}
+
+static int launch_loss_mma(const HgLossArgs& L, cudaStream_t s) {
+  const size_t smem = mh::Layout(L.actor.H).total;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    HG_CUDA(cudaFuncSetAttribute(ppo_head_loss_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int ntiles = (L.rows + mh::ROWS - 1) / mh::ROWS;
+  const int cap = 2 * num_sms();
+  HG_CUDA(launch_kernel(ppo_head_loss_mma_kernel, dim3(ntiles < cap ? ntiles : cap), dim3(mh::THREADS), smem, s, 1, L));
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
+}
+
 static size_t loss_smem_bytes(const HgLossArgs& L, int AT) {
   auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
   size_t t = 0;
@@ -594,6 +1039,8 @@ extern "C" int hg_ppo_head_loss(const HgLossArgs* L, void* stream) {
   HG_CHECK(L->actions && L->old_mu && L->old_sigma && L->old_log_prob && L->advantages && L->returns && L->old_values &&
                L->critic_obs && L->std && L->g_std && L->stats, "hg_ppo_head_loss: null pointer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static const bool simt_only = getenv("HG_LOSS_SIMT") != nullptr;     // A/B switch for the tests
+  if (!simt_only && loss_mma_eligible(*L)) return launch_loss_mma(*L, s);
   if (L->A == 12) return launch_loss<12, true>(*L, s);     // XBot-L: 12 actions
   if (L->A == 20) return launch_loss<20, true>(*L, s);
   if (L->A <= 12) return launch_loss<12, false>(*L, s);

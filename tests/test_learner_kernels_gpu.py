@@ -136,8 +136,10 @@ def test_head_loss_forward_backward(rows, A, H):
     for i in range(3):
         assert torch.allclose(gW[i], ref["gW"][i], rtol=2e-4, atol=1e-6), (i, float((gW[i] - ref["gW"][i]).abs().max()))
         assert torch.allclose(gb[i], ref["gb"][i], rtol=2e-4, atol=1e-6), i
-        # dZ is stored in bf16: 2^-8 relative
-        assert torch.allclose(dZ[i].float(), ref["dZ"][i], rtol=1e-2, atol=1e-9), (i, float((dZ[i].float() - ref["dZ"][i]).abs().max()))
+        # dZ is stored in bf16: 2^-8 relative; the tensor-core path forms dOut W from 16-bit split operands, so an
+        # element that is a near-cancelling sum carries ~2^-16 of its TERMS (hence the scale-aware atol)
+        atol_dz = 2e-5 * float(ref["dZ"][i].abs().max())
+        assert torch.allclose(dZ[i].float(), ref["dZ"][i], rtol=1e-2, atol=atol_dz), (i, float((dZ[i].float() - ref["dZ"][i]).abs().max()))
         assert torch.allclose(gbh[i], ref["dZ"][i].sum(0), rtol=1e-3, atol=1e-6), i
     assert torch.allclose(gstd, ref["gstd"], rtol=2e-4, atol=1e-6)
 

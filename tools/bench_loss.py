@@ -1,0 +1,40 @@
+"""Stand-alone timing of hg_ppo_head_loss at the update's minibatch shape (61440 rows, H=128, A=12)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import ctypes as C
+import torch
+from humanoid_gym_with_comments_b200._lib import HgHeadNet, HgLossArgs, check, current_stream, load, ptr
+DEV = "cuda:0"
+rows, A, H = int(os.environ.get("HG_ROWS", 61440)), 12, 128
+g = torch.Generator(device=DEV).manual_seed(0)
+TN = rows * 4
+rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
+h = [torch.nn.functional.elu(rn(rows, H)).to(torch.bfloat16) for _ in range(3)]
+n_out = [A, 1, 3]
+W = [0.1 * rn(n, H) for n in n_out]; b = [0.1 * rn(n) for n in n_out]
+std = 0.7 + 0.5 * torch.rand(A, device=DEV, generator=g)
+idx = torch.randperm(TN, device=DEV, generator=g)[:rows]
+store = dict(actions=rn(TN, A), old_mu=0.3 * rn(TN, A), old_sigma=0.8 + 0.4 * torch.rand(TN, A, device=DEV, generator=g),
+             old_logp=-12 + rn(TN), adv=rn(TN), ret=rn(TN), old_v=rn(TN), cobs=rn(TN, 219))
+gW = [torch.zeros_like(w) for w in W]; gb = [torch.zeros_like(x) for x in b]
+gbh = [torch.zeros(H, device=DEV) for _ in range(3)]
+dZ = [torch.zeros(rows, H, dtype=torch.bfloat16, device=DEV) for _ in range(3)]
+gstd = torch.zeros(A, device=DEV); stats = torch.zeros(8, device=DEV)
+nets = [HgHeadNet(h=ptr(h[i]), ld_h=H, H=H, n_out=n_out[i], W=ptr(W[i]), b=ptr(b[i]), gW=ptr(gW[i]), gb=ptr(gb[i]),
+                  dZ=ptr(dZ[i]), ld_dz=H, gb_hidden=ptr(gbh[i])) for i in range(3)]
+args = HgLossArgs(actor=nets[0], critic=nets[1], linvel=nets[2], rows=rows, A=A, idx=ptr(idx),
+                  actions=ptr(store["actions"]), old_mu=ptr(store["old_mu"]), old_sigma=ptr(store["old_sigma"]),
+                  old_log_prob=ptr(store["old_logp"]), advantages=ptr(store["adv"]), returns=ptr(store["ret"]),
+                  old_values=ptr(store["old_v"]), critic_obs=ptr(store["cobs"]), ld_cobs=219, lv_col=53, std=ptr(std),
+                  g_std=ptr(gstd), clip_param=0.2, value_loss_coef=1.0, entropy_coef=0.001, lin_vel_coef=1.0,
+                  use_clipped_value_loss=1, inv_world=1.0, stats=ptr(stats))
+lib = load()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+ts = []
+for i in range(8):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); check(lib.hg_ppo_head_loss(C.byref(args), current_stream())); e1.record(); torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+print("loss head", "SIMT" if os.environ.get("HG_LOSS_SIMT") else "mma", f"rows {rows}: median {sorted(ts[2:])[3]:.1f} us  all {[round(t, 1) for t in ts]}")
