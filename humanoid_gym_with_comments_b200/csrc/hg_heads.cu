@@ -607,12 +607,11 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
     st_row[u] = i / chunks;                      // >= ROWS when this thread has no chunk u
     st_col[u] = (i - st_row[u] * chunks) * 8;
   }
-  const __nv_bfloat16* h_g[3] = {reinterpret_cast<const __nv_bfloat16*>(L.actor.h), reinterpret_cast<const __nv_bfloat16*>(L.critic.h),
-                                 reinterpret_cast<const __nv_bfloat16*>(L.linvel.h)};
-  const long long h_ld[3] = {L.actor.ld_h, L.critic.ld_h, L.linvel.ld_h};
-  __nv_bfloat16* dz_g[3] = {reinterpret_cast<__nv_bfloat16*>(L.actor.dZ), reinterpret_cast<__nv_bfloat16*>(L.critic.dZ),
-                            reinterpret_cast<__nv_bfloat16*>(L.linvel.dZ)};
-  const long long dz_ld[3] = {L.actor.ld_dz, L.critic.ld_dz, L.linvel.ld_dz};
+  // per-net kernel parameters picked with selects (a runtime-indexed array would live in local memory)
+  auto net_h = [&](int net) { return reinterpret_cast<const __nv_bfloat16*>(net == 0 ? L.actor.h : net == 1 ? L.critic.h : L.linvel.h); };
+  auto net_ldh = [&](int net) { return net == 0 ? L.actor.ld_h : net == 1 ? L.critic.ld_h : L.linvel.ld_h; };
+  auto net_dz = [&](int net) { return reinterpret_cast<__nv_bfloat16*>(net == 0 ? L.actor.dZ : net == 1 ? L.critic.dZ : L.linvel.dZ); };
+  auto net_lddz = [&](int net) { return net == 0 ? L.actor.ld_dz : net == 1 ? L.critic.ld_dz : L.linvel.ld_dz; };
   __syncthreads();
 
   // ---- accumulators that live for the whole launch
@@ -643,7 +642,7 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
         if (st_row[u] < ROWS) {
           const bool ok = st_row[u] < valid;
           cp_async16(sh_u + (uint32_t)((net * ROWS + st_row[u]) * HP + st_col[u]) * 2,
-                     h_g[net] + (long long)(row0 + (ok ? st_row[u] : 0)) * h_ld[net] + st_col[u], ok);
+                     net_h(net) + (long long)(row0 + (ok ? st_row[u] : 0)) * net_ldh(net) + st_col[u], ok);
         }
       }
     }
@@ -671,30 +670,30 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    // -- forward: out[net][64][16] = h W^T, one (net, 16-row group) job per warp pass
-    for (int job = warp; job < 3 * (ROWS / 16); job += WARPS) {
-      const int net = job / (ROWS / 16), rg = job - net * (ROWS / 16);
-      // A: rows rg*16.., matrices {rows 0-7 | 8-15} x {k 0-7 | 8-15};  B: W[n][k], matrices {n 0-7 | 8-15} x {k 0-7 | 8-15}
+    // -- forward: out[net][64][16] = h W^T.  Jobs = (net, 16-row group, n8 tile); the second n8 tile exists only for the
+    //    actor (outputs 8..A-1): 16 jobs, two per warp.
+    for (int job = warp; job < 4 * (ROWS / 16); job += WARPS) {
+      const int q = job / (ROWS / 16), rg = job - q * (ROWS / 16);
+      const int net = q < 2 ? 0 : q - 1, nt = q == 1 ? 1 : 0;
+      // A: rows rg*16.., matrices {rows 0-7 | 8-15} x {k 0-7 | 8-15};  B: W[n][k], matrices {k 0-7 | 8-15} of two 16-wide k steps
       const uint32_t a_addr = sh_u + (uint32_t)((net * ROWS + rg * 16 + (mi & 1) * 8 + rr) * HP + (mi >> 1) * 8) * 2;
-      const uint32_t b_addr = wm_u + (uint32_t)(((net == 0 ? 0 : 3) * NO + (mi >> 1) * 8 + rr) * HP + (mi & 1) * 8) * 2;
-      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      for (int k0 = 0; k0 < H; k0 += 16) {
-        uint32_t a[4];
-        ldsm_x4(a, a_addr + k0 * 2);
+      const uint32_t b_addr = wm_u + (uint32_t)(((net == 0 ? 0 : 3) * NO + nt * 8 + rr) * HP + mi * 8) * 2;
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k0 = 0; k0 < H; k0 += 32) {            // H % 32 == 0 on this path
+        uint32_t a0[4], a1[4];
+        ldsm_x4(a0, a_addr + k0 * 2);
+        ldsm_x4(a1, a_addr + (k0 + 16) * 2);
 #pragma unroll
         for (int sp = 2; sp >= 0; --sp) {               // smallest term first
-          uint32_t b[4];
+          uint32_t b[4];                                // {b0, b1} of k step k0 and of k step k0 + 16
           ldsm_x4(b, b_addr + (uint32_t)(sp * NO * HP + k0) * 2);
-          mma16816(c[0], a, b[0], b[1]);
-          mma16816(c[1], a, b[2], b[3]);
+          mma16816(c, a0, b[0], b[1]);
+          mma16816(c, a1, b[2], b[3]);
         }
       }
-      float* o = s_out + (size_t)(net * ROWS + rg * 16) * NO;
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        *reinterpret_cast<float2*>(o + g8 * NO + nt * 8 + 2 * t4) = make_float2(c[nt][0], c[nt][1]);
-        *reinterpret_cast<float2*>(o + (g8 + 8) * NO + nt * 8 + 2 * t4) = make_float2(c[nt][2], c[nt][3]);
-      }
+      float* o = s_out + (size_t)(net * ROWS + rg * 16) * NO + nt * 8 + 2 * t4;
+      *reinterpret_cast<float2*>(o + g8 * NO) = make_float2(c[0], c[1]);
+      *reinterpret_cast<float2*>(o + (g8 + 8) * NO) = make_float2(c[2], c[3]);
     }
     __syncthreads();
 
@@ -820,6 +819,10 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
         const uint32_t w_off = (uint32_t)(((mi & 1) * 8 + rr) * HP + n0 + (mi >> 1) * 8) * 2;
         ldsm_x4_t(bh, w_u + w_off);
         ldsm_x4_t(bm, w_u + (uint32_t)(NO * HP) * 2 + w_off);
+        const __nv_bfloat16* h_lane = sh + (size_t)(net * ROWS + g8) * HP + n0 + 2 * t4;    // this lane's first (row, col)
+        const long long ldz = net_lddz(net);
+        __nv_bfloat16* dz_lane = net_dz(net) + (long long)(row0 + g8) * ldz + n0 + 2 * t4;
+#pragma unroll
         for (int rg = 0; rg < ROWS / 16; ++rg) {
           uint32_t ah[4], al[4];
           const uint32_t a_off = (uint32_t)((rg * 16 + (mi & 1) * 8 + rr) * DP + (mi >> 1) * 8) * 2;
@@ -836,14 +839,13 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
           for (int nt = 0; nt < 2; ++nt) {
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {             // rows g8 and g8 + 8
-              const int row = rg * 16 + g8 + hf * 8, col = n0 + nt * 8 + 2 * t4;
-              const float2 h2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sh + (size_t)(net * ROWS + row) * HP + col));
+              const int off = rg * 16 + hf * 8;          // row offset from this lane's first row (g8)
+              const float2 h2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(h_lane + off * HP + nt * 8));
               const float z0 = c[nt][2 * hf] * (h2.x > 0.f ? 1.f : h2.x + 1.f);
               const float z1 = c[nt][2 * hf + 1] * (h2.y > 0.f ? 1.f : h2.y + 1.f);
               gbh[j][2 * nt] += z0;
               gbh[j][2 * nt + 1] += z1;
-              if (row < valid)
-                *reinterpret_cast<uint32_t*>(dz_g[net] + (long long)(row0 + row) * dz_ld[net] + col) = pack_bf16x2(z0, z1);
+              if (g8 + off < valid) *reinterpret_cast<uint32_t*>(dz_lane + off * ldz + nt * 8) = pack_bf16x2(z0, z1);
             }
           }
         }
@@ -911,7 +913,7 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
 
 static bool loss_mma_eligible(const HgLossArgs& L) {
   const int H = L.actor.H;
-  return H == L.critic.H && H == L.linvel.H && H % 16 == 0 && H >= 16 && H <= mh::HMAX && L.A <= mh::NO;
+  return H == L.critic.H && H == L.linvel.H && H % 32 == 0 && H >= 32 && H <= mh::HMAX && L.A <= mh::NO;
 }
 
 static int launch_loss_mma(const HgLossArgs& L, cudaStream_t s) {
