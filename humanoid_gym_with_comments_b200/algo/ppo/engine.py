@@ -10,6 +10,7 @@ nn.Sequential of Linear/ELU) as driven by `ppo.py:116-126` (rollout) and `ppo.py
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -153,8 +154,10 @@ class MLPEngine:
     @staticmethod
     def _block_n(ns: Sequence[int], kind: str = "fwd", rows: int = 1 << 30) -> int:
         """UMMA N of the accumulator tile, from tools/bench_gemm.py on B200: 256-wide tiles win whenever some
-        problem of the group is at least 256 wide (less shared-memory traffic per MMA), except for the dX launches
-        whose K is tiny and whose epilogue (ELU' + column sums) is the bound."""
+        problem of the group is at least 256 wide (less L2 -> shared-memory traffic per MMA); rollout-sized launches
+        keep 128-wide tiles (more tiles to fill the SMs)."""
+        if kind == "dx" and rows > 8192:
+            return int(os.environ.get("HG_DX_BN", 256)) if max(ns) >= 256 else 128
         if kind == "dx" or rows <= 8192:
             return 128       # rollout-sized launches: more, smaller tiles fill the 148 SMs better
         return 256 if max(ns) >= 256 else 128

@@ -28,12 +28,8 @@ constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
 #ifndef HG_EPI_WARPS
-#define HG_EPI_WARPS 8
+#define HG_EPI_WARPS 16
 #endif
-constexpr int NUM_EPI_WARPS = HG_EPI_WARPS;          // 8 or 16: 2 or 4 epilogue warps per scheduler
-constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
-constexpr int EPI_COL_SPLIT = NUM_EPI_WARPS / 4;      // column slices per tile
-constexpr int EPI_TILE_FLOATS = 32 * 33;      // per-warp transpose tile of the split-K epilogue
 constexpr int MN_ATOM_BYTES = BLOCK_K * 128;  // 8192: one [64 x 64] bf16 atom
 
 template <int BLOCK_N, int EPI, int CG>
@@ -41,7 +37,15 @@ struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KB
   static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;          // 8 / 16 / 32 KB (per CTA)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_TILE_FLOATS * 4;   // per-warp transpose tiles of the epilogues
+  // per-warp staging tile: 32 x 33 floats for the transposing split-K epilogue, 32 rows x 80 B for the bf16 ones
+  static constexpr int EPI_TILE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 32 * 33 * 4 : 32 * 80;
+  static constexpr bool F32_OUT = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32);
+  // epilogue warps: 4 per scheduler for the bf16 epilogues (they bound the short-K launches: 16 beat 8 by ~20 %);
+  // the fp32 ones sit behind K = rows main loops and keep 8 so that their 4 KB staging tiles leave a deeper TMA ring
+  static constexpr int EPI_WARPS = F32_OUT ? 8 : HG_EPI_WARPS;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int COL_SPLIT = EPI_WARPS / 4;       // column slices per tile
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILE_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET - EPI_BYTES) / STAGE_BYTES;  // 3..7 deep TMA ring
   static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
   static_assert(STAGES >= 3, "pipeline too shallow");
@@ -131,6 +135,15 @@ __device__ __forceinline__ float exp2f_fast(float x) {
   return y;
 }
 
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 w;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(saddr) : "memory");
+  return w;
+}
+
 constexpr int EPI_ROW_PITCH = 80;   // bytes per staged row: 64 B of bf16 + 16 B pad (conflict-free 16-byte accesses)
 
 // Write the warp's 32 rows x 32 columns (one row per lane, fp32 in registers) as bf16 with COALESCED global stores:
@@ -138,18 +151,18 @@ constexpr int EPI_ROW_PITCH = 80;   // bytes per staged row: 64 B of bf16 + 16 B
 // store instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.
 __device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* tile, int lane, __nv_bfloat16* out_col0,
                                                 long long ldo, int row_base, int M) {
-  uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+  const uint32_t tb = smem_u32(tile);
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const uint4 w = make_uint4(pack_bf16x2(z[j], z[j + 1]), pack_bf16x2(z[j + 2], z[j + 3]),
                                pack_bf16x2(z[j + 4], z[j + 5]), pack_bf16x2(z[j + 6], z[j + 7]));
-    *reinterpret_cast<uint4*>(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16) = w;
+    sts128(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16, w);
   }
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + (lane >> 2), piece = lane & 3;
-    const uint4 w = *reinterpret_cast<const uint4*>(tb + r * EPI_ROW_PITCH + piece * 16);
+    const uint4 w = lds128(tb + r * EPI_ROW_PITCH + piece * 16);
 #ifdef HG_DBG_NOSTORE
     if (row_base + r < M && w.x == 0x12345678u)
 #else
@@ -235,23 +248,26 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
     if (full) {
       // activation rows of the layer below: coalesced global -> shared (4 lanes per 64-byte row segment), then each
       // lane reads back its own row
-      uint8_t* tb = reinterpret_cast<uint8_t*>(tile);
+      const uint32_t tb = smem_u32(tile);
       const int row_base = row - lane;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + (lane >> 2), piece = lane & 3;
-        *reinterpret_cast<uint4*>(tb + r * EPI_ROW_PITCH + piece * 16) = pre[i];
+        sts128(tb + r * EPI_ROW_PITCH + piece * 16, pre[i]);
       }
       __syncwarp();
+      // dZ = dH * elu'(h), elu'(h) = 1 (h > 0) or h + 1 (h <= 0)  ==  fma(dH, min(h, 0), dH).  Rows past M need no
+      // predicate: TMA zero-fills their A rows, so their accumulators are exactly 0.
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        const uint4 hw = *reinterpret_cast<const uint4*>(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16);
+        const uint4 hw = lds128(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16);
         const uint32_t hv[4] = {hw.x, hw.y, hw.z, hw.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 h = unpack_bf16x2(hv[k]);
-          d[j + 2 * k] = row_ok ? __uint_as_float(v[j + 2 * k]) * (h.x > 0.f ? 1.f : h.x + 1.f) : 0.f;
-          d[j + 2 * k + 1] = row_ok ? __uint_as_float(v[j + 2 * k + 1]) * (h.y > 0.f ? 1.f : h.y + 1.f) : 0.f;
+          const float a0 = __uint_as_float(v[j + 2 * k]), a1 = __uint_as_float(v[j + 2 * k + 1]);
+          d[j + 2 * k] = fmaf(a0, fminf(h.x, 0.f), a0);
+          d[j + 2 * k + 1] = fmaf(a1, fminf(h.y, 0.f), a1);
         }
       }
       __syncwarp();
@@ -350,7 +366,7 @@ __device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr) {
 //         the leader CTA issues the MMAs for both, each tensor core reads the other half of B from its peer's
 //         shared memory.  Operand fill per SM drops from 16 + 32 KB to 16 + 16 KB per 128x256x64 MMA block.
 template <int BLOCK_N, int EPI, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ GroupParams P) {
+__global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kernel(const __grid_constant__ GroupParams P) {
   using K = Cfg<BLOCK_N, EPI, CG>;
   constexpr int A_BYTES = K::A_BYTES, STAGE_BYTES = K::STAGE_BYTES, STAGES = K::STAGES;
   constexpr int B_ROWS = BLOCK_N / CG;                      // rows (K-major) / columns (MN-major) of B this CTA loads
@@ -387,7 +403,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), CG * NUM_EPI_WARPS);
+      mbar_init(smem_u32(&tempty_bar[a]), CG * K::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -498,42 +514,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     // ================================================================ epilogue: warps 4..(4+NUM_EPI_WARPS)
     const int quad = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;          // which column slice of the tile
-    constexpr int SLICE = BLOCK_N / EPI_COL_SPLIT;
+    constexpr int SLICE = BLOCK_N / K::COL_SPLIT;
     constexpr int CHUNKS = SLICE / 32;         // 32-column chunks per warp
-    float* tile = epi_tiles + (warp - 4) * EPI_TILE_FLOATS;
+    float* tile = epi_tiles + (warp - 4) * (K::EPI_TILE_BYTES / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
+    // Measured on B200 (tools/bench_gemm_dx.py, 61440 x {512,768} x 256): sixteen epilogue warps with the plain loop
+    // below beat eight by ~20 %; double-buffering the TMEM loads or fetching the DELU activations a tile ahead costs
+    // more in registers (640 threads -> 102 per thread) than it hides in latency, so neither is done.
+    constexpr bool DELU = (EPI == HG_EPI_DELU_BF16);
     for (int t = group_id; t < P.total_tiles; t += num_groups) {
       const Tile ti = decode_tile(P, t);
       const DevProblem& q = P.p[ti.g];
       const int row = (ti.m_blk * CG + rank) * BLOCK_M + quad * 32 + lane;
-      uint4 pre[EPI == HG_EPI_DELU_BF16 ? CHUNKS : 1][4];
-      if constexpr (EPI == HG_EPI_DELU_BF16) {
+      const int col0 = ti.n_blk * BLOCK_N + half * SLICE;
+      const int nchunks = q.N > col0 ? min(CHUNKS, (q.N - col0 + 31) >> 5) : 0;
+      // DELU: the activation rows are requested BEFORE the accumulator barrier, their latency hides behind the main loop
+      uint4 pre[DELU ? CHUNKS : 1][4];
+      if constexpr (DELU) {
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c)
-          prefetch_act(q, row - lane, ti.n_blk * BLOCK_N + half * SLICE + c * 32, lane, pre[c]);
+        for (int c = 0; c < CHUNKS; ++c) prefetch_act(q, row - lane, col0 + c * 32, lane, pre[c]);   // (bounds-checked inside)
       }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + half * SLICE;
 #pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
-        const int n0 = ti.n_blk * BLOCK_N + half * SLICE + c * 32;
-        if (n0 >= q.N) break;
-        uint32_t v[32];
-#ifdef HG_DBG_EPI_NOLD
+        if (c < nchunks) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+#if defined(HG_DBG_EPI_NONE)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0;
+          for (int j = 0; j < 32; ++j) asm volatile("" ::"r"(v[j]));
 #else
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
+          epilogue_chunk<EPI>(q, row, col0 + c * 32, v, lane, tile, pre[DELU ? c : 0]);
 #endif
-#ifdef HG_DBG_EPI_NONE
-#pragma unroll
-        for (int j = 0; j < 32; ++j) asm volatile("" ::"r"(v[j]));
-#else
-        epilogue_chunk<EPI>(q, row, n0, v, lane, tile, pre[EPI == HG_EPI_DELU_BF16 ? c : 0]);
-#endif
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -603,7 +620,7 @@ static int launch(const GroupParams& gp, cudaStream_t stream) {
   }
   const int max_groups = num_sms() / CG;
   const int groups = gp.total_tiles < max_groups ? gp.total_tiles : max_groups;
-  HG_CUDA(launch_kernel(gemm_kernel<BLOCK_N, EPI, CG>, dim3(groups * CG), dim3(NUM_THREADS), smem, stream, CG, gp));
+  HG_CUDA(launch_kernel(gemm_kernel<BLOCK_N, EPI, CG>, dim3(groups * CG), dim3(Cfg<BLOCK_N, EPI, CG>::THREADS), smem, stream, CG, gp));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;
