@@ -28,7 +28,8 @@ HG_NUM_REWARDS = 22
 HG_STATS_SLOTS = 8
 HG_MAX_SHADOWS = 16
 ENV_PHASE_REWARD, ENV_PHASE_OBS, ENV_PHASE_ALL = 1, 2, 3
-EPI_STORE_F32, EPI_BIAS_ELU_BF16, EPI_DELU_BF16, EPI_ATOMIC_F32, EPI_BIAS_BF16 = range(5)
+EPI_STORE_F32, EPI_BIAS_ELU_BF16, EPI_DELU_BF16, EPI_ATOMIC_F32, EPI_BIAS_BF16, EPI_BIAS_ELU_HEAD = range(6)
+HEAD_NONE, HEAD_POLICY, HEAD_LINEAR = range(3)
 
 REWARD_NAMES = ["action_smoothness", "base_acc", "base_height", "collision", "default_joint_pos", "dof_acc", "dof_vel",
                 "feet_air_time", "feet_clearance", "feet_contact_forces", "feet_contact_number", "feet_distance",
@@ -89,6 +90,11 @@ class HgGemmProblem(C.Structure):
                 ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("M", C.c_int32), ("N", C.c_int32),
                 ("K", C.c_int32), ("k_splits", C.c_int32), ("out", C.c_void_p), ("ldo", C.c_int64),
                 ("bias", C.c_void_p), ("act", C.c_void_p), ("ldact", C.c_int64), ("colsum", C.c_void_p)]
+
+
+class HgFusedHead(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_out", C.c_int32), ("W", C.c_void_p), ("b", C.c_void_p), ("out", C.c_void_p),
+                ("std", C.c_void_p), ("actions", C.c_void_p), ("sigma", C.c_void_p), ("log_prob", C.c_void_p)]
 
 
 class HgHeadNet(C.Structure):
@@ -173,6 +179,8 @@ _SIGNATURES = {
     "hg_gemm_plan_create": (C.c_int, [C.POINTER(HgGemmProblem), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "hg_gemm_plan_run": (C.c_int, [C.c_void_p, _P]),
     "hg_gemm_plan_destroy": (None, [C.c_void_p]),
+    "hg_gemm_plan_create_heads": (C.c_int, [C.POINTER(HgGemmProblem), C.POINTER(HgFusedHead), C.c_int, C.POINTER(C.c_void_p)]),
+    "hg_gemm_plan_run_heads": (C.c_int, [C.c_void_p, _P, C.c_uint64, C.c_uint64, _P]),
     "hg_gae_returns": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
     "hg_ingest_rows": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, C.c_int64, _P, C.c_int64, _P]),
     "hg_gather_rows_bf16": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P]),
@@ -206,7 +214,7 @@ def load(auto_build: bool = True) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.hg_abi_version() != 2:
+    if lib.hg_abi_version() != 3:
         raise HgError("libhgb200.so ABI mismatch")
     _lib = lib
     return lib

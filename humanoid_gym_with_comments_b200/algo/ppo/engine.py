@@ -183,6 +183,17 @@ class MLPEngine:
         self._all_plans.append(handle.value)
         return handle.value
 
+    @staticmethod
+    def can_fuse_heads(nets: Sequence[NetSpec], n_outs: Sequence[int]) -> bool:
+        """The fused last-layer + head launch needs equal depth, last hidden width <= 128 (multiple of 32) and at most
+        16 outputs per head."""
+        depth = {n.num_hidden for n in nets}
+        return (len(depth) == 1 and all(n.hidden[-1] <= 128 and n.hidden[-1] % 32 == 0 for n in nets)
+                and all(1 <= o <= 16 for o in n_outs))
+
+    def run_head_plan(self, plan: int, eps, seed: int, counter: int) -> None:
+        check(self.lib.hg_gemm_plan_run_heads(plan, ptr(eps), seed, counter, current_stream()))
+
     def run_plans(self, plans: List[int]) -> None:
         st = current_stream()
         run = self.lib.hg_gemm_plan_run
@@ -199,10 +210,12 @@ class MLPEngine:
 
     # -- forward of all hidden layers ---------------------------------------------------------
     def forward_hidden(self, nets: Sequence[NetSpec], inputs: Dict[str, torch.Tensor], in_cols: Dict[str, int],
-                       ws: Workspace, rows: int, make_plans: bool = False):
+                       ws: Workspace, rows: int, make_plans: bool = False, heads=None):
         """inputs[name]: bf16 [rows, ld] (ld multiple of 8; only the first in_cols[name] columns are read).
         Fills ws.h[name][l] = elu(W_l h_{l-1} + b_l) for every hidden layer, one grouped launch per depth.
-        With make_plans=True nothing is launched: the prepared launches are returned for `run_plans`."""
+        With make_plans=True nothing is launched: the prepared launches are returned for `run_plans`.
+        heads (plans only): {net name: HgFusedHead} -- the LAST depth becomes one fused launch (last hidden layer +
+        output layer + sampling, `run_head_plan`); its activations are not written to ws.h."""
         plans = []
         depth = max(n.num_hidden for n in nets)
         for l in range(depth):
@@ -220,7 +233,14 @@ class MLPEngine:
                     M=rows, N=lin.out_features, K=k, k_splits=1, out=ptr(out), ldo=out.stride(0),
                     bias=ptr(lin.bias.data), act=0, ldact=0, colsum=0))
                 ns.append(lin.out_features)
-            if make_plans:
+            if make_plans and heads is not None and l == depth - 1:
+                hs = [heads[net.name] for net in nets if l < net.num_hidden]
+                arr, harr = (HgGemmProblem * len(probs))(*probs), (_lib.HgFusedHead * len(hs))(*hs)
+                handle = C.c_void_p()
+                check(self.lib.hg_gemm_plan_create_heads(arr, harr, len(probs), C.byref(handle)))
+                self._all_plans.append(handle.value)
+                plans.append(handle.value)
+            elif make_plans:
                 plans.append(self._plan(probs, EPI_BIAS_ELU_BF16, self._block_n(ns, "fwd", rows)))
             else:
                 self._launch(probs, EPI_BIAS_ELU_BF16, self._block_n(ns, "fwd", rows))

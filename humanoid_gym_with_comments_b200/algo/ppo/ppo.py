@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 import torch.optim as optim
 
@@ -169,6 +171,7 @@ class PPO:
         self._seed = int(torch.initial_seed()) & (2 ** 64 - 1)
         self._gamma_f = float(gamma)
         self.eps_override = None     # callable(step) -> [N, A] standard-normal draws
+        self.fuse_rollout_head = os.environ.get("HG_FUSE_HEAD", "1") != "0"   # last hidden layer + output layer + sampling in one launch
         self.perm_override = None    # int64 [num_mini_batches * mini_batch_size] permutation
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
@@ -194,9 +197,18 @@ class PPO:
             N, A = st.num_envs, ac.num_actions
             _, _, o16, p16 = st.slot(t)
             ws = ac.workspace(N)
-            gemms = eng.forward_hidden((ac.net_actor, ac.net_critic), {"actor": o16, "critic": p16},
-                                       {"actor": st.obs_cols, "critic": st.priv_cols}, ws, N, make_plans=True)
             la, lc = ac.net_actor.linears[-1], ac.net_critic.linears[-1]
+            heads = None
+            if self.fuse_rollout_head and eng.can_fuse_heads((ac.net_actor, ac.net_critic), (A, 1)):
+                heads = {"actor": _lib.HgFusedHead(kind=_lib.HEAD_POLICY, n_out=A, W=ptr(la.weight.data), b=ptr(la.bias.data),
+                                                   out=ptr(st.mu[t]), std=ptr(ac.std.data), actions=ptr(st.actions[t]),
+                                                   sigma=ptr(st.sigma[t]), log_prob=ptr(st.actions_log_prob[t])),
+                         "critic": _lib.HgFusedHead(kind=_lib.HEAD_LINEAR, n_out=1, W=ptr(lc.weight.data), b=ptr(lc.bias.data),
+                                                    out=ptr(st.values[t]))}
+            gemms = eng.forward_hidden((ac.net_actor, ac.net_critic), {"actor": o16, "critic": p16},
+                                       {"actor": st.obs_cols, "critic": st.priv_cols}, ws, N, make_plans=True, heads=heads)
+            if heads is not None:
+                gemms = (gemms[:-1], gemms[-1])          # (plain plans, fused last-layer + head plan)
             ha, hc = ws.h["actor"][-1], ws.h["critic"][-1]
             views = dict(actions=st.actions[t], values=st.values[t], log_prob=st.actions_log_prob[t].view(-1),
                          mu=st.mu[t], sigma=st.sigma[t], rewards=st.rewards[t].view(-1))
@@ -219,14 +231,18 @@ class PPO:
         gemms, head_args, head_out, views, _ = self._slot_plan(t)
         if not st.holds(obs, critic_obs, t):          # a bound env already wrote this slot and its bf16 shadow
             st.ingest(obs, critic_obs, t)
-        ac._engine.run_plans(gemms)
         if self.eps_override is not None:
             eps = self.eps_override(t).to(st.actions.device).float().contiguous()
         else:
             eps = torch.randn(head_out[0], head_out[1], device=st.actions.device) if self.torch_rng else None
         ac._rng_counter += 1
-        check(self._lib.hg_policy_head_rollout(*head_args, ptr(eps), self._seed, ac._rng_counter, *head_out,
-                                               current_stream()))
+        if isinstance(gemms, tuple):                  # last hidden layer, output layers and sampling in one launch
+            ac._engine.run_plans(gemms[0])
+            ac._engine.run_head_plan(gemms[1], eps, self._seed, ac._rng_counter)
+        else:
+            ac._engine.run_plans(gemms)
+            check(self._lib.hg_policy_head_rollout(*head_args, ptr(eps), self._seed, ac._rng_counter, *head_out,
+                                                   current_stream()))
         tr = self.transition
         tr.actions = views["actions"]
         tr.values = views["values"]

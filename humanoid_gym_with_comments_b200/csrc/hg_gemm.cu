@@ -45,7 +45,9 @@ struct Cfg {
   static constexpr int EPI_WARPS = F32_OUT ? 8 : HG_EPI_WARPS;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int COL_SPLIT = EPI_WARPS / 4;       // column slices per tile
-  static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILE_BYTES;
+  // HEAD: [16][128] fp32 output weights + [4 slices][128][17] fp32 partial sums + per-output constants
+  static constexpr int HEAD_BYTES = (16 * 128 + 4 * 128 * 17 + 64) * 4;
+  static constexpr int EPI_BYTES = (EPI == HG_EPI_BIAS_ELU_HEAD) ? HEAD_BYTES : EPI_WARPS * EPI_TILE_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET - EPI_BYTES) / STAGE_BYTES;  // 3..7 deep TMA ring
   static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
   static_assert(STAGES >= 3, "pipeline too shallow");
@@ -71,6 +73,10 @@ struct alignas(64) GroupParams {
   DevProblem p[HG_MAX_GROUP];
   int num_problems;
   int total_tiles;
+  // HG_EPI_BIAS_ELU_HEAD only: the fused output layers and the sampling stream of this launch
+  HgFusedHead heads[HG_MAX_GROUP];
+  const float* eps;
+  unsigned long long seed, counter;
 };
 
 struct Tile {
@@ -290,6 +296,121 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
       float s = warp_colsum32(d, lane);
       if (n0 + lane < q.N) atomicAdd(q.colsum + n0 + lane, s);
     }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ fused rollout head
+// Epilogue of HG_EPI_BIAS_ELU_HEAD (16 epilogue warps = 4 TMEM lane quarters x 4 column slices of 32): every warp turns
+// its 32 x 32 accumulator chunk into h = bf16(elu(acc + bias)), multiplies it with the staged fp32 output weights and
+// writes its partial sums to the tile's [slice][128 rows][n_out] array in shared memory; after a barrier among the
+// epilogue warps, one thread per row adds the four slices IN A FIXED ORDER (rollouts stay bit-reproducible) and
+// finishes the head (policy: sample + log-prob; linear: value).
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <int BLOCK_N, int CG>
+__device__ __forceinline__ void head_epilogue(const GroupParams& P, float* sm, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                              uint32_t tmem_base, int group_id, int num_groups, int warp, int lane) {
+  static_assert(BLOCK_N == 128 || CG >= 1, "");
+  float* sW = sm;                    // [16][128]
+  float* sAcc = sm + 16 * 128;       // [4][128][17]
+  float* sB = sAcc + 4 * 128 * 17;   // [16] output bias, [16] std
+  const int quad = warp & 3, slice = (warp - 4) >> 2;
+  const int et = (warp - 4) * 32 + lane;       // 0..511
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int t = group_id; t < P.total_tiles; t += num_groups) {
+    const Tile ti = decode_tile(P, t);
+    const DevProblem& q = P.p[ti.g];
+    const HgFusedHead& hd = P.heads[ti.g];
+    const int n_out = hd.n_out;
+    for (int i = et; i < n_out * q.N; i += 512) {
+      const int a = i / q.N, k = i - a * q.N;
+      sW[a * 128 + k] = __ldg(hd.W + i);
+    }
+    if (et < n_out) {
+      sB[et] = __ldg(hd.b + et);
+      sB[16 + et] = hd.kind == HG_HEAD_POLICY ? __ldg(hd.std + et) : 0.f;
+    }
+    epi_bar_sync();
+    mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+    tc_fence_after();
+    const int n0 = slice * 32;
+    const int rt = quad * 32 + lane;           // row inside the tile
+    const bool live = n0 < q.N;                // N % 32 == 0: a live chunk is a full chunk
+    uint32_t v[32];
+    if (live) {
+      tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + n0, v);
+      tmem_ld_wait();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));      // accumulator is in registers: hand it back
+    if (live) {
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(v[j]) + (q.bias ? __ldg(q.bias + n0 + j) : 0.f);
+        const float e = x > 0.f ? x : exp2f_fast(x * 1.4426950408889634f) - 1.f;
+        z[j] = __bfloat162float(__float2bfloat16_rn(e));     // what the stored activation would hold
+      }
+      for (int a = 0; a < n_out; ++a) {
+        const float4* w4 = reinterpret_cast<const float4*>(sW + a * 128 + n0);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 wa = w4[j >> 2], wb = w4[(j >> 2) + 1];
+          s0 += z[j] * wa.x + z[j + 1] * wa.y + z[j + 2] * wa.z + z[j + 3] * wa.w;
+          s1 += z[j + 4] * wb.x + z[j + 5] * wb.y + z[j + 6] * wb.z + z[j + 7] * wb.w;
+        }
+        sAcc[(slice * 128 + rt) * 17 + a] = s0 + s1;
+      }
+    } else {
+      for (int a = 0; a < n_out; ++a) sAcc[(slice * 128 + rt) * 17 + a] = 0.f;
+    }
+    epi_bar_sync();
+    const int row = ti.m_blk * BLOCK_M + rt;
+    // every thread of the row's four slices finishes `per` outputs (fixed-order sum of the slice partials), so the
+    // sampling / log-prob math is spread over all 512 epilogue threads
+    auto dot = [&](int a) {
+      return ((sAcc[rt * 17 + a] + sAcc[(128 + rt) * 17 + a]) + sAcc[(256 + rt) * 17 + a]) + sAcc[(384 + rt) * 17 + a];
+    };
+    const int per = (n_out + 3) >> 2, a_lo = slice * per, a_hi = min(n_out, a_lo + per);
+    float lp = 0.f;
+    if (row < q.M) {
+      if (hd.kind == HG_HEAD_POLICY) {
+        int have = -1;
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int a = a_lo; a < a_hi; ++a) {
+          if (P.eps == nullptr && (a >> 2) != have) {      // four normals per Philox call, keyed by (row, a / 4)
+            have = a >> 2;
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)have, (uint32_t)P.counter, (uint32_t)(P.counter >> 32)),
+                                          make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+            const float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
+            e[0] = n01.x; e[1] = n01.y; e[2] = n23.x; e[3] = n23.y;
+          }
+          const int k = a & 3;
+          const float m = dot(a) + sB[a], sd = sB[16 + a];
+          const float ee = P.eps ? __ldg(P.eps + (long long)row * n_out + a) : (k == 0 ? e[0] : k == 1 ? e[1] : k == 2 ? e[2] : e[3]);
+          const float act = m + sd * ee;                         // Normal(mu, std).sample()  (actor_critic.py:129,133)
+          const float d = act - m;
+          lp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;   // Normal.log_prob
+          hd.actions[(long long)row * n_out + a] = act;
+          hd.out[(long long)row * n_out + a] = m;
+          hd.sigma[(long long)row * n_out + a] = sd;
+        }
+      } else {
+        for (int a = a_lo; a < a_hi; ++a) hd.out[(long long)row * n_out + a] = dot(a) + sB[a];
+      }
+    }
+    if (hd.kind == HG_HEAD_POLICY) {       // (uniform per tile) log-prob = fixed-order sum of the four slices' terms
+      epi_bar_sync();                      // every dot() has been read: the partial-sum array can be reused
+      sAcc[slice * 128 + rt] = lp;
+      epi_bar_sync();
+      if (slice == 0 && row < q.M) hd.log_prob[row] = ((sAcc[rt] + sAcc[128 + rt]) + sAcc[256 + rt]) + sAcc[384 + rt];
+    }
+    epi_bar_sync();          // the next tile re-stages sW / sAcc
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
   }
 }
 
@@ -519,6 +640,9 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
     float* tile = epi_tiles + (warp - 4) * (K::EPI_TILE_BYTES / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (EPI == HG_EPI_BIAS_ELU_HEAD) {
+      head_epilogue<BLOCK_N, CG>(P, epi_tiles, tfull_bar, tempty_bar, tmem_base, group_id, num_groups, warp, lane);
+    } else {
     // Measured on B200 (tools/bench_gemm_dx.py, 61440 x {512,768} x 256): sixteen epilogue warps with the plain loop
     // below beat eight by ~20 %; double-buffering the TMEM loads or fetching the DELU activations a tile ahead costs
     // more in registers (640 threads -> 102 per thread) than it hides in latency, so neither is done.
@@ -563,6 +687,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
     }
   }
 
@@ -640,6 +765,7 @@ static int dispatch_epi(const GroupParams& gp, int epi, cudaStream_t s) {
 }
 
 static int dispatch(const GroupParams& gp, int epi, int block_n, int cg, cudaStream_t s) {
+  if (epi == HG_EPI_BIAS_ELU_HEAD) return launch<128, HG_EPI_BIAS_ELU_HEAD, 1>(gp, s);   // validated: block_n 128, cg 1
   if (cg == 2) return block_n == 128 ? dispatch_epi<128, 2>(gp, epi, s) : dispatch_epi<256, 2>(gp, epi, s);
   return block_n == 128 ? dispatch_epi<128, 1>(gp, epi, s) : dispatch_epi<256, 1>(gp, epi, s);
 }
@@ -652,7 +778,9 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
   HG_CHECK(cg == 1 || cg == 2, "cta_group must be 1 or 2");
   HG_CHECK(pr != nullptr && n >= 1 && n <= HG_MAX_GROUP, "num_problems must be in [1,%d]", HG_MAX_GROUP);
   HG_CHECK(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
-  HG_CHECK(epilogue >= HG_EPI_STORE_F32 && epilogue <= HG_EPI_BIAS_BF16, "unknown epilogue %d", epilogue);
+  HG_CHECK(epilogue >= HG_EPI_STORE_F32 && epilogue <= HG_EPI_BIAS_ELU_HEAD, "unknown epilogue %d", epilogue);
+  const bool fused_head = epilogue == HG_EPI_BIAS_ELU_HEAD;
+  HG_CHECK(!fused_head || (block_n == 128 && cg == 1), "the fused-head epilogue needs block_n 128 and cta_group 1");
   memset(&gp, 0, sizeof(gp));
   gp.num_problems = n;
   int tiles = 0;
@@ -660,7 +788,8 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
     const HgGemmProblem& h = pr[g];
     DevProblem& q = gp.p[g];
     HG_CHECK(h.M > 0 && h.N > 0 && h.K > 0, "problem %d: empty dims", g);
-    HG_CHECK(h.A && h.B && h.out, "problem %d: null pointer", g);
+    HG_CHECK(h.A && h.B && (h.out || fused_head), "problem %d: null pointer", g);
+    HG_CHECK(!fused_head || (h.N <= 128 && h.N % 32 == 0), "problem %d: the fused head needs N <= 128, N %% 32 == 0", g);
     HG_CHECK(h.k_splits >= 1, "problem %d: k_splits", g);
     HG_CHECK(h.k_splits == 1 || epilogue == HG_EPI_ATOMIC_F32, "split-K needs the atomic epilogue");
     HG_CHECK(epilogue != HG_EPI_DELU_BF16 || h.act, "problem %d: DELU epilogue needs act", g);
@@ -702,6 +831,7 @@ struct HgGemmPlan {
 
 extern "C" int hg_gemm_grouped(const HgGemmProblem* pr, int n, int epilogue, int block_n, int cta_group, void* stream) {
   using namespace hg;
+  HG_CHECK(epilogue != HG_EPI_BIAS_ELU_HEAD, "HG_EPI_BIAS_ELU_HEAD launches go through hg_gemm_plan_create_heads");
   GroupParams gp;
   int rc = build_params(pr, n, epilogue, block_n, cta_group, gp);
   if (rc != HG_OK) return rc;
@@ -711,6 +841,7 @@ extern "C" int hg_gemm_grouped(const HgGemmProblem* pr, int n, int epilogue, int
 extern "C" int hg_gemm_plan_create(const HgGemmProblem* pr, int n, int epilogue, int block_n, int cta_group, HgGemmPlan** out) {
   using namespace hg;
   HG_CHECK(out != nullptr, "hg_gemm_plan_create: null output");
+  HG_CHECK(epilogue != HG_EPI_BIAS_ELU_HEAD, "HG_EPI_BIAS_ELU_HEAD plans are made by hg_gemm_plan_create_heads");
   HgGemmPlan* plan = new HgGemmPlan();
   int rc = build_params(pr, n, epilogue, block_n, cta_group, plan->gp);
   if (rc != HG_OK) {
@@ -727,7 +858,45 @@ extern "C" int hg_gemm_plan_create(const HgGemmProblem* pr, int n, int epilogue,
 extern "C" int hg_gemm_plan_run(const HgGemmPlan* plan, void* stream) {
   using namespace hg;
   HG_CHECK(plan != nullptr, "hg_gemm_plan_run: null plan");
+  HG_CHECK(plan->epilogue != HG_EPI_BIAS_ELU_HEAD, "hg_gemm_plan_run: fused-head plans run through hg_gemm_plan_run_heads");
   return dispatch(plan->gp, plan->epilogue, plan->block_n, plan->cta_group, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" void hg_gemm_plan_destroy(HgGemmPlan* plan) { delete plan; }
+
+extern "C" int hg_gemm_plan_create_heads(const HgGemmProblem* pr, const HgFusedHead* heads, int n, HgGemmPlan** out) {
+  using namespace hg;
+  HG_CHECK(out != nullptr && heads != nullptr, "hg_gemm_plan_create_heads: null argument");
+  static_assert(HG_EPI_WARPS == 16, "the fused-head epilogue synchronises 16 epilogue warps");
+  HgGemmPlan* plan = new HgGemmPlan();
+  int rc = build_params(pr, n, HG_EPI_BIAS_ELU_HEAD, 128, 1, plan->gp);
+  for (int g = 0; rc == HG_OK && g < n; ++g) {
+    const HgFusedHead& h = heads[g];
+    const bool ok = (h.kind == HG_HEAD_POLICY || h.kind == HG_HEAD_LINEAR) && h.n_out >= 1 && h.n_out <= 16 && h.W && h.b && h.out &&
+                    (h.kind != HG_HEAD_POLICY || (h.std && h.actions && h.sigma && h.log_prob));
+    if (!ok) {
+      set_error("hg_gemm_plan_create_heads: bad head %d", g);
+      rc = HG_ERR_INVALID;
+    }
+    plan->gp.heads[g] = h;
+  }
+  if (rc != HG_OK) {
+    delete plan;
+    return rc;
+  }
+  plan->epilogue = HG_EPI_BIAS_ELU_HEAD;
+  plan->block_n = 128;
+  plan->cta_group = 1;
+  *out = plan;
+  return HG_OK;
+}
+
+extern "C" int hg_gemm_plan_run_heads(const HgGemmPlan* plan, const float* eps, uint64_t seed, uint64_t counter, void* stream) {
+  using namespace hg;
+  HG_CHECK(plan != nullptr && plan->epilogue == HG_EPI_BIAS_ELU_HEAD, "hg_gemm_plan_run_heads: not a fused-head plan");
+  GroupParams gp = plan->gp;
+  gp.eps = eps;
+  gp.seed = seed;
+  gp.counter = counter;
+  return dispatch(gp, HG_EPI_BIAS_ELU_HEAD, 128, 1, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -14,37 +14,7 @@
 
 namespace hg {
 
-constexpr float LOG_SQRT_2PI = 0.9189385332046727f;  // log(sqrt(2*pi)) as torch.distributions.Normal uses it
 constexpr float HALF_LOG_2PI_PLUS_HALF = 1.4189385332046727f;
-
-// ------------------------------------------------------------------------------------------ Philox4x32-10
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u;
-    key.y += 0xBB67AE85u;
-  }
-  return ctr;
-}
-__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-  const float u1 = (a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
-  const float u2 = b * 2.3283064365386963e-10f;
-  const float r = sqrtf(-2.0f * logf(u1));
-  float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  return make_float2(r * c, r * s);
-}
-// standard normal number `j` of row `row` for (seed, counter)
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t counter, uint32_t row, uint32_t j) {
-  uint4 r = philox4x32_10(make_uint4(row, j >> 2, (uint32_t)counter, (uint32_t)(counter >> 32)),
-                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
-  const int k = j & 3;
-  return k == 0 ? n01.x : k == 1 ? n01.y : k == 2 ? n23.x : n23.y;
-}
 
 // ------------------------------------------------------------------------------------------ shared helpers
 // Stage `rows` rows of a bf16 activation matrix into shared memory as [rows][H + 8] (the +8 keeps 16-byte row

@@ -21,7 +21,7 @@ extern "C" {
 #define HG_ERR_INVALID (-1)
 #define HG_ERR_CUDA (-2)
 
-#define HG_ABI_VERSION 2
+#define HG_ABI_VERSION 3
 
 const char* hg_last_error(void);
 int hg_abi_version(void);
@@ -47,7 +47,8 @@ enum HgEpilogue {
   HG_EPI_DELU_BF16 = 2,     /* out bf16 [M,ldo] = acc * elu'(act[m,n]); colsum[n] += column sums      */
                             /*   (dX of a Linear, times ELU' of the layer below, + its bias gradient) */
   HG_EPI_ATOMIC_F32 = 3,    /* out f32 [M,ldo] += acc   (split-K weight gradient)                     */
-  HG_EPI_BIAS_BF16 = 4      /* out bf16 [M,ldo] = acc + bias[n]                                       */
+  HG_EPI_BIAS_BF16 = 4,     /* out bf16 [M,ldo] = acc + bias[n]                                       */
+  HG_EPI_BIAS_ELU_HEAD = 5  /* elu(acc + bias[n]) is NOT stored: it feeds a fused output layer (HgFusedHead)  */
 };
 
 typedef struct HgGemmProblem {
@@ -79,6 +80,29 @@ int hg_gemm_plan_create(const HgGemmProblem* problems_host, int num_problems, in
                         HgGemmPlan** out);
 int hg_gemm_plan_run(const HgGemmPlan* plan, void* stream);
 void hg_gemm_plan_destroy(HgGemmPlan* plan);
+
+/* Rollout only: the LAST hidden layer of each net together with its output layer and everything PPO.act does with it
+ * (actor_critic.py:127-148, ppo.py:116-126).  One 128-row tile holds complete rows of the last hidden layer (N <= 128),
+ * so the epilogue rounds elu(acc + bias) to bf16 (the value the update's forward pass will see), multiplies by the
+ * fp32 output weights and
+ *   HG_HEAD_POLICY: mu = W h + b, a = mu + std * eps, log-prob of a        -> out (mu), actions, sigma, log_prob
+ *   HG_HEAD_LINEAR: out = W h + b                                         (critic value)
+ * eps is an optional [M, n_out] tensor of externally drawn normals; NULL -> Philox4x32-10 keyed by (seed, counter),
+ * the same stream as hg_policy_head_rollout.  Requires block_n = 128, cta_group = 1, N <= 128, N % 32 == 0, n_out <= 16. */
+enum HgHeadKind { HG_HEAD_NONE = 0, HG_HEAD_POLICY = 1, HG_HEAD_LINEAR = 2 };
+typedef struct HgFusedHead {
+  int32_t kind, n_out;
+  const float* W;      /* f32 [n_out, N] */
+  const float* b;      /* f32 [n_out] */
+  float* out;          /* f32 [M, n_out] */
+  const float* std;    /* POLICY: f32 [n_out] */
+  float* actions;      /* POLICY: f32 [M, n_out] */
+  float* sigma;        /* POLICY: f32 [M, n_out] */
+  float* log_prob;     /* POLICY: f32 [M] */
+} HgFusedHead;
+int hg_gemm_plan_create_heads(const HgGemmProblem* problems_host, const HgFusedHead* heads_host, int num_problems,
+                              HgGemmPlan** out);
+int hg_gemm_plan_run_heads(const HgGemmPlan* plan, const float* eps, uint64_t seed, uint64_t counter, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * GAE: replaces RolloutStorage.compute_returns (humanoid/algo/ppo/rollout_storage.py:122-143).

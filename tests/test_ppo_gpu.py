@@ -319,3 +319,36 @@ def test_cpu_tensors_are_rejected():
         alg.act(torch.zeros(8, 705), torch.zeros(8, 219))
     with pytest.raises(HgError):
         RolloutStorage(8, 2, [705], [219], [12], device="cpu")
+
+
+@pytest.mark.parametrize("N", [200, 4096])
+def test_fused_rollout_head_matches_separate_head_kernel(N):
+    """PPO.act through the fused launch (last hidden GEMM + output layers + sampling, HG_EPI_BIAS_ELU_HEAD) against the
+    same step through hg_policy_head_rollout: identical Philox stream and identical external eps, fp32 round-off only."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    obs = torch.randn(N, 705, device=DEV, generator=g)
+    priv = torch.randn(N, 219, device=DEV, generator=g)
+    eps = torch.randn(N, 12, device=DEV, generator=g)
+    outs = {}
+    for fused in (True, False):
+        for mode in ("eps", "philox"):
+            alg, _ = make_alg(N, 2, seed=3)
+            with torch.no_grad():
+                alg.actor_critic.std.fill_(0.7)
+            alg.fuse_rollout_head = fused
+            alg.torch_rng = False
+            alg.eps_override = (lambda t: eps) if mode == "eps" else None
+            alg._seed = 1234
+            with torch.inference_mode():
+                a = alg.act(obs, priv).clone()
+            st = alg.storage
+            assert isinstance(alg._slot_plan(0)[0], tuple) == fused
+            outs[(fused, mode)] = (a, st.mu[0].clone(), st.sigma[0].clone(), st.actions_log_prob[0].clone(), st.values[0].clone())
+    torch.cuda.synchronize()
+    for mode in ("eps", "philox"):
+        for name, x, y in zip(("actions", "mu", "sigma", "log_prob", "values"), outs[(True, mode)], outs[(False, mode)]):
+            assert torch.allclose(x, y, rtol=1e-5, atol=2e-5), (mode, name, float((x - y).abs().max()))
+    # the external-eps run also matches the definition: a = mu + sigma * eps
+    a, mu, sigma, _, _ = outs[(True, "eps")]
+    assert torch.allclose(a, mu + sigma * eps, atol=1e-6)
+    assert float((outs[(True, "philox")][0] - outs[(True, "eps")][0]).abs().max()) > 0.1      # a different stream indeed

@@ -14,9 +14,13 @@ with contextlib.redirect_stdout(io.StringIO()):
 alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0.994, lam=0.9, value_loss_coef=1.0,
           entropy_coef=0.001, learning_rate=1e-5, max_grad_norm=1.0, schedule="adaptive", desired_kl=0.01, device=dev)
 alg.init_storage(N, T, [705], [219], [12])
-env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev)
+env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, torch_rng_noise=False)
+env.bind_storage(alg.storage)
+alg.torch_rng = False
 obs, cobs = env.get_observations(), env.get_privileged_observations()
-for it in range(iters):
+for it in range(iters + 1):        # iteration 0 warms up (plans, workspaces); profile the rest with --profile-from-start off
+    if it == 1:
+        torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStart()
     with torch.inference_mode():
         for i in range(T):
             a = alg.act(obs, cobs)
@@ -25,3 +29,4 @@ for it in range(iters):
         alg.compute_returns(cobs)
     print(alg.update())
 torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
