@@ -209,7 +209,7 @@ def run_ours(a):
     torch.manual_seed(1000 + rank)               # per-rank env / sampling streams
     env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, pool=4, seed=rank, torch_rng_noise=a.torch_rng)
     if not a.unbound_env:
-        env.bind_storage(alg.storage)
+        env.bind_storage(alg.storage, gamma=alg.gamma)
     obs, critic_obs = env.get_observations(), env.get_privileged_observations()
     state = {"obs": obs, "critic_obs": critic_obs}
     h2d_bytes_per_env_step = sum(v.numel() * v.element_size() for v in env.pool[0].values())

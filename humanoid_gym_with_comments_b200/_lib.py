@@ -159,7 +159,8 @@ class HgEnvBuffers(C.Structure):
                 ("priv_next", C.c_void_p), ("priv_next_ld", C.c_int64),
                 ("obs16_next", C.c_void_p), ("obs16_next_ld", C.c_int64),
                 ("priv16_next", C.c_void_p), ("priv16_next_ld", C.c_int64)] + \
-               [(n, C.c_void_p) for n in ("rew_buf", "reset_buf", "time_out_buf", "reward_terms")]
+               [(n, C.c_void_p) for n in ("rew_buf", "reset_buf", "time_out_buf", "reward_terms", "store_values",
+                                          "store_rewards", "store_dones")] + [("store_gamma", C.c_float)]
 
 
 class HgActionArgs(C.Structure):

@@ -258,6 +258,14 @@ class PPO:
         t = st.step
         if t >= st.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
+        stored = getattr(st, "env_stored", None)
+        if stored is not None and stored == (t, rewards.data_ptr(), dones.data_ptr(), self._gamma_f):
+            # a bound env (SyntheticXBotEnv.bind_storage(storage, gamma)) already wrote this transition's record
+            st.env_stored = None
+            st.step = t + 1
+            self.transition.clear()
+            self.actor_critic.reset(dones)
+            return
         val_ptr, rew_ptr, done_ptr = self._slot_plan(t)[4]
         if not (rewards.is_cuda and dones.is_cuda):
             _lib.require_cuda(rewards, dones)

@@ -452,6 +452,10 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
     }
     if (C.only_positive_rewards) rew = fmaxf(rew, 0.f);                              // :899-900
     B.rew_buf[n] = rew;
+    if (B.store_rewards) {       // the learner's transition record (same rounding as hg_store_rewards_dones)
+      B.store_rewards[n] = __fadd_rn(rew, __fmul_rn(B.store_gamma, __fmul_rn(B.store_values[n], s_tout[lane] ? 1.f : 0.f)));
+      B.store_dones[n] = reset ? 1 : 0;
+    }
   }
   if (!doB) return;
   if (!doA && ok && warp == 1 && s_reset[lane]) {
@@ -578,6 +582,9 @@ extern "C" int hg_env_step(const HgEnvConfig* cfg, const HgEnvBuffers* buf, void
                buf->ref_dof_pos && buf->episode_length_buf && buf->episode_sums && buf->obs_prev && buf->priv_prev &&
                buf->obs_next && buf->priv_next && buf->rew_buf && buf->reset_buf && buf->time_out_buf,
            "hg_env_step: null buffer");
+  HG_CHECK((buf->store_rewards != nullptr) == (buf->store_dones != nullptr) && (buf->store_rewards != nullptr) == (buf->store_values != nullptr),
+           "hg_env_step: store_values / store_rewards / store_dones go together");
+  HG_CHECK(!buf->store_rewards || (cfg->phases & HG_ENV_PHASE_REWARD), "hg_env_step: the transition store needs the reward phase");
   const int blocks = (cfg->num_envs + ENV_PER_BLOCK - 1) / ENV_PER_BLOCK;
   const int So = 11 + 3 * cfg->D, Sp = 25 + 4 * cfg->D;
   const size_t smem = (size_t)(ENV_PER_BLOCK * (So + Sp) + HG_NUM_REWARDS * ENV_PER_BLOCK + 4 * ENV_PER_BLOCK) * 4;

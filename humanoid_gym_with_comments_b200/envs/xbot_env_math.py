@@ -240,13 +240,15 @@ class XBotEnvMath:
     def step(self, sim: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None, phases: int = ENV_PHASE_ALL,
              obs_out: Optional[torch.Tensor] = None, priv_out: Optional[torch.Tensor] = None,
              obs16_out: Optional[torch.Tensor] = None, priv16_out: Optional[torch.Tensor] = None,
-             raw_actions: Optional[torch.Tensor] = None, clip_actions: float = 18.0):
+             raw_actions: Optional[torch.Tensor] = None, clip_actions: float = 18.0, store=None):
         """One fused post-physics step on the Isaac-Gym-shaped tensors in `sim` (keys: root_states, dof_state,
         contact_forces, rigid_state, commands, torques, rand_push_force, rand_push_torque, env_frictions, body_mass;
         optional `actions` [N,D] = the actions applied this step, copied into `self.actions` first).
         `noise`: N(0,1) draws [N, num_single_obs] (the reference's `randn_like`, :877) or None for in-kernel Philox.
         `obs_out` / `priv_out` (+ optional bf16 shadows `obs16_out` / `priv16_out`): destinations, e.g. the learner's
         next storage slot, instead of the internal double buffer.
+        `store` = (values, rewards_out, dones_out, gamma): also write the learner's transition record
+        rewards_out = rew + gamma * values * time_out, dones_out = reset (what PPO.process_env_step would store).
         Returns (obs_buf, privileged_obs_buf, rew_buf, reset_buf, time_out_buf)."""
         acts = sim.get("actions")
         if acts is not None:
@@ -272,6 +274,10 @@ class XBotEnvMath:
         else:
             b.priv16_next = 0
         b.reward_terms = ptr(self.reward_terms)
+        if store is not None:
+            b.store_values, b.store_rewards, b.store_dones, b.store_gamma = ptr(store[0]), ptr(store[1]), ptr(store[2]), store[3]
+        else:
+            b.store_values = b.store_rewards = b.store_dones = 0
         self._c.phases = phases
         check(self._lib.hg_env_step(C.byref(self._c), C.byref(b), current_stream()))
         if phases & 2:
@@ -382,11 +388,14 @@ class SyntheticXBotEnv:
                 self._copy_done[slot].record(self._copy_stream)
                 self._next_prefetch += 1
 
-    def bind_storage(self, storage):
+    def bind_storage(self, storage, gamma: Optional[float] = None):
         """Let `step()` write the next observations (fp32 + bf16 shadow) straight into the learner's next storage
         slot: `PPO.act` then finds them in place and launches no ingest / copy (replaces, together with the env
-        kernel, rollout_storage.py:90-91).  Pass None to unbind."""
+        kernel, rollout_storage.py:90-91).  With `gamma` (the learner's discount) the env kernel also stores the
+        transition's bootstrapped reward and done flag (ppo.py:129-133), and `PPO.process_env_step` launches nothing
+        when it is handed this env's reward / reset buffers.  Pass None to unbind."""
         self._storage = storage
+        self._store_gamma = gamma
 
     def get_observations(self):
         return self.obs_buf
@@ -413,7 +422,13 @@ class SyntheticXBotEnv:
         st = self._storage
         if st is not None and st.step + 1 <= st.num_transitions_per_env:
             o, p, o16, p16 = st.slot(st.step + 1)
-            out = self.math.step(sim, noise, obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16, raw_actions=actions)
+            store = None
+            if getattr(self, "_store_gamma", None) is not None:
+                t = st.step
+                store = (st.values[t], st.rewards[t], st.dones[t], float(self._store_gamma))
+                st.env_stored = (t, self.math.rew_buf.data_ptr(), self.math.reset_buf.data_ptr(), float(self._store_gamma))
+            out = self.math.step(sim, noise, obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16, raw_actions=actions,
+                                 store=store)
         else:
             out = self.math.step(sim, noise, raw_actions=actions)   # clip(+-18) of step() (:633-635) fused in the kernel
         if slot is not None:

@@ -323,6 +323,13 @@ typedef struct HgEnvBuffers {
   uint8_t* reset_buf;           /* [N] */
   uint8_t* time_out_buf;        /* [N] */
   float* reward_terms;          /* [HG_NUM_REWARDS, N] or NULL (debug/parity) */
+  /* optional (all three or none): the learner's transition record for the step these rewards belong to, i.e. what
+   * PPO.process_env_step + RolloutStorage.add_transitions would store (ppo.py:129-133, rollout_storage.py:93-94):
+   *   store_rewards[n] = rew + store_gamma * store_values[n] * time_out,   store_dones[n] = reset */
+  const float* store_values;    /* [N] value estimates of the step that produced the actions */
+  float* store_rewards;         /* [N] */
+  uint8_t* store_dones;         /* [N] */
+  float store_gamma;
 } HgEnvBuffers;
 
 int hg_env_step(const HgEnvConfig* cfg_host, const HgEnvBuffers* buf_host, void* stream);

@@ -247,15 +247,17 @@ def test_bound_env_writes_storage_slots_identically():
     slot.  Must be bit-identical to the generic path (env buffer -> ingest kernel) for a whole rollout, including the
     carry-over of the last observation into the next iteration (slot T -> slot 0).  (After an update the two runs may
     differ in the last bits: gradient sums use fp32 atomics.)"""
+    from humanoid_gym_with_comments_b200 import _lib
     N, T = 256, 6
-    outs = []
-    for bound in (False, True):
+    outs, launches = [], []
+    for bound in (0, 1, 2):           # generic path | obs written into the slots | + transition record stored by the env kernel
         torch.manual_seed(7)
         env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), DEV, seed=3)
         alg, cfg = make_alg(N, T)
         if bound:
-            env.bind_storage(alg.storage)
+            env.bind_storage(alg.storage, gamma=cfg.gamma if bound == 2 else None)
         torch.manual_seed(11)
+        l0 = _lib.load().hg_launch_count()
         obs, critic_obs = env.get_observations(), env.get_privileged_observations()
         res = []
         for it in range(2):
@@ -270,11 +272,14 @@ def test_bound_env_writes_storage_slots_identically():
                                             st.values, st.rewards, st.dones, st.returns, st.advantages)])
             st.clear()                                  # next iteration without an update: weights stay identical
         outs.append(res)
+        launches.append(_lib.load().hg_launch_count() - l0)
     names = ("observations", "privileged_observations", "obs16", "priv16", "actions", "values", "rewards", "dones",
              "returns", "advantages")
-    for it, (a, b) in enumerate(zip(outs[0], outs[1])):
-        for name, x, y in zip(names, a, b):
-            assert torch.equal(x, y), (it, name)
+    for other in (1, 2):
+        for it, (a, b) in enumerate(zip(outs[0], outs[other])):
+            for name, x, y in zip(names, a, b):
+                assert torch.equal(x, y), (other, it, name)
+    assert launches[1] - launches[2] == 2 * T           # one launch less per step: no hg_store_rewards_dones
 
 
 def test_checkpoint_roundtrip_and_export():

@@ -16,7 +16,7 @@ alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0
 alg.init_storage(N, T, [705], [219], [12])
 env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, torch_rng_noise=bool(os.environ.get("HG_TORCH_NOISE")))
 if not os.environ.get("HG_UNBOUND"):
-    env.bind_storage(alg.storage)
+    env.bind_storage(alg.storage, gamma=alg.gamma)
 obs, cobs = env.get_observations(), env.get_privileged_observations()
 acc = [0.0, 0.0, 0.0]
 cpu = [0.0, 0.0, 0.0]

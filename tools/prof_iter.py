@@ -15,7 +15,7 @@ alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0
           entropy_coef=0.001, learning_rate=1e-5, max_grad_norm=1.0, schedule="adaptive", desired_kl=0.01, device=dev)
 alg.init_storage(N, T, [705], [219], [12])
 env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, torch_rng_noise=False)
-env.bind_storage(alg.storage)
+env.bind_storage(alg.storage, gamma=alg.gamma)
 alg.torch_rng = False
 obs, cobs = env.get_observations(), env.get_privileged_observations()
 for it in range(iters + 1):        # iteration 0 warms up (plans, workspaces); profile the rest with --profile-from-start off
