@@ -307,10 +307,18 @@ def run_ours(a):
         pass
     peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_BF16_TFLOPS))
     achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:      # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture (never measured under ncu here)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_update_gemms.json")))
+        traffic, traffic_src = float(tj["traffic_bytes_per_launch"]), "profiles/r01_ncu_update_gemms.json (dram read + write, mean over one minibatch's 8 launches)"
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "hg::gemm_kernel (grouped tcgen05 GEMM; update-phase launches)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
-                "traffic": None, "launches": sum(v["launches"] for v in upd.values()), "kernel_ms_per_iteration": g_ms,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "flop_per_launch": g_fl / max(1, sum(v["launches"] for v in upd.values())),
+                "launches": sum(v["launches"] for v in upd.values()), "kernel_ms_per_iteration": g_ms,
                 "share_of_iteration": g_ms / iter_ms if iter_ms else None,
                 "by_kind": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                                 "tflops": round(v["flop"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else None}
