@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 
 import os
+import time
 
 import torch
 import torch.optim as optim
@@ -317,6 +318,7 @@ class PPO:
         eng = ac.engine()
         flat = ac.flat
         lib = _lib.load()
+        t_host0 = time.perf_counter()
         self.optimizer.bind()
         if abs(self.learning_rate - self._lr_synced) > 0:       # user changed alg.learning_rate by hand
             self.optimizer.set_lr(self.learning_rate)
@@ -373,6 +375,7 @@ class PPO:
                 self.optimizer.fused_step(rows_global=M * self.world_size, max_grad_norm=self.max_grad_norm,
                                           adaptive=adaptive, desired_kl=self.desired_kl, loss_log=loss_log, log_slot=slot)
                 slot += 1
+        self.last_update_enqueue_ms = (time.perf_counter() - t_host0) * 1e3    # host time to enqueue the whole update
         log = loss_log.cpu()                                      # the single host sync of update()
         self.last_update_log = log
         self.learning_rate = float(log[-1, 5])

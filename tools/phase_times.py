@@ -35,6 +35,7 @@ for it in range(iters + 3):
     ev[2].record(); tc[2] = time.perf_counter()
     alg.update()
     ev[3].record(); tc[3] = time.perf_counter()
+    upd_enq = alg.last_update_enqueue_ms
     torch.cuda.synchronize()
     if it >= 3:
         for k in range(3):
@@ -56,4 +57,4 @@ if os.environ.get("HG_NOSYNC"):
     torch.cuda.synchronize()
     print(f"back-to-back: {e0.elapsed_time(e1) / iters:.3f} ms / iteration")
 print(f"envs {N} T {T} PDL={os.environ.get('HG_PDL', 'default')}: rollout {acc[0]:.3f} ms  returns {acc[1]:.3f} ms  update {acc[2]:.3f} ms  total {sum(acc):.3f} ms"
-      f" | host enqueue: {cpu[0]:.2f} / {cpu[1]:.2f} / {cpu[2]:.2f} ms")
+      f" | host enqueue: {cpu[0]:.2f} / {cpu[1]:.2f} / {cpu[2]:.2f} ms (update enqueue alone {upd_enq:.2f} ms)")
