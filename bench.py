@@ -37,12 +37,13 @@ METRIC = "ppo_env_steps_per_sec"
 UNIT = "env-steps/s"
 NETS = dict(actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128])
 FALLBACK_BF16_TFLOPS = 1400.0     # B200_PROFILING.md fallback (sustained)
+FALLBACK_HBM_GBS = 6650.0       # B200_PROFILING.md fallback
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
@@ -53,6 +54,9 @@ def parse():
     ap.add_argument("--torch-rng", action="store_true",
                     help="draw action / observation noise with torch.randn (stream parity with the reference on the same device) instead of the in-kernel Philox4x32-10")
     ap.add_argument("--unbound-env", action="store_true", help="env writes its own buffers; PPO.act ingests them (generic drop-in path)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' runs the same torch port on cuda:0 at the FULL workload (the torch-CUDA "
+                         "figure north_star's target is quoted against); the default and the driver's arm is 'cpu'")
     return ap.parse_args()
 
 
@@ -140,20 +144,30 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_baseline(a, seconds_budget=20.0, iters=None):
-    """The reference algorithm (oracle restatement: torch CPU fp32, autograd backward, all host threads) on a bounded
-    sample: `cpu_sample_envs` envs x horizon steps, same nets / hyper-parameters / env math.  Returns env-steps/s."""
+def cpu_baseline(a, seconds_budget=20.0, iters=None, device="cpu", envs=None):
+    """The reference algorithm (oracle restatement: torch fp32, autograd backward, all host threads) on a bounded
+    sample: `cpu_sample_envs` envs x horizon steps, same nets / hyper-parameters / env math.  Returns env-steps/s.
+    device="cuda" (only `--impl reference --ref-device cuda`) runs the very same torch code on cuda:0 -- the torch-CUDA
+    figure of the reference's algorithm."""
+    import torch
+    with torch.device(device):
+        return _port_iterations(a, seconds_budget, iters, device, envs)
+
+
+def _port_iterations(a, seconds_budget, iters, device, envs):
     import torch
     from oracle import env_oracle as eo
     from oracle import ppo_oracle as po
     torch.set_num_threads(os.cpu_count() or 1)
-    N, T = a.cpu_sample_envs, a.horizon
+    on_gpu = device != "cpu"
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
+    N, T = envs or a.cpu_sample_envs, a.horizon
     cfg = po.xbot_ppo_config()
     torch.manual_seed(0)
     p = po.init_params(705, 219, 12, (512, 256, 128), (768, 256, 128), (128, 128), 1.0)
     spec = eo.xbot_spec(12)
     est = eo.EnvState(spec, N)
-    g = torch.Generator().manual_seed(0)
+    g = torch.Generator(device=device).manual_seed(0)
     pool = [eo.synthetic_sim_state(spec, N, g) for _ in range(4)]
     st, lr = po.AdamState(), cfg.learning_rate
     out = eo.env_step(spec, est, pool[0], torch.randn(N, spec.So, generator=g))
@@ -182,19 +196,22 @@ def cpu_baseline(a, seconds_budget=20.0, iters=None):
         _, _, _, lr = po.ppo_update(p, st, ro, torch.randperm(N * T), cfg, lr)
 
     iteration(0)                                   # warm-up
+    sync()
     times = []
     t_end = time.perf_counter() + seconds_budget
     i = 1
     while (iters is None and time.perf_counter() < t_end and len(times) < 50) or (iters is not None and len(times) < iters):
         t0 = time.perf_counter()
         iteration(i)
+        sync()
         times.append(time.perf_counter() - t0)
         i += 1
     med = statistics.median(times)
-    return {"value": N * T / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    where = "torch-CUDA fp32 (cuda:0, eager)" if on_gpu else "torch-CPU fp32"
+    return {"value": N * T / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "device": device,
             "sample": f"{N} envs x {T} steps per iteration (env math + rollout + GAE + update), median of {len(times)} "
-                      f"iterations after 1 warm-up, {med * 1e3:.0f} ms/iteration; oracle = torch-CPU fp32 restatement of the "
-                      f"reference pinned bit-exact to it (the reference itself is Python and is not present on this box)"}, med
+                      f"iterations after 1 warm-up, {med * 1e3:.0f} ms/iteration; oracle = {where} restatement of the "
+                      f"reference pinned bit-exact to it on CPU (the reference itself is Python and is not present on this box)"}, med
 
 
 def run_reference(a):
@@ -202,10 +219,14 @@ def run_reference(a):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    base, med = cpu_baseline(a, iters=max(1, a.steps) + 0, seconds_budget=1e9) if a.steps <= 20 else cpu_baseline(a, 60.0)
+    if a.ref_device == "cuda":      # the port on the GPU at the full workload (not the driver's arm: a one-off comparison)
+        base, med = cpu_baseline(a, iters=max(1, a.steps), seconds_budget=1e9, device="cuda", envs=a.envs)
+    else:
+        base, med = cpu_baseline(a, iters=max(1, a.steps) + 0, seconds_budget=1e9) if a.steps <= 20 else cpu_baseline(a, 60.0)
     line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(a, world), "cpu_baseline": base,
+            "ref_device": a.ref_device,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -308,11 +329,20 @@ def run_ours(a):
 
     def probe(self, problems, epi, block_n):
         fl = sum(2.0 * p.M * p.N * p.K for p in problems)
+        # algorithmic HBM bytes of the launch as the layers are laid out (every distinct bf16 operand read once, the
+        # output written once; DELU also reads the activation tile, the split-K RED output is one fp32 write)
+        seen, by = set(), 0.0
+        for p in problems:
+            for key, nbytes in (((p.A, p.M, p.K), 2.0 * p.M * p.K), ((p.B, p.N, p.K), 2.0 * p.N * p.K)):
+                if key not in seen:
+                    seen.add(key)
+                    by += nbytes
+            by += {0: 4.0, 1: 2.0, 2: 4.0, 3: 4.0, 4: 2.0}[epi] * p.M * p.N
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         orig(self, problems, epi, block_n)
         e1.record()
-        records.append((epi, block_n, fl, e0, e1, [(p.M, p.N, p.K) for p in problems]))
+        records.append((epi, block_n, fl, e0, e1, [(p.M, p.N, p.K) for p in problems], by))
 
     eng_mod.MLPEngine._launch = probe
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -323,13 +353,14 @@ def run_ours(a):
     eng_mod.MLPEngine._launch = orig
     iter_ms = ev0.elapsed_time(ev1)
     by_kind = {}
-    for epi, bn, fl, e0, e1, shapes in records:
+    for epi, bn, fl, e0, e1, shapes, by in records:
         big = shapes[0][0] >= 8192 or shapes[0][2] >= 8192
         key = f"{['store','fwd_bias_elu','dx_delu','dw_atomic','bias'][epi]}_bn{bn}_{'update' if big else 'rollout'}"
-        d = by_kind.setdefault(key, {"launches": 0, "ms": 0.0, "flop": 0.0})
+        d = by_kind.setdefault(key, {"launches": 0, "ms": 0.0, "flop": 0.0, "bytes": 0.0})
         d["launches"] += 1
         d["ms"] += e0.elapsed_time(e1)
         d["flop"] += fl
+        d["bytes"] += by
     upd = {k: v for k, v in by_kind.items() if k.endswith("update")}
     g_ms = sum(v["ms"] for v in upd.values())
     g_fl = sum(v["flop"] for v in upd.values())
@@ -339,6 +370,10 @@ def run_ours(a):
     except Exception:
         pass
     peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_BF16_TFLOPS))
+    hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
+    g_by = sum(v["bytes"] for v in upd.values())
+    # the layer-by-layer design sits at the ridge (~190 FLOP/B against 211): per kind, the floor is the slower of the two roofs
+    floor_ms = sum(max(v["flop"] / (peak * 1e12), v["bytes"] / (hbm_peak * 1e9)) * 1e3 for v in upd.values())
     achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
     traffic, traffic_src = None, None
     try:      # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture (never measured under ncu here)
@@ -353,9 +388,52 @@ def run_ours(a):
                 "flop_per_launch": g_fl / max(1, sum(v["launches"] for v in upd.values())),
                 "launches": sum(v["launches"] for v in upd.values()), "kernel_ms_per_iteration": g_ms,
                 "share_of_iteration": g_ms / iter_ms if iter_ms else None,
+                "hbm_view": {"algorithmic_bytes_per_launch": g_by / max(1, sum(v["launches"] for v in upd.values())),
+                             "achieved_gbs": g_by / (g_ms / 1e3) / 1e9 if g_ms > 0 else None, "peak_gbs": hbm_peak,
+                             "frac": g_by / (g_ms / 1e3) / 1e9 / hbm_peak if g_ms > 0 else None,
+                             "frac_of_binding_roof": floor_ms / g_ms if g_ms > 0 else None,
+                             "note": "same launches against the HBM roof: activations round-trip through HBM between the "
+                                     "layer launches, so the short-K launches (dX, critic layer 1, layer 3) are bound by "
+                                     "bytes, not FLOPs; frac_of_binding_roof = sum over kinds of max(tensor floor, HBM floor) / measured"},
                 "by_kind": {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
-                                "tflops": round(v["flop"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else None}
+                                "tflops": round(v["flop"] / (v["ms"] / 1e3) / 1e12, 2) if v["ms"] > 0 else None,
+                                "gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if v["ms"] > 0 else None}
                             for k, v in sorted(by_kind.items())}}
+
+    # ---- the HBM-bound kernels of the path against the measured copy bandwidth (SURVEY 8d figures), CUDA-event timed
+    def time_calls(fn, reps):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps        # us per call
+
+    aux = {}
+    try:
+        st = alg.storage
+        lastv = torch.zeros(N, 1, device=dev)
+        us = time_calls(lambda: st.compute_returns(lastv, alg.gamma, alg.lam), 20)
+        gae_bytes = 25.0 * N * T                     # scan 17 B + normalisation pass 8 B per (t, env)
+        aux["gae_returns"] = {"us": us, "bytes": gae_bytes, "gbs": gae_bytes / us / 1e3, "frac": gae_bytes / us / 1e3 / hbm_peak,
+                              "launches_per_call": 2}
+        acts = torch.zeros(N, 12, device=dev)
+        slot_i = [0]
+
+        def env_once():                              # walks through the storage slots like the rollout does
+            st.step = slot_i[0] % (T - 1)
+            slot_i[0] += 1
+            env.step(acts)
+            st.env_stored = None
+        us = time_calls(env_once, min(T - 1, 40))
+        env_bytes = (4.0 * (47 * 29 + 73 * 5) + 900.0) * N        # SURVEY 8d K-a: history shift + state, D = 12
+        st.step = 0
+        aux["env_step"] = {"us": us, "bytes": env_bytes, "gbs": env_bytes / us / 1e3, "frac": env_bytes / us / 1e3 / hbm_peak,
+                           "launches_per_call": 1}
+    except Exception as e:       # never lose the headline line to an auxiliary measurement
+        aux["error"] = repr(e)
 
     base = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -366,7 +444,7 @@ def run_ours(a):
                 "dtype": "bf16 tensor-core GEMMs with fp32 accumulate; fp32 elsewhere", "data": "synthetic",
                 "config": workload_config(a, world), "clocks": clocks.summary(), "e2e": e2e,
                 "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
-                "roofline": roofline, "cpu_baseline": base}
+                "roofline": roofline, "hbm_kernels": aux, "cpu_baseline": base}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
