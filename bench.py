@@ -354,7 +354,7 @@ def run_ours(a):
     iter_ms = ev0.elapsed_time(ev1)
     by_kind = {}
     for epi, bn, fl, e0, e1, shapes, by in records:
-        big = shapes[0][0] >= 8192 or shapes[0][2] >= 8192
+        big = not (shapes[0][0] == N or shapes[0][2] == N)      # rollout launches have N rows, update launches N*T/4
         key = f"{['store','fwd_bias_elu','dx_delu','dw_atomic','bias'][epi]}_bn{bn}_{'update' if big else 'rollout'}"
         d = by_kind.setdefault(key, {"launches": 0, "ms": 0.0, "flop": 0.0, "bytes": 0.0})
         d["launches"] += 1

@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("HG_LIB_PATH") or os.path.join(HERE, "libhgb200.so")   # HG_LIB_PATH: kernel-variant experiments (tools/build_variant.sh)
 BUILD_DIR = os.path.join(HERE, "csrc", "_build")
-SOURCES = ["hg_runtime.cu", "hg_gemm.cu", "hg_gae.cu", "hg_misc.cu", "hg_heads.cu", "hg_optim.cu", "hg_env.cu"]
-EXTRA_FLAGS = {"hg_env.cu": ["-fmad=false"]}
+SOURCES = ["hg_runtime.cu", "hg_gemm.cu", "hg_gae.cu", "hg_misc.cu", "hg_heads.cu", "hg_optim.cu", "hg_env.cu", "hg_env_aux.cu"]
+EXTRA_FLAGS = {"hg_env.cu": ["-fmad=false"], "hg_env_aux.cu": ["-fmad=false"]}
 if os.environ.get("HG_EPI_WARPS"):
     EXTRA_FLAGS["hg_gemm.cu"] = ["-DHG_EPI_WARPS=" + os.environ["HG_EPI_WARPS"]]
 if os.environ.get("HG_GEMM_DEFS"):
@@ -160,7 +160,8 @@ class HgEnvBuffers(C.Structure):
                 ("obs16_next", C.c_void_p), ("obs16_next_ld", C.c_int64),
                 ("priv16_next", C.c_void_p), ("priv16_next_ld", C.c_int64)] + \
                [(n, C.c_void_p) for n in ("rew_buf", "reset_buf", "time_out_buf", "reward_terms", "store_values",
-                                          "store_rewards", "store_dones")] + [("store_gamma", C.c_float)]
+                                          "store_rewards", "store_dones")] + [("store_gamma", C.c_float),
+                                                                              ("root_vel_prepush", C.c_void_p)]
 
 
 class HgActionArgs(C.Structure):
@@ -170,6 +171,17 @@ class HgActionArgs(C.Structure):
                 ("dof_state", C.c_void_p), ("p_gains", C.c_void_p), ("d_gains", C.c_void_p),
                 ("default_dof_pos", C.c_void_p), ("torque_limits", C.c_void_p), ("torques", C.c_void_p)]
 
+
+class HgCommandArgs(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_envs", "mode", "resampling_steps", "ep_increment", "heading_command", "push")] + \
+               [("cmd_scale", C.c_float * 4), ("cmd_lo", C.c_float * 4), ("push_vel_scale", C.c_float),
+                ("push_vel_lo", C.c_float), ("push_ang_scale", C.c_float), ("push_ang_lo", C.c_float),
+                ("episode_length_buf", C.c_void_p), ("reset_buf", C.c_void_p), ("u_cmd", C.c_void_p), ("u_push", C.c_void_p),
+                ("seed", C.c_uint64), ("counter", C.c_uint64), ("commands", C.c_void_p), ("root_states", C.c_void_p),
+                ("root_vel_prepush", C.c_void_p), ("rand_push_force", C.c_void_p), ("rand_push_torque", C.c_void_p)]
+
+
+CMD_CALLBACK, CMD_RESET = 0, 1
 
 _P = C.c_void_p
 _SIGNATURES = {
@@ -195,6 +207,8 @@ _SIGNATURES = {
     "hg_cast_weight_bf16": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "hg_env_step": (C.c_int, [C.POINTER(HgEnvConfig), C.POINTER(HgEnvBuffers), _P]),
     "hg_action_torque": (C.c_int, [C.POINTER(HgActionArgs), _P]),
+    "hg_command_step": (C.c_int, [C.POINTER(HgCommandArgs), _P]),
+    "hg_episode_means": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
 
@@ -215,7 +229,7 @@ def load(auto_build: bool = True) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.hg_abi_version() != 3:
+    if lib.hg_abi_version() != 4:
         raise HgError("libhgb200.so ABI mismatch")
     _lib = lib
     return lib

@@ -158,6 +158,8 @@ class MLPEngine:
         keep 128-wide tiles (more tiles to fill the SMs)."""
         if kind == "dx" and rows > 8192:
             return int(os.environ.get("HG_DX_BN", 256)) if max(ns) >= 256 else 128
+        if kind == "fwd" and rows <= 8192:
+            return int(os.environ.get("HG_ROLLOUT_BN", 128))       # experiment switch (tools/rollout_variants.sh)
         if kind == "dx" or rows <= 8192:
             return 128       # rollout-sized launches: more, smaller tiles fill the 148 SMs better
         return 256 if max(ns) >= 256 else 128
@@ -170,7 +172,9 @@ class MLPEngine:
             return self.cta_group_override
         if epi == EPI_DELU_BF16:
             return 1
-        return 2 if max(p.M for p in problems) >= 8192 or max(p.K for p in problems) >= 8192 else 1
+        if max(p.M for p in problems) >= 8192 or max(p.K for p in problems) >= 8192:
+            return 2
+        return int(os.environ.get("HG_ROLLOUT_CG", 1)) if epi == EPI_BIAS_ELU_BF16 else 1
 
     def _launch(self, problems: List[HgGemmProblem], epi: int, block_n: int) -> None:
         arr = (HgGemmProblem * len(problems))(*problems)

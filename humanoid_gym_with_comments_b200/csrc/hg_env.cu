@@ -149,58 +149,49 @@ __device__ __forceinline__ BaseFrame base_frame(const HgEnvBuffers& B, int n, bo
   f.lin = {__ldg(root + 7), __ldg(root + 8), __ldg(root + 9)};
   f.ang = {__ldg(root + 10), __ldg(root + 11), __ldg(root + 12)};
   f.root_z = __ldg(root + 2);
-  f.blv = quat_rotate_inverse(q, f.lin);                                        // :785-787
-  f.bav = quat_rotate_inverse(q, f.ang);
+  if (B.root_vel_prepush) {     // a push this step: the base-frame velocities were taken BEFORE it (:785-786 precede :791)
+    const float* pre = B.root_vel_prepush + (size_t)n * 6;
+    f.blv = quat_rotate_inverse(q, Vec3{__ldg(pre), __ldg(pre + 1), __ldg(pre + 2)});
+    f.bav = quat_rotate_inverse(q, Vec3{__ldg(pre + 3), __ldg(pre + 4), __ldg(pre + 5)});
+  } else {
+    f.blv = quat_rotate_inverse(q, f.lin);                                      // :785-787
+    f.bav = quat_rotate_inverse(q, f.ang);
+  }
   f.pg = quat_rotate_inverse(q, Vec3{0.f, 0.f, -1.f});
   f.eul = need_euler ? euler_xyz_wrapped(q) : Vec3{0.f, 0.f, 0.f};              // :788
   return f;
 }
 
-// dst[c] = clip(reset ? 0 : src[c]) for c < count, one warp, 16 independent 128-byte loads in flight per lane-iteration.
-__device__ __forceinline__ void shift_rows(const float* __restrict__ src, float* __restrict__ dst,
-                                           __nv_bfloat16* __restrict__ dst16, int count, bool reset, float clip, int lane) {
-  if (reset) {
-    for (int c = lane; c < count; c += 32) {
-      dst[c] = 0.f;
-      if (dst16) dst16[c] = __float2bfloat16_rn(0.f);
-    }
-    return;
-  }
-  int c = lane;
-  for (; c + 15 * 32 < count; c += 16 * 32) {
-    float v[16];
+// dst[c] = clip(reset ? 0 : src[c]) for begin <= c < min(count, begin + DEPTH*32), one warp.  Every load of the unit is
+// issued before the first store (DEPTH independent 128-byte requests per lane), so a unit costs ONE global round trip.
+template <int DEPTH>
+__device__ __forceinline__ void shift_load(const float* __restrict__ src, int begin, int count, bool reset, int lane, float (&v)[DEPTH]) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldg(src + c + u * 32);
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const float w = clampf(v[u], -clip, clip);
-      dst[c + u * 32] = w;
-      if (dst16) dst16[c + u * 32] = __float2bfloat16_rn(w);
-    }
-  }
-  for (; c + 3 * 32 < count; c += 4 * 32) {
-    float v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldg(src + c + u * 32);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float w = clampf(v[u], -clip, clip);
-      dst[c + u * 32] = w;
-      if (dst16) dst16[c + u * 32] = __float2bfloat16_rn(w);
-    }
-  }
-  for (; c < count; c += 32) {
-    const float w = clampf(__ldg(src + c), -clip, clip);
-    dst[c] = w;
-    if (dst16) dst16[c] = __float2bfloat16_rn(w);
+  for (int u = 0; u < DEPTH; ++u) {
+    const int c = begin + lane + u * 32;
+    v[u] = (!reset && c < count) ? __ldg(src + c) : 0.f;
   }
 }
+template <int DEPTH>
+__device__ __forceinline__ void shift_store(float* __restrict__ dst, __nv_bfloat16* __restrict__ dst16, int begin, int count,
+                                            float clip, int lane, const float (&v)[DEPTH]) {
+#pragma unroll
+  for (int u = 0; u < DEPTH; ++u) {
+    const int c = begin + lane + u * 32;
+    if (c < count) {
+      const float w = clampf(v[u], -clip, clip);
+      dst[c] = w;
+      if (dst16) dst16[c] = __float2bfloat16_rn(w);
+    }
+  }
+}
+constexpr int SHIFT_UNIT = 512;   // floats per streaming unit (16 loads per lane)
 
 // One thread per env for the scalar math (32 envs per block; the block's 4 warps split the work by role so the
 // dependent-latency chain per env is ~4x shorter), then all 128 threads stream the history rows.
 //   warp 0: observation frames (phase, euler, base-frame velocities, joint terms)      compute_observations :818-887
 //   warp 1: joint-space rewards     warp 2: feet / contact rewards (+ their state)     warp 3: base-motion rewards
-__global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_constant__ HgEnvConfig C,
+__global__ void __launch_bounds__(ENV_THREADS, 2) env_step_kernel(const __grid_constant__ HgEnvConfig C,
                                                                const __grid_constant__ HgEnvBuffers B) {
   extern __shared__ __align__(16) float s_env[];
   pdl_trigger();
@@ -230,16 +221,25 @@ __global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const __grid_cons
     // ---------------------------------------------------------------- history shift (:883-887): needs only the reset flag,
     // so these 12 warps stream the 14 old actor frames / 2 old critic frames while warps 0-3 do the per-env math.
     if (doB) {
+      // Work units: the actor history of an env in slabs of SHIFT_UNIT floats, then its critic history in slabs of
+      // SHIFT_UNIT; units are dealt round-robin to the 12 streaming warps (16 envs x 3 units at D = 12: 4 round trips each).
       const int envs_here = min(ENV_PER_BLOCK, C.num_envs - n0);
-      for (int el = warp - ENV_ROLE_WARPS; el < envs_here; el += ENV_THREADS / 32 - ENV_ROLE_WARPS) {
+      const int cnt_o = (C.frame_stack - 1) * So, cnt_p = (C.c_frame_stack - 1) * Sp;
+      const int upo = (cnt_o + SHIFT_UNIT - 1) / SHIFT_UNIT, upe = upo + (cnt_p + SHIFT_UNIT - 1) / SHIFT_UNIT;
+      for (int u = warp - ENV_ROLE_WARPS; u < envs_here * upe; u += ENV_THREADS / 32 - ENV_ROLE_WARPS) {
+        const int el = u / upe, part = u - el * upe;
         const int ne = n0 + el;
         const bool reset = env_base(C, B, ne, doA).reset;       // warp-uniform broadcast loads
-        __nv_bfloat16* o16 = B.obs16_next ? reinterpret_cast<__nv_bfloat16*>(B.obs16_next) + (size_t)ne * B.obs16_next_ld : nullptr;
-        __nv_bfloat16* p16 = B.priv16_next ? reinterpret_cast<__nv_bfloat16*>(B.priv16_next) + (size_t)ne * B.priv16_next_ld : nullptr;
-        shift_rows(B.obs_prev + (size_t)ne * B.obs_prev_ld + So, B.obs_next + (size_t)ne * B.obs_next_ld, o16,
-                   (C.frame_stack - 1) * So, reset, C.clip_obs, lane);
-        shift_rows(B.priv_prev + (size_t)ne * B.priv_prev_ld + Sp, B.priv_next + (size_t)ne * B.priv_next_ld, p16,
-                   (C.c_frame_stack - 1) * Sp, reset, C.clip_obs, lane);
+        const bool actor = part < upo;
+        const float* src = actor ? B.obs_prev + (size_t)ne * B.obs_prev_ld + So : B.priv_prev + (size_t)ne * B.priv_prev_ld + Sp;
+        float* dst = actor ? B.obs_next + (size_t)ne * B.obs_next_ld : B.priv_next + (size_t)ne * B.priv_next_ld;
+        __nv_bfloat16* d16 = nullptr;
+        if (actor && B.obs16_next) d16 = reinterpret_cast<__nv_bfloat16*>(B.obs16_next) + (size_t)ne * B.obs16_next_ld;
+        if (!actor && B.priv16_next) d16 = reinterpret_cast<__nv_bfloat16*>(B.priv16_next) + (size_t)ne * B.priv16_next_ld;
+        const int begin = (actor ? part : part - upo) * SHIFT_UNIT, count = actor ? cnt_o : cnt_p;
+        float v[SHIFT_UNIT / 32];
+        shift_load(src, begin, count, reset, lane, v);
+        shift_store(dst, d16, begin, count, C.clip_obs, lane, v);
       }
     }
   } else if (ok) {

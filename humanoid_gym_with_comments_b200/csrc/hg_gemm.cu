@@ -152,11 +152,13 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 
 constexpr int EPI_ROW_PITCH = 80;   // bytes per staged row: 64 B of bf16 + 16 B pad (conflict-free 16-byte accesses)
 
+__device__ __forceinline__ void tile_colsum_mma(uint32_t tile_addr, int lane, float (&c)[4][2]);
+
 // Write the warp's 32 rows x 32 columns (one row per lane, fp32 in registers) as bf16 with COALESCED global stores:
 // each lane parks its 64-byte row in the warp's shared tile, then 4 lanes cooperate on each row segment, so one
 // store instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.
 __device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* tile, int lane, __nv_bfloat16* out_col0,
-                                                long long ldo, int row_base, int M) {
+                                                long long ldo, int row_base, int M, float* colsum = nullptr) {
   const uint32_t tb = smem_u32(tile);
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
@@ -165,6 +167,17 @@ __device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* til
     sts128(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16, w);
   }
   __syncwarp();
+  if (colsum) {     // (warp-uniform) bias gradient of the layer below: column sums of the staged tile, 32 REDs per chunk
+    float c[4][2];
+    tile_colsum_mma(tb, lane, c);
+    if (lane < 4) {
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        atomicAdd(colsum + nb * 8 + 2 * lane, c[nb][0]);
+        atomicAdd(colsum + nb * 8 + 2 * lane + 1, c[nb][1]);
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = i * 8 + (lane >> 2), piece = lane & 3;
@@ -177,6 +190,28 @@ __device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* til
       *(reinterpret_cast<uint4*>(out_col0 + (long long)(row_base + r) * ldo) + piece) = w;
   }
   __syncwarp();
+}
+
+// Column sums of the warp's staged 32 x 32 bf16 tile (rows EPI_ROW_PITCH bytes apart) on the tensor core: ones[16x16] x
+// tile[16 x 8] per mma.sync.m16n8k16, the tile read as B fragments with ldmatrix.trans.  Every row of the product holds
+// the column sums, so lane t ends up with the sums of columns nb*8 + 2*(t%4) + {0,1}, nb = 0..3, in c[nb][0..1].
+// Replaces a 31-shuffle butterfly (~190 instructions per chunk) with 4 ldmatrix + 8 mma; the summands are the
+// bf16-rounded values the weight-gradient GEMM reads, accumulated in fp32.
+__device__ __forceinline__ void tile_colsum_mma(uint32_t tile_addr, int lane, float (&c)[4][2]) {
+  const uint32_t ones = 0x3F803F80u;      // bf16x2 (1.0, 1.0)
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb) {
+    uint32_t b0, b1, b2, b3;              // k rows 0-7, 8-15, 16-23, 24-31 of column block nb
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(tile_addr + lane * EPI_ROW_PITCH + nb * 16) : "memory");
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
+                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(ones), "r"(b0), "r"(b1));
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
+                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(ones), "r"(b2), "r"(b3));
+    c[nb][0] = d0;
+    c[nb][1] = d1;
+  }
 }
 
 // Activation rows of the layer below for one 32x32 chunk, in the coalesced pattern of store_rows_bf16 (4 lanes per
@@ -270,14 +305,17 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
         const uint32_t hv[4] = {hw.x, hw.y, hw.z, hw.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 h = unpack_bf16x2(hv[k]);
+          uint32_t m2;                                   // min(h, 0) on the packed pair, then widen (bf16 -> fp32 is a shift)
+          asm("min.bf16x2 %0, %1, %2;" : "=r"(m2) : "r"(hv[k]), "r"(0u));
           const float a0 = __uint_as_float(v[j + 2 * k]), a1 = __uint_as_float(v[j + 2 * k + 1]);
-          d[j + 2 * k] = fmaf(a0, fminf(h.x, 0.f), a0);
-          d[j + 2 * k + 1] = fmaf(a1, fminf(h.y, 0.f), a1);
+          d[j + 2 * k] = fmaf(a0, __uint_as_float(m2 << 16), a0);
+          d[j + 2 * k + 1] = fmaf(a1, __uint_as_float(m2 & 0xFFFF0000u), a1);
         }
       }
       __syncwarp();
-      store_rows_bf16(d, tile, lane, reinterpret_cast<__nv_bfloat16*>(q.out) + n0, q.ldo, row_base, q.M);
+      store_rows_bf16(d, tile, lane, reinterpret_cast<__nv_bfloat16*>(q.out) + n0, q.ldo, row_base, q.M,
+                      q.colsum ? q.colsum + n0 : nullptr);
+      return;
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {

@@ -20,8 +20,8 @@ from typing import Dict, Optional
 import torch
 
 from .. import _lib
-from .._lib import (ENV_PHASE_ALL, HG_NUM_REWARDS, REWARD_NAMES, HgActionArgs, HgEnvBuffers, HgEnvConfig, check,
-                    current_stream, ptr)
+from .._lib import (CMD_CALLBACK, CMD_RESET, ENV_PHASE_ALL, ENV_PHASE_OBS, ENV_PHASE_REWARD, HG_NUM_REWARDS, REWARD_NAMES,
+                    HgActionArgs, HgCommandArgs, HgEnvBuffers, HgEnvConfig, check, current_stream, ptr)
 
 # humanoid_config.py:395-430 (XBotLCfg.rewards.scales)
 XBOT_REWARD_SCALES = dict(
@@ -71,6 +71,15 @@ class XBotMathConfig:
     noise_quat: float = 0.03
     reward_scales: Dict[str, float] = field(default_factory=lambda: dict(XBOT_REWARD_SCALES))
     phase_mul_reciprocal: bool = False   # True reproduces torch-CUDA's x/c == x*(1/c)
+    # commands / domain_rand scalars read by _post_physics_step_callback (humanoid_config.py:331-337,349-370)
+    resampling_time: float = 8.0
+    heading_command: bool = True
+    command_ranges: Dict[str, tuple] = field(default_factory=lambda: dict(
+        lin_vel_x=(-0.3, 0.6), lin_vel_y=(-0.3, 0.3), ang_vel_yaw=(-0.3, 0.3), heading=(-3.14, 3.14)))
+    push_robots: bool = True
+    push_interval_s: float = 4.0
+    max_push_vel_xy: float = 0.2
+    max_push_ang_vel: float = 0.4
 
     @staticmethod
     def for_dof(num_dof: int, num_envs: int = 4096) -> "XBotMathConfig":
@@ -181,6 +190,85 @@ class XBotEnvMath:
         self._buf_cache = {}
         self._lib = _lib.load()
 
+    # ------------------------------------------------------------------ callback, pushes, extras
+    def _callback_state(self):
+        if not hasattr(self, "commands"):
+            N, z = self.num_envs, lambda *s, **k: torch.zeros(*s, device=self.device, **k)
+            self.commands = z(N, 4)                      # x vel, y vel, yaw vel, heading (:271)
+            self.rand_push_force, self.rand_push_torque = z(N, 3), z(N, 3)
+            self.root_vel_prepush = z(N, 6)
+            self.common_step_counter = 0
+            self.episode_means_tensor = z(HG_NUM_REWARDS)
+            self.episode_reset_count = z(1, dtype=torch.int32)
+            cfg = self.cfg
+            self.resampling_steps = int(cfg.resampling_time / cfg.dt)                  # :1005
+            self.push_interval = math.ceil(cfg.push_interval_s / cfg.dt)               # :191
+            a = HgCommandArgs()
+            a.num_envs, a.resampling_steps, a.heading_command = N, self.resampling_steps, 1 if cfg.heading_command else 0
+            for i, k in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw", "heading")):
+                lo, hi = cfg.command_ranges[k]
+                a.cmd_scale[i], a.cmd_lo[i] = hi - lo, lo                              # python double difference, cast once
+            a.push_vel_scale, a.push_vel_lo = cfg.max_push_vel_xy - (-cfg.max_push_vel_xy), -cfg.max_push_vel_xy
+            a.push_ang_scale, a.push_ang_lo = cfg.max_push_ang_vel - (-cfg.max_push_ang_vel), -cfg.max_push_ang_vel
+            a.commands, a.rand_push_force, a.rand_push_torque = ptr(self.commands), ptr(self.rand_push_force), ptr(self.rand_push_torque)
+            a.root_vel_prepush = ptr(self.root_vel_prepush)
+            a.episode_length_buf, a.reset_buf = ptr(self.episode_length_buf), ptr(self.reset_buf)
+            a.seed = self.seed
+            self._cmd_args = a
+
+    def post_physics_callback(self, root_states: torch.Tensor, u_cmd: Optional[torch.Tensor] = None,
+                              u_push: Optional[torch.Tensor] = None, ep_increment: int = 1) -> bool:
+        """`_post_physics_step_callback` (humanoid_env.py:1001-1016), one launch, BEFORE the reward kernel: periodic
+        command resampling, heading -> yaw-rate command, and every `push_interval` steps the random push written into
+        `root_states` (in place; the pre-push velocities go to `self.root_vel_prepush`, which `step` must then be given).
+        `ep_increment=1` because the env kernel performs `episode_length_buf += 1` (:780) itself.
+        u_cmd [N,3] / u_push [N,5]: torch.rand draws, or None for the in-kernel Philox.  Returns whether it pushed."""
+        self._callback_state()
+        _lib.require_cuda(root_states, u_cmd, u_push)
+        self.common_step_counter += 1                                                  # :781
+        a = self._cmd_args
+        a.mode, a.ep_increment = CMD_CALLBACK, ep_increment
+        pushed = bool(self.cfg.push_robots and self.common_step_counter % self.push_interval == 0)
+        a.push = 1 if pushed else 0
+        a.root_states, a.u_cmd, a.u_push = ptr(root_states), ptr(u_cmd), ptr(u_push)
+        a.counter = self.common_step_counter
+        check(self._lib.hg_command_step(C.byref(a), current_stream()))
+        return pushed
+
+    def reset_bookkeeping(self, u_cmd: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """The parts of `reset_idx` that are neither simulator calls nor buffer zeroing, two launches, BETWEEN the
+        HG_ENV_PHASE_REWARD and HG_ENV_PHASE_OBS launches: `_resample_commands(env_ids)` (:1127) and
+        extras["episode"]["rew_*"] (:1141-1143).  Returns the extras dict (device scalars, views of one [22] tensor;
+        left unchanged on steps without a reset, as the reference's early return does)."""
+        self._callback_state()
+        _lib.require_cuda(u_cmd)
+        a = self._cmd_args
+        a.mode, a.push, a.u_cmd, a.u_push = CMD_RESET, 0, ptr(u_cmd), 0
+        a.counter = self.common_step_counter
+        check(self._lib.hg_command_step(C.byref(a), current_stream()))
+        check(self._lib.hg_episode_means(ptr(self.episode_sums_tensor), ptr(self.reset_buf), HG_NUM_REWARDS, self.num_envs,
+                                         float(self.cfg.episode_length_s), ptr(self.episode_means_tensor),
+                                         ptr(self.episode_reset_count), current_stream()))
+        return {"rew_" + name: self.episode_means_tensor[k] for k, name in enumerate(REWARD_NAMES)
+                if self.cfg.reward_scales.get(name, 0.0) != 0}
+
+    def step_with_callbacks(self, sim: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None,
+                            u_cmd: Optional[torch.Tensor] = None, u_push: Optional[torch.Tensor] = None,
+                            u_cmd_reset: Optional[torch.Tensor] = None, **kw):
+        """The whole tensor side of `post_physics_step` (:770-806) in the reference's order, five launches:
+        callback -> termination + rewards -> reset bookkeeping (commands, extras) -> observations + history + hand-over.
+        `sim["root_states"]` is modified in place by a push; commands / push buffers are this object's persistent ones.
+        Returns (obs, priv, rew, reset, time_out, extras_episode)."""
+        self._callback_state()
+        pushed = self.post_physics_callback(sim["root_states"], u_cmd, u_push)
+        sim = dict(sim, commands=self.commands, rand_push_force=self.rand_push_force, rand_push_torque=self.rand_push_torque)
+        pre = self.root_vel_prepush if pushed else None
+        self.step(sim, noise, phases=ENV_PHASE_REWARD, root_vel_prepush=pre, **kw)
+        episode = self.reset_bookkeeping(u_cmd_reset)
+        sim.pop("actions", None)                       # already copied into self.actions by the first launch
+        out = self.step(sim, noise, phases=ENV_PHASE_OBS, root_vel_prepush=pre, **kw)
+        return (*out, episode)
+
     @property
     def episode_sums(self) -> Dict[str, torch.Tensor]:
         return {name: self.episode_sums_tensor[k] for k, name in enumerate(REWARD_NAMES)
@@ -240,7 +328,8 @@ class XBotEnvMath:
     def step(self, sim: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None, phases: int = ENV_PHASE_ALL,
              obs_out: Optional[torch.Tensor] = None, priv_out: Optional[torch.Tensor] = None,
              obs16_out: Optional[torch.Tensor] = None, priv16_out: Optional[torch.Tensor] = None,
-             raw_actions: Optional[torch.Tensor] = None, clip_actions: float = 18.0, store=None):
+             raw_actions: Optional[torch.Tensor] = None, clip_actions: float = 18.0, store=None,
+             root_vel_prepush: Optional[torch.Tensor] = None):
         """One fused post-physics step on the Isaac-Gym-shaped tensors in `sim` (keys: root_states, dof_state,
         contact_forces, rigid_state, commands, torques, rand_push_force, rand_push_torque, env_frictions, body_mass;
         optional `actions` [N,D] = the actions applied this step, copied into `self.actions` first).
@@ -278,6 +367,7 @@ class XBotEnvMath:
             b.store_values, b.store_rewards, b.store_dones, b.store_gamma = ptr(store[0]), ptr(store[1]), ptr(store[2]), store[3]
         else:
             b.store_values = b.store_rewards = b.store_dones = 0
+        b.root_vel_prepush = ptr(root_vel_prepush)     # set on push steps only (post_physics_callback)
         self._c.phases = phases
         check(self._lib.hg_env_step(C.byref(self._c), C.byref(b), current_stream()))
         if phases & 2:
@@ -319,7 +409,12 @@ class SyntheticXBotEnv:
     replaced by cycling through a pool of pre-generated Isaac-Gym-shaped state tensors; everything after it
     (the hot path) is the fused kernel.  Drives `OnPolicyRunner`-style loops in bench.py and the tests."""
 
-    def __init__(self, cfg: XBotMathConfig, device, pool: int = 4, seed: int = 0, torch_rng_noise: bool = True):
+    def __init__(self, cfg: XBotMathConfig, device, pool: int = 4, seed: int = 0, torch_rng_noise: bool = True,
+                 callbacks: bool = False):
+        """callbacks=True also runs `_post_physics_step_callback` (command resampling, heading command, pushes) and the
+        command / extras["episode"] part of `reset_idx` every step: five launches per step instead of
+        one, commands and push buffers owned by the env instead of taken from the synthetic pool."""
+        self.callbacks = callbacks
         self.cfg, self.device = cfg, torch.device(device)
         self.math = XBotEnvMath(cfg, device)
         self.num_envs = cfg.num_envs
@@ -420,7 +515,18 @@ class SyntheticXBotEnv:
         noise = torch.randn(self.num_envs, self.cfg.num_single_obs, device=self.device) if (
             self.torch_rng_noise and self.cfg.add_noise) else None
         st = self._storage
-        if st is not None and st.step + 1 <= st.num_transitions_per_env:
+        if self.callbacks:
+            if st is not None:
+                raise _lib.HgError("callbacks=True runs the two-phase env step and cannot be bound to a RolloutStorage")
+            if not hasattr(self, "_root_scratch"):
+                self._root_scratch = torch.empty_like(sim["root_states"])
+            self._root_scratch.copy_(sim["root_states"])           # a push overwrites root velocities in place
+            sim = dict(sim, root_states=self._root_scratch)
+            ur = (lambda *sh: torch.rand(*sh, device=self.device)) if self.torch_rng_noise else (lambda *sh: None)
+            *out, episode = self.math.step_with_callbacks(sim, noise, u_cmd=ur(self.num_envs, 3), u_push=ur(self.num_envs, 5),
+                                                          u_cmd_reset=ur(self.num_envs, 3), raw_actions=actions)
+            self.extras["episode"] = episode
+        elif st is not None and st.step + 1 <= st.num_transitions_per_env:
             o, p, o16, p16 = st.slot(st.step + 1)
             store = None
             if getattr(self, "_store_gamma", None) is not None:

@@ -21,7 +21,7 @@ extern "C" {
 #define HG_ERR_INVALID (-1)
 #define HG_ERR_CUDA (-2)
 
-#define HG_ABI_VERSION 3
+#define HG_ABI_VERSION 4
 
 const char* hg_last_error(void);
 int hg_abi_version(void);
@@ -330,6 +330,11 @@ typedef struct HgEnvBuffers {
   float* store_rewards;         /* [N] */
   uint8_t* store_dones;         /* [N] */
   float store_gamma;
+  /* optional [N,6]: root_states[:,7:13] as they were BEFORE this step's push (written by hg_command_step).  The
+   * reference rotates base_lin_vel / base_ang_vel from the root state before `_post_physics_step_callback` pushes
+   * the robots (humanoid_env.py:785-791), while base_acc and last_root_vel read the pushed values (:803,1385-1391).
+   * NULL: the base-frame velocities come from root_states (no push this step). */
+  const float* root_vel_prepush;
 } HgEnvBuffers;
 
 int hg_env_step(const HgEnvConfig* cfg_host, const HgEnvBuffers* buf_host, void* stream);
@@ -359,6 +364,46 @@ typedef struct HgActionArgs {
   float* torques;              /* [N,D] or NULL */
 } HgActionArgs;
 int hg_action_torque(const HgActionArgs* args_host, void* stream);
+
+/* The tensor math around the reward / observation kernels of post_physics_step, one launch each:
+ *
+ * HG_CMD_CALLBACK = `_post_physics_step_callback` (humanoid_env.py:1001-1016):
+ *   envs with (episode_length + ep_increment) % resampling_steps == 0 get new commands (`_resample_commands`,
+ *   :1018-1032: x, y and heading -- or yaw rate when heading_command is 0 -- drawn as scale * u + lo, then x and y are
+ *   zeroed where their norm is <= 0.2); with heading_command the yaw-rate command of EVERY env becomes
+ *   clip(0.5 * wrap_to_pi(commands[:,3] - heading), -1, 1), heading = atan2 of quat_apply(base_quat, (1,0,0)) (:1007-1010,
+ *   utils/math.py:46-49); with push != 0 (`_push_robots`, :665-681, decided by the host from
+ *   common_step_counter % push_interval) root_states[:,7:9] = rand_push_force[:,:2] = U(-max_push_vel_xy, +) and
+ *   root_states[:,10:13] = rand_push_torque = U(-max_push_ang_vel, +), the pre-push velocities going to root_vel_prepush.
+ * HG_CMD_RESET = the `_resample_commands(env_ids)` call of `reset_idx` (:1127) for the envs whose reset_buf is set.
+ *
+ * u_cmd [N,3] / u_push [N,5]: U[0,1) draws (torch.rand), or NULL -> in-kernel Philox4x32-10 (seed, counter). */
+#define HG_CMD_CALLBACK 0
+#define HG_CMD_RESET 1
+typedef struct HgCommandArgs {
+  int32_t num_envs, mode, resampling_steps, ep_increment, heading_command, push;
+  float cmd_scale[4], cmd_lo[4];       /* x, y, yaw rate, heading: (float)(hi - lo) and (float)lo of command_ranges */
+  float push_vel_scale, push_vel_lo;   /* (float)(2 max_push_vel_xy), (float)(-max_push_vel_xy) */
+  float push_ang_scale, push_ang_lo;
+  const int64_t* episode_length_buf;   /* [N] (HG_CMD_CALLBACK) */
+  const uint8_t* reset_buf;            /* [N] (HG_CMD_RESET) */
+  const float* u_cmd;                  /* [N,3] or NULL */
+  const float* u_push;                 /* [N,5] or NULL */
+  uint64_t seed, counter;
+  float* commands;                     /* [N,4] in / out */
+  float* root_states;                  /* [N,13] quaternion read; velocities overwritten by a push */
+  float* root_vel_prepush;             /* [N,6] out, or NULL */
+  float* rand_push_force;              /* [N,3] */
+  float* rand_push_torque;             /* [N,3] */
+} HgCommandArgs;
+int hg_command_step(const HgCommandArgs* args_host, void* stream);
+
+/* extras["episode"]["rew_<term>"] of reset_idx (humanoid_env.py:1141-1143): for each of the K rows of episode_sums [K,N],
+ * mean over the envs with reset_buf set, divided by max_episode_length_s.  Launch it between the HG_ENV_PHASE_REWARD and
+ * HG_ENV_PHASE_OBS launches (the second one zeroes the sums).  count_out[0] = number of reset envs; when it is 0 the
+ * means are left untouched (reset_idx returns early, :1113-1114).  Fixed-order double-precision reduction. */
+int hg_episode_means(const float* episode_sums, const uint8_t* reset_buf, int num_terms, int num_envs,
+                     float max_episode_length_s, float* means_out, int32_t* count_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .isaac_math import euler_xyz_wrapped, quat_rotate_inverse
+from .isaac_math import euler_xyz_wrapped, quat_apply, quat_rotate_inverse
 
 # humanoid_config.py:395-430 (XBotLCfg.rewards.scales); zero entries are dropped (:207-212)
 XBOT_REWARD_SCALES = dict(
@@ -180,14 +180,89 @@ def _ref_dof_pos(spec: EnvSpec, ep_len: torch.Tensor) -> torch.Tensor:
     return ref
 
 
+@dataclass
+class CallbackSpec:
+    """Config scalars of `_post_physics_step_callback` / `_resample_commands` / `_push_robots` / the `extras` part of
+    `reset_idx` (humanoid_config.py:331-337,349-370,64; derived values as humanoid_env.py:188-191,1005)."""
+    resampling_steps: int = 800            # int(commands.resampling_time / dt) = int(8 / 0.01)
+    heading_command: bool = True
+    lin_vel_x: tuple = (-0.3, 0.6)
+    lin_vel_y: tuple = (-0.3, 0.3)
+    ang_vel_yaw: tuple = (-0.3, 0.3)
+    heading: tuple = (-3.14, 3.14)
+    push_robots: bool = True
+    push_interval: float = 400.0           # np.ceil(push_interval_s / dt) = ceil(4 / 0.01)
+    max_push_vel_xy: float = 0.2
+    max_push_ang_vel: float = 0.4
+    max_episode_length_s: float = 24.0
+
+
+def rand_float(lower: float, upper: float, u: torch.Tensor) -> torch.Tensor:
+    """`torch_rand_float` of Isaac Gym: (upper - lower) * torch.rand(shape) + lower, with the U[0,1) draw `u` given."""
+    return (upper - lower) * u + lower
+
+
+def wrap_to_pi(angles: torch.Tensor) -> torch.Tensor:
+    """humanoid/utils/math.py:46-49."""
+    angles = angles % (2 * math.pi)
+    return angles - 2 * math.pi * (angles > math.pi)
+
+
+def resample_commands(cb: CallbackSpec, commands: torch.Tensor, ids: torch.Tensor, u: torch.Tensor) -> None:
+    """`_resample_commands` (humanoid_env.py:1018-1032) for env ids `ids`; u [N,3] holds each env's three U[0,1) draws
+    (x, y, heading-or-yaw).  In place."""
+    if len(ids) == 0:
+        return
+    commands[ids, 0] = rand_float(cb.lin_vel_x[0], cb.lin_vel_x[1], u[ids, 0])
+    commands[ids, 1] = rand_float(cb.lin_vel_y[0], cb.lin_vel_y[1], u[ids, 1])
+    if cb.heading_command:
+        commands[ids, 3] = rand_float(cb.heading[0], cb.heading[1], u[ids, 2])
+    else:
+        commands[ids, 2] = rand_float(cb.ang_vel_yaw[0], cb.ang_vel_yaw[1], u[ids, 2])
+    commands[ids, :2] *= (torch.norm(commands[ids, :2], dim=1) > 0.2).unsqueeze(1)          # :1032
+
+
+def post_physics_callback(cb: CallbackSpec, ep_len: torch.Tensor, common_step_counter: int, quat: torch.Tensor,
+                          commands: torch.Tensor, root_states: torch.Tensor, rand_push_force: torch.Tensor,
+                          rand_push_torque: torch.Tensor, u_cmd: torch.Tensor, u_push: torch.Tensor) -> bool:
+    """`_post_physics_step_callback` (humanoid_env.py:1001-1016) + `_push_robots` (:665-681), in place on commands /
+    root_states / rand_push_force / rand_push_torque.  ep_len and common_step_counter are the already incremented values
+    (:780-781).  u_cmd [N,3], u_push [N,5] are U[0,1) draws.  Returns whether this step pushed."""
+    ids = (ep_len % cb.resampling_steps == 0).nonzero(as_tuple=False).flatten()
+    resample_commands(cb, commands, ids, u_cmd)
+    if cb.heading_command:
+        forward_vec = torch.tensor([1.0, 0.0, 0.0]).repeat(quat.shape[0], 1)
+        forward = quat_apply(quat, forward_vec)
+        heading = torch.atan2(forward[:, 1], forward[:, 0])
+        commands[:, 2] = torch.clip(0.5 * wrap_to_pi(commands[:, 3] - heading), -1.0, 1.0)
+    pushed = cb.push_robots and (common_step_counter % cb.push_interval == 0)
+    if pushed:
+        rand_push_force[:, :2] = rand_float(-cb.max_push_vel_xy, cb.max_push_vel_xy, u_push[:, :2])
+        root_states[:, 7:9] = rand_push_force[:, :2]
+        rand_push_torque[:] = rand_float(-cb.max_push_ang_vel, cb.max_push_ang_vel, u_push[:, 2:5])
+        root_states[:, 10:13] = rand_push_torque
+    return bool(pushed)
+
+
+def episode_means(cb: CallbackSpec, episode_sums: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """extras["episode"]["rew_<name>"] of reset_idx (:1141-1143): mean over the reset envs of every episode sum,
+    divided by max_episode_length_s.  episode_sums [K,N] -> [K]."""
+    return torch.stack([torch.mean(episode_sums[k][ids]) / cb.max_episode_length_s for k in range(episode_sums.shape[0])])
+
+
 def env_step(spec: EnvSpec, st: EnvState, sim: Dict[str, torch.Tensor], noise: Optional[torch.Tensor],
-             noise_vec: Optional[torch.Tensor] = None):
+             noise_vec: Optional[torch.Tensor] = None, callback: Optional[Dict] = None):
     """One post-physics step.  `sim` holds the Isaac-Gym-shaped tensors for this step:
     root_states [N,13], dof_pos [N,D], dof_vel [N,D], contact_forces [N,B,3], rigid_state [N,B,13],
     commands [N,4], actions [N,D] (already delayed/noised/clipped, :624-635), torques [N,D],
     rand_push_force [N,3], rand_push_torque [N,3], env_frictions [N,1], body_mass [N,1].
     `noise` [N,So] is the N(0,1) draw of `randn_like` (:877) or None.
-    Returns dict(obs, priv, rew, reset, time_out, terms[K,N]).  Mutates `st`."""
+    Returns dict(obs, priv, rew, reset, time_out, terms[K,N]).  Mutates `st`.
+    `callback` = dict(spec=CallbackSpec, common_step_counter=int (already incremented), u_cmd [N,3],
+    u_push [N,5], u_cmd_reset [N,3]): additionally runs `_post_physics_step_callback` between the base-frame quantities
+    and check_termination, and the command resampling + episode means of `reset_idx`; commands, rand_push_force and
+    rand_push_torque then live in `st` (sim's are ignored) and the returned dict gains commands, root_states,
+    pushed, episode_means (None when no env reset: reset_idx returns early, :1113-1114)."""
     N = st.N
     feet, knees = list(spec.feet), list(spec.knees)
     if noise_vec is None:
@@ -204,6 +279,14 @@ def env_step(spec: EnvSpec, st: EnvState, sim: Dict[str, torch.Tensor], noise: O
     gravity = torch.tensor([0.0, 0.0, -1.0]).repeat(N, 1)
     proj_grav = quat_rotate_inverse(quat, gravity)                              # :787
     euler = euler_xyz_wrapped(quat)                                             # :788
+    push_force, push_torque, pushed, ep_means = sim["rand_push_force"], sim["rand_push_torque"], False, None
+    if callback is not None:                                                    # :791 (base velocities above are PRE-push)
+        if not hasattr(st, "commands"):
+            st.commands, st.rand_push_force, st.rand_push_torque = torch.zeros(N, 4), torch.zeros(N, 3), torch.zeros(N, 3)
+        root = root.clone()
+        cmd, push_force, push_torque = st.commands, st.rand_push_force, st.rand_push_torque
+        pushed = post_physics_callback(callback["spec"], st.episode_length_buf, callback["common_step_counter"], quat, cmd,
+                                       root, push_force, push_torque, callback["u_cmd"], callback["u_push"])
 
     # check_termination :811-816
     reset = torch.any(torch.norm(cf[:, list(spec.termination_bodies), :], dim=-1) > 1.0, dim=1)
@@ -298,6 +381,9 @@ def env_step(spec: EnvSpec, st: EnvState, sim: Dict[str, torch.Tensor], noise: O
     # ---- reset_idx buffer part :1132-1139, :1141-1144, :1160-1163
     ids = reset.nonzero(as_tuple=False).flatten()
     if len(ids) > 0:
+        if callback is not None:
+            resample_commands(callback["spec"], cmd, ids, callback["u_cmd_reset"])     # :1127
+            ep_means = episode_means(callback["spec"], st.episode_sums, ids)           # :1141-1143 (before the zeroing)
         st.last_last_actions[ids] = 0.0
         st.actions[ids] = 0.0
         st.last_actions[ids] = 0.0
@@ -321,7 +407,7 @@ def env_step(spec: EnvSpec, st: EnvState, sim: Dict[str, torch.Tensor], noise: O
     diff = dof_pos - st.ref_dof_pos
     priv = torch.cat((command_input, q, dq, st.actions, diff,
                       base_lin_vel * spec.lin_vel_scale, base_ang_vel * spec.ang_vel_scale,
-                      euler * spec.quat_scale, sim["rand_push_force"][:, :2], sim["rand_push_torque"],
+                      euler * spec.quat_scale, push_force[:, :2], push_torque,
                       sim["env_frictions"], sim["body_mass"] / 30.0, stance, contact), dim=-1)
     frame = torch.cat((command_input, q, dq, st.actions, base_ang_vel * spec.ang_vel_scale,
                        euler * spec.quat_scale), dim=-1)
@@ -340,8 +426,12 @@ def env_step(spec: EnvSpec, st: EnvState, sim: Dict[str, torch.Tensor], noise: O
 
     obs_buf = torch.clip(obs_buf, -spec.clip_obs, spec.clip_obs)               # :654-657
     priv_buf = torch.clip(priv_buf, -spec.clip_obs, spec.clip_obs)
-    return dict(obs=obs_buf, priv=priv_buf, rew=rew, reset=reset, time_out=time_out, terms=terms,
-                base_lin_vel=base_lin_vel, base_ang_vel=base_ang_vel, euler=euler, proj_grav=proj_grav)
+    out = dict(obs=obs_buf, priv=priv_buf, rew=rew, reset=reset, time_out=time_out, terms=terms,
+               base_lin_vel=base_lin_vel, base_ang_vel=base_ang_vel, euler=euler, proj_grav=proj_grav)
+    if callback is not None:
+        out.update(commands=cmd.clone(), root_states=root.clone(), pushed=pushed, episode_means=ep_means,
+                   rand_push_force=push_force.clone(), rand_push_torque=push_torque.clone())
+    return out
 
 
 def synthetic_sim_state(spec: EnvSpec, N: int, gen: torch.Generator, upright: bool = True,

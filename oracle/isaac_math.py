@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE (oracle).  Isaac Gym is a closed NVIDIA tarball (`setup.py:43` of the
 reference pins it only as "isaacgym  # preview4"); it is not under /root/reference, so its
-published algorithm is restated here.  PARITY UNPINNED for these four helpers: the reference
+published algorithm is restated here.  PARITY UNPINNED for these helpers: the reference
 holds no test for them.  Independent cross-check: reference `humanoid/scripts/sim2sim.py:57-77`
 (`quaternion_to_euler_array`) and `:87-89` (scipy inverse rotation) -- see
 tests/test_oracle_cpu.py::test_isaac_math_vs_sim2sim_formulas.
@@ -52,6 +52,17 @@ def euler_xyz_wrapped(q: torch.Tensor) -> torch.Tensor:
     e = torch.stack((r, p, y), dim=1)
     e[e > math.pi] -= 2 * math.pi
     return e
+
+
+def quat_apply(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Rotate b [N,3] by unit quaternion a [N,4] (xyzw): b + w*t + q_xyz x t with t = 2*(q_xyz x b), in that op order
+    (Isaac Gym Preview 4 `torch_utils.quat_apply`; call site `humanoid_env.py:1008`, heading of the base)."""
+    shape = b.shape
+    a = a.reshape(-1, 4)
+    b = b.reshape(-1, 3)
+    xyz = a[:, :3]
+    t = torch.cross(xyz, b, dim=-1) * 2
+    return (b + a[:, 3:] * t + torch.cross(xyz, t, dim=-1)).view(shape)
 
 
 def to_torch(x, dtype=torch.float, device="cpu", requires_grad=False):

@@ -203,6 +203,67 @@ def env_case(D, N=16, steps=20, seed=3):
     return out, dict(resets=n_reset, time_outs=n_to, maxabs=worst)
 
 
+def callback_case(D=12, N=32, steps=12, seed=5):
+    """the reference's `_post_physics_step_callback` (+ `_resample_commands`, `_push_robots`) and the
+    command resampling / episode means of `reset_idx`, run inside the stateful env loop with replayed uniform draws."""
+    spec = eo.xbot_spec(D)
+    cb = eo.CallbackSpec()
+    g = torch.Generator().manual_seed(seed)
+    ref = rh.RefEnv(D, N, spec)
+    st = eo.EnvState(spec, N)
+    ep0 = torch.randint(0, 2300, (N,), generator=g)
+    ep0[:8] = torch.tensor([2398, 2399, 798, 799, 1598, 1599, 31, 790])     # time-outs and resampling boundaries in the run
+    st.episode_length_buf = ep0.clone()
+    ref.e.episode_length_buf = ep0.clone()
+    counter0 = 395                                                           # common_step_counter reaches 400 (a push) at step 4
+    ref.e.common_step_counter = counter0
+    cmd0 = torch.cat((0.5 * torch.randn(N, 3, generator=g), 3.0 * (2 * torch.rand(N, 1, generator=g) - 1)), dim=1)
+    ref.e.commands = cmd0.clone()
+    st.commands, st.rand_push_force, st.rand_push_torque = cmd0.clone(), torch.zeros(N, 3), torch.zeros(N, 3)
+    assert ref.e.cfg.commands.heading_command == cb.heading_command and ref.e.cfg.domain_rand.push_robots == cb.push_robots
+    assert int(ref.e.cfg.commands.resampling_time / ref.e.dt) == cb.resampling_steps
+    assert float(ref.e.cfg.domain_rand.push_interval) == cb.push_interval
+    assert ref.e.max_episode_length_s == cb.max_episode_length_s
+    for k in ("lin_vel_x", "lin_vel_y", "ang_vel_yaw", "heading"):
+        assert tuple(ref.e.command_ranges[k]) == getattr(cb, k), k
+    keys = ("root_states", "dof_state", "contact_forces", "rigid_state", "actions", "torques", "env_frictions", "body_mass")
+    outs = ("obs", "priv", "rew", "reset", "time_out", "commands", "root_states_out", "rand_push_force", "rand_push_torque")
+    acc = {k: [] for k in keys + outs + ("noise", "u_cmd", "u_push", "u_cmd_reset", "episode_means", "has_means", "pushed")}
+    n_resampled = 0
+    for s_ in range(steps):
+        sim = eo.synthetic_sim_state(spec, N, g, upright=(s_ % 3 != 2), base_contact_frac=0.06)
+        noise = torch.randn(N, spec.So, generator=g)
+        u_cmd, u_push, u_rst = torch.rand(N, 3, generator=g), torch.rand(N, 5, generator=g), torch.rand(N, 3, generator=g)
+        a = ref.step(sim, noise, callback=dict(u_cmd=u_cmd, u_push=u_push, u_cmd_reset=u_rst))
+        b = eo.env_step(spec, st, sim, noise, callback=dict(spec=cb, common_step_counter=counter0 + s_ + 1, u_cmd=u_cmd,
+                                                            u_push=u_push, u_cmd_reset=u_rst))
+        n_resampled += int(((ep0 + s_ + 1) % cb.resampling_steps == 0).sum()) if s_ == 0 else 0
+        for k in ("obs", "priv", "rew", "reset", "time_out", "commands", "root_states", "rand_push_force", "rand_push_torque"):
+            assert torch.equal(a[k], b[k]), (D, s_, k, (a[k].float() - b[k].float()).abs().max())
+        assert (a["episode_means"] is None) == (b["episode_means"] is None)
+        if a["episode_means"] is not None:
+            assert torch.equal(a["episode_means"], b["episode_means"]), s_
+        for k in ("obs", "priv", "rew", "reset", "time_out", "commands", "rand_push_force", "rand_push_torque"):
+            acc[k].append(_np(a[k]))
+        acc["root_states_out"].append(_np(a["root_states"]))
+        acc["pushed"].append(np.array(b["pushed"]))
+        acc["has_means"].append(np.array(a["episode_means"] is not None))
+        acc["episode_means"].append(_np(a["episode_means"]) if a["episode_means"] is not None
+                                    else np.zeros(len(spec.active_rewards()), dtype=np.float32))
+        for k in keys:
+            acc[k].append(_np(sim[k]))
+        for k, v in (("noise", noise), ("u_cmd", u_cmd), ("u_push", u_push), ("u_cmd_reset", u_rst)):
+            acc[k].append(_np(v))
+    out = dict(D=D, N=N, steps=steps, ep_len0=_np(ep0), counter0=np.array(counter0), commands0=_np(cmd0))
+    for k, v in acc.items():
+        out[k] = np.stack(v)
+    out["final_episode_sums"] = _np(torch.stack([ref.e.episode_sums[k] for k in spec.active_rewards()]))
+    n_push, n_means = int(out["pushed"].sum()), int(out["has_means"].sum())
+    changed = int((out["commands"][-1][:, :2] != _np(cmd0)[:, :2]).any(axis=1).sum())
+    assert n_push >= 1 and n_means >= 3 and changed >= 6, (n_push, n_means, changed)
+    return out, dict(pushes=n_push, steps_with_means=n_means, envs_with_new_commands=changed, resets=int(out["reset"].sum()))
+
+
 # ---------------------------------------------------------------- tiny protobuf walker for the ONNX actor
 def _varint(buf, i):
     v, sh = 0, 0
@@ -328,6 +389,8 @@ def main():
         save(f"env_d{D}.npz", d, rep)
     d, rep = torque_case()
     save("pre_physics_d12.npz", d, rep)
+    d, rep = callback_case()
+    save("env_callback_d12.npz", d, rep)
     d, rep = onnx_probe()
     save("onnx_actor_probe.npz", d, rep)
     json.dump(manifest, open(os.path.join(GOLD, "MANIFEST.json"), "w"), indent=1, sort_keys=True)

@@ -45,6 +45,8 @@ def _install_stubs():
     pkg._hg_stub = True
     for sub in ("gymapi", "gymtorch", "gymutil", "terrain_utils"):
         m = types.ModuleType("isaacgym." + sub)
+        if sub == "gymtorch":
+            m.unwrap_tensor = lambda t: t          # _push_robots hands root_states back to the simulator (:680-681)
         setattr(pkg, sub, m)
         sys.modules["isaacgym." + sub] = m
     tu = types.ModuleType("isaacgym.torch_utils")
@@ -53,7 +55,7 @@ def _install_stubs():
     tu.get_euler_xyz = isaac_math.get_euler_xyz
     tu.to_torch = isaac_math.to_torch
     tu.get_axis_params = isaac_math.get_axis_params
-    tu.quat_apply = lambda a, b: b
+    tu.quat_apply = isaac_math.quat_apply
     tu.normalize = lambda x, eps=1e-9: x / x.norm(p=2, dim=-1).clamp(min=eps).unsqueeze(-1)
     tu.torch_rand_float = lambda lo, hi, shape, device: (hi - lo) * torch.rand(*shape, device=device) + lo
     tu.__all__ = ["torch", "np", "quat_rotate_inverse", "get_euler_xyz", "to_torch", "get_axis_params",
@@ -101,7 +103,21 @@ def load_env_class(D: int):
 
 
 _BOUND = ["_get_phase", "_get_gait_phase", "compute_ref_state", "_get_noise_scale_vec", "check_termination",
-          "compute_observations", "compute_reward", "_prepare_reward_function"]
+          "compute_observations", "compute_reward", "_prepare_reward_function", "_post_physics_step_callback",
+          "_resample_commands", "_push_robots"]
+
+
+class _Replay:
+    """Feeds `torch_rand_float` the given U[0,1) draws: the reference draws `len(env_ids)` numbers per call, the
+    kernels take one draw per env, so each queued call carries the rows it must return."""
+
+    def __init__(self):
+        self.queue = []
+
+    def __call__(self, lower, upper, shape, device):
+        u = self.queue.pop(0)
+        assert tuple(u.shape) == tuple(shape), (u.shape, shape)
+        return (upper - lower) * u + lower
 
 
 class RefEnv:
@@ -150,18 +166,39 @@ class RefEnv:
         e.noise_scale_vec = e._get_noise_scale_vec(cfg)
         e._prepare_reward_function()
         e.ref_dof_pos = z(N, D)       # the reference first sets it in compute_observations() at init (:177)
+        # _post_physics_step_callback / _resample_commands / _push_robots state (:188-191,257-271)
+        e.max_episode_length_s = cfg.env.episode_length_s
+        cfg.domain_rand.push_interval = np.ceil(cfg.domain_rand.push_interval_s / e.dt)
+        e.command_ranges = class_to_dict(cfg.commands.ranges)
+        e.commands = z(N, cfg.commands.num_commands)
+        e.forward_vec = torch.tensor([1.0, 0.0, 0.0]).repeat(N, 1)
+        e.common_step_counter = 0
+        e.gym = types.SimpleNamespace(set_actor_root_state_tensor=lambda sim, t: None)
+        e.sim = None
+        self.replay = _Replay()
         self.e = e
         self._randn = None
 
-    def step(self, sim, noise):
+    def step(self, sim, noise, callback=None):
+        """callback = dict(u_cmd [N,3], u_push [N,5], u_cmd_reset [N,3]): also run the reference's
+        `_post_physics_step_callback` (with `_resample_commands`, `_push_robots`) and the command resampling + episode
+        means of `reset_idx`, replaying the given uniform draws; commands / push buffers then persist in the env."""
         e = self.e
+        g = self.cls.__init__.__globals__
+        g["torch_rand_float"] = self.replay
         from .isaac_math import quat_rotate_inverse
         get_euler_xyz_tensor = self.cls.__init__.__globals__["get_euler_xyz_tensor"]
         e.root_states, e.dof_pos, e.dof_vel = sim["root_states"], sim["dof_pos"], sim["dof_vel"]
-        e.contact_forces, e.rigid_state, e.commands = sim["contact_forces"], sim["rigid_state"], sim["commands"]
+        e.contact_forces, e.rigid_state = sim["contact_forces"], sim["rigid_state"]
         e.actions = sim["actions"].clone()
         e.torques = sim["torques"]
-        e.rand_push_force, e.rand_push_torque = sim["rand_push_force"], sim["rand_push_torque"]
+        if callback is None:
+            e.commands = sim["commands"]
+            e.rand_push_force, e.rand_push_torque = sim["rand_push_force"], sim["rand_push_torque"]
+        else:
+            e.root_states = e.root_states.clone()
+            if not hasattr(e, "rand_push_force"):
+                e.rand_push_force, e.rand_push_torque = torch.zeros(e.num_envs, 3), torch.zeros(e.num_envs, 3)
         e.env_frictions, e.body_mass = sim["env_frictions"], sim["body_mass"]
         e.episode_length_buf += 1
         e.base_quat = e.root_states[:, 3:7]
@@ -169,9 +206,24 @@ class RefEnv:
         e.base_ang_vel = quat_rotate_inverse(e.base_quat, e.root_states[:, 10:13])
         e.projected_gravity = quat_rotate_inverse(e.base_quat, e.gravity_vec)
         e.base_euler_xyz = get_euler_xyz_tensor(e.base_quat)
+        ep_means = None
+        if callback is not None:
+            e.common_step_counter += 1
+            ids = (e.episode_length_buf % int(e.cfg.commands.resampling_time / e.dt) == 0).nonzero(as_tuple=False).flatten()
+            u = callback["u_cmd"]
+            self.replay.queue = [u[ids, 0:1], u[ids, 1:2], u[ids, 2:3]]
+            if e.cfg.domain_rand.push_robots and e.common_step_counter % e.cfg.domain_rand.push_interval == 0:
+                self.replay.queue += [callback["u_push"][:, :2], callback["u_push"][:, 2:5]]
+            e._post_physics_step_callback()
+            assert not self.replay.queue
         e.check_termination()
         e.compute_reward()
         ids = e.reset_buf.nonzero(as_tuple=False).flatten()
+        if len(ids) > 0 and callback is not None:          # reset_idx :1127 and :1141-1143, the reference's own lines
+            u = callback["u_cmd_reset"]
+            self.replay.queue = [u[ids, 0:1], u[ids, 1:2], u[ids, 2:3]]
+            e._resample_commands(ids)
+            ep_means = torch.stack([torch.mean(e.episode_sums[k][ids]) / e.max_episode_length_s for k in e.episode_sums])
         if len(ids) > 0:                                   # tensor part of reset_idx (:1132-1163)
             e.last_last_actions[ids] = 0.0
             e.actions[ids] = 0.0
@@ -200,5 +252,9 @@ class RefEnv:
         clip = e.cfg.normalization.clip_observations
         obs = torch.clip(e.obs_buf, -clip, clip)
         priv = torch.clip(e.privileged_obs_buf, -clip, clip)
-        return dict(obs=obs, priv=priv, rew=e.rew_buf.clone(), reset=e.reset_buf.clone(),
-                    time_out=e.time_out_buf.clone())
+        out = dict(obs=obs, priv=priv, rew=e.rew_buf.clone(), reset=e.reset_buf.clone(),
+                   time_out=e.time_out_buf.clone())
+        if callback is not None:
+            out.update(commands=e.commands.clone(), root_states=e.root_states.clone(), episode_means=ep_means,
+                       rand_push_force=e.rand_push_force.clone(), rand_push_torque=e.rand_push_torque.clone())
+        return out

@@ -30,7 +30,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hgb200.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes prototypes and header disagree"
-    assert lib.hg_abi_version() == 3
+    assert lib.hg_abi_version() == 4
     assert lib.hg_launch_count() == 0            # nothing launched on a CPU box
 
 
@@ -46,14 +46,15 @@ def test_struct_layouts_match_header_sizes():
     """Compile a 10-line C program against the header and compare sizeof() with the ctypes mirrors."""
     src = '#include "hgb200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(HgGemmProblem),sizeof(HgHeadNet),sizeof(HgLossArgs),sizeof(HgBf16Shadow),sizeof(HgAdamArgs),' \
-          'sizeof(HgEnvConfig),sizeof(HgEnvBuffers));printf("%zu\\n",sizeof(HgFusedHead));return 0;}\n'
+          'sizeof(HgEnvConfig),sizeof(HgEnvBuffers));printf("%zu %zu %zu\\n",sizeof(HgFusedHead),sizeof(HgCommandArgs),' \
+          'sizeof(HgActionArgs));return 0;}\n'
     tmp = os.path.join(_lib.BUILD_DIR, "abi_probe")
     os.makedirs(_lib.BUILD_DIR, exist_ok=True)
     open(tmp + ".c", "w").write(src)
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), tmp + ".c", "-o", tmp], check=True)
     sizes = [int(x) for x in subprocess.run([tmp], capture_output=True, text=True, check=True).stdout.split()]
     mirrors = [_lib.HgGemmProblem, _lib.HgHeadNet, _lib.HgLossArgs, _lib.HgBf16Shadow, _lib.HgAdamArgs, _lib.HgEnvConfig,
-               _lib.HgEnvBuffers, _lib.HgFusedHead]
+               _lib.HgEnvBuffers, _lib.HgFusedHead, _lib.HgCommandArgs, _lib.HgActionArgs]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 
@@ -62,6 +63,8 @@ def test_argument_validation_without_gpu():
     assert lib.hg_gemm_grouped(None, 0, 0, 128, 1, None) == -1
     assert b"num_problems" in lib.hg_last_error()
     assert lib.hg_gae_returns(None, None, None, None, 0.9, 0.9, 1, 1, None, None, None, None) == -1
+    assert lib.hg_command_step(None, None) == -1
+    assert lib.hg_episode_means(None, None, 22, 16, 24.0, None, None, None) == -1
 
 
 def test_reference_api_surface():

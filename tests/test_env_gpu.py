@@ -120,3 +120,130 @@ def test_in_kernel_noise_statistics():
     assert torch.allclose(d1[:, on].std(0), sigma[on], rtol=0.05)
     assert float(d1[:, on].mean(0).abs().max()) < 4 * float(sigma.max()) / N ** 0.5
     assert not torch.equal(d1, d2)
+
+
+# ---------------------------------------------------------------------------------- SURVEY 8f rank 2
+CB_SIM_KEYS = ("root_states", "dof_state", "contact_forces", "rigid_state", "torques", "env_frictions", "body_mass")
+
+
+def test_callback_golden_replay(golden_dir):
+    """`_post_physics_step_callback` (+ `_resample_commands`, `_push_robots`) and the command / extras part of `reset_idx`
+    inside the stateful env loop, against the fixture recorded from the UNMODIFIED reference with replayed uniform draws.
+    Exact: flags, which envs were resampled / pushed, the pushed root velocities and push buffers (pure fp32 mul + add).
+    <= 1e-5 relative: the heading-derived yaw command (atan2f vs libm), observations, rewards, episode means."""
+    z = np.load(f"{golden_dir}/env_callback_d12.npz")
+    N, steps = int(z["N"]), int(z["steps"])
+    env = XBotEnvMath(XBotMathConfig.for_dof(12, num_envs=N), DEV)
+    env.episode_length_buf.copy_(torch.tensor(z["ep_len0"]))
+    env._callback_state()
+    env.commands.copy_(torch.tensor(z["commands0"]))
+    env.common_step_counter = int(z["counter0"])
+    t = lambda k, s: torch.tensor(z[k][s]).to(DEV).contiguous()
+    pushes = means = 0
+    for s in range(steps):
+        sim = {k: t(k, s) for k in CB_SIM_KEYS}
+        sim["actions"] = t("actions", s)
+        obs, priv, rew, reset, tout, episode = env.step_with_callbacks(sim, t("noise", s), u_cmd=t("u_cmd", s), u_push=t("u_push", s),
+                                                                       u_cmd_reset=t("u_cmd_reset", s))
+        torch.cuda.synchronize()
+        assert torch.equal(reset.cpu(), torch.tensor(z["reset"][s])) and torch.equal(tout.cpu(), torch.tensor(z["time_out"][s])), s
+        want_cmd = torch.tensor(z["commands"][s])
+        got_cmd = env.commands.cpu()
+        assert torch.equal(got_cmd[:, [0, 1, 3]], want_cmd[:, [0, 1, 3]]), f"step {s}: resampled commands"
+        assert close(got_cmd[:, 2], want_cmd[:, 2])[0], f"step {s}: heading -> yaw command {close(got_cmd[:, 2], want_cmd[:, 2])[1]}"
+        assert torch.equal(sim["root_states"].cpu(), torch.tensor(z["root_states_out"][s])), f"step {s}: pushed root states"
+        assert torch.equal(env.rand_push_force.cpu(), torch.tensor(z["rand_push_force"][s]))
+        assert torch.equal(env.rand_push_torque.cpu(), torch.tensor(z["rand_push_torque"][s]))
+        for name, got, want in (("obs", obs, z["obs"][s]), ("priv", priv, z["priv"][s]), ("rew", rew, z["rew"][s])):
+            ok, err = close(got.cpu(), torch.tensor(want))
+            assert ok, f"step {s} {name}: max abs err {err}"
+        pushes += int(z["pushed"][s])
+        assert int(env.episode_reset_count.item()) == int(z["reset"][s].sum())
+        if z["has_means"][s]:
+            means += 1
+            ok, err = close(env.episode_means_tensor.cpu(), torch.tensor(z["episode_means"][s]))
+            assert ok, f"step {s}: episode means {err}"
+            assert set(episode) == {"rew_" + k for k in eo.xbot_spec(12).active_rewards()}
+    assert pushes >= 1 and means >= 3
+    ok, err = close(env.episode_sums_tensor.cpu(), torch.tensor(z["final_episode_sums"]))
+    assert ok, err
+
+
+def test_callback_vs_oracle_4096_and_philox():
+    """4096 envs x 6 steps with a push on step 2 against the oracle (given draws), then the in-kernel Philox draws:
+    resampled commands stay inside their ranges, are zeroed below 0.2 and untouched elsewhere."""
+    N = 4096
+    spec, cb = eo.xbot_spec(12), eo.CallbackSpec()
+    cfg = XBotMathConfig.for_dof(12, num_envs=N)
+    env = XBotEnvMath(cfg, DEV)
+    st = eo.EnvState(spec, N)
+    g = torch.Generator().manual_seed(11)
+    ep0 = torch.randint(0, 2300, (N,), generator=g)
+    ep0[:300] = 798                                            # a block of envs hits the resampling boundary on step 2
+    st.episode_length_buf = ep0.clone()
+    env.episode_length_buf.copy_(ep0)
+    env._callback_state()
+    cmd0 = torch.cat((0.5 * torch.randn(N, 3, generator=g), 3.0 * (2 * torch.rand(N, 1, generator=g) - 1)), dim=1)
+    st.commands, st.rand_push_force, st.rand_push_torque = cmd0.clone(), torch.zeros(N, 3), torch.zeros(N, 3)
+    env.commands.copy_(cmd0)
+    env.common_step_counter = 398
+    for s in range(6):
+        sim = eo.synthetic_sim_state(spec, N, g, base_contact_frac=0.03)
+        noise = torch.randn(N, spec.So, generator=g)
+        u_cmd, u_push, u_rst = torch.rand(N, 3, generator=g), torch.rand(N, 5, generator=g), torch.rand(N, 3, generator=g)
+        want = eo.env_step(spec, st, sim, noise, callback=dict(spec=cb, common_step_counter=398 + s + 1, u_cmd=u_cmd, u_push=u_push,
+                                                               u_cmd_reset=u_rst))
+        dsim = {k: sim[k].to(DEV).contiguous() for k in CB_SIM_KEYS}
+        dsim["actions"] = sim["actions"].to(DEV)
+        obs, priv, rew, reset, tout, _ = env.step_with_callbacks(dsim, noise.to(DEV), u_cmd=u_cmd.to(DEV), u_push=u_push.to(DEV),
+                                                                 u_cmd_reset=u_rst.to(DEV))
+        assert want["pushed"] == (s == 1)
+        assert torch.equal(reset.cpu(), want["reset"])
+        assert torch.equal(env.commands.cpu()[:, [0, 1, 3]], want["commands"][:, [0, 1, 3]])
+        assert close(env.commands.cpu()[:, 2], want["commands"][:, 2])[0]
+        assert torch.equal(dsim["root_states"].cpu(), want["root_states"])
+        for name, a, b in (("obs", obs, want["obs"]), ("priv", priv, want["priv"]), ("rew", rew, want["rew"])):
+            ok, err = close(a.cpu(), b)
+            assert ok, (s, name, err)
+        if want["episode_means"] is not None:
+            ok, err = close(env.episode_means_tensor.cpu(), want["episode_means"])
+            assert ok, (s, err)
+    # in-kernel Philox draws
+    env.episode_length_buf.fill_(799)
+    before = env.commands.clone()
+    env.episode_length_buf[N // 2:] = 5
+    root = dsim["root_states"].clone()
+    env.common_step_counter = 799                              # -> 800: a push step
+    assert env.post_physics_callback(root) is True
+    c = env.commands.cpu()
+    half = N // 2
+    assert torch.equal(c[half:, [0, 1, 3]], before.cpu()[half:, [0, 1, 3]])          # not at the boundary: untouched
+    x, y, h = c[:half, 0], c[:half, 1], c[:half, 3]
+    nz = (x != 0) | (y != 0)
+    assert 0.3 < nz.float().mean() < 1.0
+    assert (x[nz] >= -0.3).all() and (x[nz] <= 0.6).all() and (y[nz] >= -0.3).all() and (y[nz] <= 0.3).all()
+    assert (torch.sqrt(x[nz] ** 2 + y[nz] ** 2) > 0.2).all()
+    assert (h >= -3.14).all() and (h <= 3.14).all() and h.std() > 1.0
+    assert (c[:, 2].abs() <= 1.0).all()
+    pf, pt = env.rand_push_force.cpu(), env.rand_push_torque.cpu()
+    assert (pf[:, :2].abs() <= 0.2).all() and (pt.abs() <= 0.4).all() and pf[:, :2].std() > 0.05 and pt.std() > 0.1
+    assert torch.equal(root.cpu()[:, 7:9], pf[:, :2]) and torch.equal(root.cpu()[:, 10:13], pt)
+    assert torch.equal(env.root_vel_prepush.cpu(), dsim["root_states"].cpu()[:, 7:13])
+
+
+def test_synthetic_env_with_callbacks_is_a_complete_vecenv():
+    """`SyntheticXBotEnv(callbacks=True)`: the VecEnv loop with command resampling, pushes and extras["episode"]."""
+    from humanoid_gym_with_comments_b200.envs import SyntheticXBotEnv
+    torch.manual_seed(0)
+    env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=512), DEV, callbacks=True)
+    env.math._callback_state()
+    env.math.common_step_counter = 397
+    acts = torch.zeros(512, 12, device=DEV)
+    seen_push = False
+    for i in range(5):
+        obs, priv, rew, dones, extras = env.step(acts)
+        seen_push = seen_push or bool(env.math.rand_push_force.abs().sum() > 0)
+        assert obs.shape == (512, 705) and priv.shape == (512, 219) and rew.shape == (512,)
+        assert set(extras) >= {"time_outs", "episode"} and len(extras["episode"]) == 22
+        assert all(torch.isfinite(v) for v in extras["episode"].values())
+    assert seen_push and torch.isfinite(obs).all() and (env.math.commands[:, 2].abs() <= 1).all()

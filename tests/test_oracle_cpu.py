@@ -115,6 +115,55 @@ def test_env_golden(D, golden_dir):
     assert z["reset"].sum() > 0 and z["time_out"].sum() > 0
 
 
+def test_env_callback_golden(golden_dir):
+    """the oracle's `_post_physics_step_callback` / `_resample_commands` / `_push_robots` / episode-mean
+    restatement replays the fixture recorded from the unmodified reference bit for bit."""
+    z = np.load(f"{golden_dir}/env_callback_d12.npz")
+    N, steps = int(z["N"]), int(z["steps"])
+    spec, cb = eo.xbot_spec(12), eo.CallbackSpec()
+    st = eo.EnvState(spec, N)
+    st.episode_length_buf = torch.tensor(z["ep_len0"])
+    st.commands, st.rand_push_force, st.rand_push_torque = torch.tensor(z["commands0"]), torch.zeros(N, 3), torch.zeros(N, 3)
+    t = lambda k, s: torch.tensor(z[k][s])
+    pushes = 0
+    for s in range(steps):
+        sim = {k: t(k, s) for k in ("root_states", "dof_state", "contact_forces", "rigid_state", "actions", "torques",
+                                    "env_frictions", "body_mass")}
+        sim["dof_pos"], sim["dof_vel"] = sim["dof_state"].view(N, 12, 2)[..., 0], sim["dof_state"].view(N, 12, 2)[..., 1]
+        sim["commands"] = sim["rand_push_force"] = sim["rand_push_torque"] = None      # must come from the callback state
+        out = eo.env_step(spec, st, sim, t("noise", s), callback=dict(
+            spec=cb, common_step_counter=int(z["counter0"]) + s + 1, u_cmd=t("u_cmd", s), u_push=t("u_push", s),
+            u_cmd_reset=t("u_cmd_reset", s)))
+        for k in ("obs", "priv", "rew", "reset", "time_out", "commands", "rand_push_force", "rand_push_torque"):
+            assert torch.equal(out[k], t(k, s)), (s, k)
+        assert torch.equal(out["root_states"], t("root_states_out", s))
+        assert bool(z["pushed"][s]) == out["pushed"]
+        pushes += int(out["pushed"])
+        assert bool(z["has_means"][s]) == (out["episode_means"] is not None)
+        if out["episode_means"] is not None:
+            assert torch.equal(out["episode_means"], t("episode_means", s))
+    assert pushes >= 1
+    assert torch.equal(st.episode_sums, torch.tensor(z["final_episode_sums"]))
+
+
+def test_quat_apply_heading_matches_euler_yaw():
+    """`quat_apply` is restated from Isaac Gym (absent from the reference tree, parity unpinned): for a pure yaw rotation
+    the heading atan2(forward_y, forward_x) must equal the yaw of `get_euler_xyz`, and the rotation must keep norms."""
+    from oracle.isaac_math import euler_xyz_wrapped, quat_apply
+    yaw = torch.linspace(-3.0, 3.0, 25)
+    q = torch.stack((torch.zeros_like(yaw), torch.zeros_like(yaw), torch.sin(yaw / 2), torch.cos(yaw / 2)), dim=1)
+    f = quat_apply(q, torch.tensor([1.0, 0.0, 0.0]).repeat(25, 1))
+    assert torch.allclose(torch.atan2(f[:, 1], f[:, 0]), yaw, atol=1e-6)
+    assert torch.allclose(euler_xyz_wrapped(q)[:, 2], yaw, atol=1e-6)
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(64, 4, generator=g)
+    q = q / q.norm(dim=1, keepdim=True)
+    v = torch.randn(64, 3, generator=g)
+    assert torch.allclose(quat_apply(q, v).norm(dim=1), v.norm(dim=1), atol=1e-5)
+    from oracle.isaac_math import quat_rotate_inverse
+    assert torch.allclose(quat_rotate_inverse(q, quat_apply(q, v)), v, atol=1e-5)
+
+
 def test_obs_layout_matches_sim2sim_description():
     """Independent pin of the 47-wide frame + oldest->newest stacking (reference scripts/sim2sim.py:210-233)."""
     spec = eo.xbot_spec(12)
