@@ -31,6 +31,7 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barrie
 #define HG_EPI_WARPS 16
 #endif
 constexpr int MN_ATOM_BYTES = BLOCK_K * 128;  // 8192: one [64 x 64] bf16 atom
+constexpr int HG_MAX_COLSUM_COLS = 2048;      // columns (summed over the problems of a group) a DELU launch can column-sum
 
 template <int BLOCK_N, int EPI, int CG>
 struct Cfg {
@@ -47,7 +48,11 @@ struct Cfg {
   static constexpr int COL_SPLIT = EPI_WARPS / 4;       // column slices per tile
   // HEAD: [16][128] fp32 output weights + [4 slices][128][17] fp32 partial sums + per-output constants
   static constexpr int HEAD_BYTES = (16 * 128 + 4 * 128 * 17 + 64) * 4;
-  static constexpr int EPI_BYTES = (EPI == HG_EPI_BIAS_ELU_HEAD) ? HEAD_BYTES : EPI_WARPS * EPI_TILE_BYTES;
+  // DELU: per-CTA column-sum accumulators (bias gradients) for every column of the group, flushed once per launch
+  // (one array per TMEM lane quarter: slot (quarter, column) has exactly one owner warp, so no shared atomics -- fp32
+  // shared atomics are CAS loops)
+  static constexpr int COLSUM_BYTES = (EPI == HG_EPI_DELU_BF16) ? 4 * HG_MAX_COLSUM_COLS * 4 : 0;
+  static constexpr int EPI_BYTES = (EPI == HG_EPI_BIAS_ELU_HEAD) ? HEAD_BYTES : EPI_WARPS * EPI_TILE_BYTES + COLSUM_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET - EPI_BYTES) / STAGE_BYTES;  // 3..7 deep TMA ring
   static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
   static_assert(STAGES >= 3, "pipeline too shallow");
@@ -65,6 +70,7 @@ struct DevProblem {
   const __nv_bfloat16* act;
   long long ldact;
   float* colsum;
+  int colsum_off;      // first slot of this problem in the CTA's shared column-sum array
 };
 
 struct alignas(64) GroupParams {
@@ -170,13 +176,19 @@ __device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* til
   if (colsum) {     // (warp-uniform) bias gradient of the layer below: column sums of the staged tile, 32 REDs per chunk
     float c[4][2];
     tile_colsum_mma(tb, lane, c);
-    if (lane < 4) {
+    // column t lives in c[t / 8][t % 2] of the lanes with lane % 4 == (t % 8) / 2: bring it to lane t (one conflict-free
+    // shared atomic per chunk).  Global REDs straight from here are costly: every CTA hits the same few lines of the
+    // bias-gradient vector and the L2 serialises requests per line (eight 4-lane REDs per chunk: 2x slower launch).
+    float mine = 0.f;
 #pragma unroll
-      for (int nb = 0; nb < 4; ++nb) {
-        atomicAdd(colsum + nb * 8 + 2 * lane, c[nb][0]);
-        atomicAdd(colsum + nb * 8 + 2 * lane + 1, c[nb][1]);
+    for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float x = __shfl_sync(0xffffffffu, c[nb][e], (lane & 7) >> 1);
+        if ((lane >> 3) == nb && (lane & 1) == e) mine = x;
       }
     }
+    colsum[lane] += mine;                 // this warp's own shared-memory accumulator (flushed once at the end of the launch)
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -195,8 +207,8 @@ __device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* til
 // Column sums of the warp's staged 32 x 32 bf16 tile (rows EPI_ROW_PITCH bytes apart) on the tensor core: ones[16x16] x
 // tile[16 x 8] per mma.sync.m16n8k16, the tile read as B fragments with ldmatrix.trans.  Every row of the product holds
 // the column sums, so lane t ends up with the sums of columns nb*8 + 2*(t%4) + {0,1}, nb = 0..3, in c[nb][0..1].
-// Replaces a 31-shuffle butterfly (~190 instructions per chunk) with 4 ldmatrix + 8 mma; the summands are the
-// bf16-rounded values the weight-gradient GEMM reads, accumulated in fp32.
+// Replaces a 31-shuffle butterfly (~190 instructions per chunk) with 4 ldmatrix + 8 mma + 8 shuffles; the summands are
+// the bf16-rounded values the weight-gradient GEMM reads, accumulated in fp32.
 __device__ __forceinline__ void tile_colsum_mma(uint32_t tile_addr, int lane, float (&c)[4][2]) {
   const uint32_t ones = 0x3F803F80u;      // bf16x2 (1.0, 1.0)
 #pragma unroll
@@ -228,7 +240,7 @@ __device__ __forceinline__ void prefetch_act(const DevProblem& q, int row_base, 
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int n0, uint32_t (&v)[32], int lane, float* tile,
-                                               const uint4 (&pre)[4]) {
+                                               const uint4 (&pre)[4], float* s_colsum) {
   const bool row_ok = row < q.M;
   const bool full = (n0 + 32 <= q.N);
   if constexpr (EPI == HG_EPI_STORE_F32) {
@@ -313,9 +325,13 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
         }
       }
       __syncwarp();
+#ifndef HG_COLSUM_BUTTERFLY
       store_rows_bf16(d, tile, lane, reinterpret_cast<__nv_bfloat16*>(q.out) + n0, q.ldo, row_base, q.M,
-                      q.colsum ? q.colsum + n0 : nullptr);
+                      q.colsum ? s_colsum + q.colsum_off + n0 : nullptr);
       return;
+#else     // A/B switch (tools/build_variant.sh): fp32 shuffle butterfly below
+      store_rows_bf16(d, tile, lane, reinterpret_cast<__nv_bfloat16*>(q.out) + n0, q.ldo, row_base, q.M);
+#endif
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -332,7 +348,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
       // bias gradient of the layer below = column sums of what was just written (bf16-rounded values
       // are what the weight-gradient GEMM will read, but the fp32 sum is the better estimate).
       float s = warp_colsum32(d, lane);
-      if (n0 + lane < q.N) atomicAdd(q.colsum + n0 + lane, s);
+      if (n0 + lane < q.N) s_colsum[q.colsum_off + n0 + lane] += s;
     }
   }
 }
@@ -685,6 +701,13 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
     // below beat eight by ~20 %; double-buffering the TMEM loads or fetching the DELU activations a tile ahead costs
     // more in registers (640 threads -> 102 per thread) than it hides in latency, so neither is done.
     constexpr bool DELU = (EPI == HG_EPI_DELU_BF16);
+    float* s_colsum_all = epi_tiles + K::EPI_WARPS * (K::EPI_TILE_BYTES / 4);     // [4 quarters][HG_MAX_COLSUM_COLS]
+    float* s_colsum = s_colsum_all + quad * HG_MAX_COLSUM_COLS;   // column c of a problem is always handled by the same
+    const int et = (warp - 4) * 32 + lane;                        // (quarter, column slice) warp: plain read-modify-write
+    if constexpr (DELU) {
+      for (int i = et; i < 4 * HG_MAX_COLSUM_COLS; i += K::EPI_WARPS * 32) s_colsum_all[i] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(K::EPI_WARPS * 32) : "memory");
+    }
     for (int t = group_id; t < P.total_tiles; t += num_groups) {
       const Tile ti = decode_tile(P, t);
       const DevProblem& q = P.p[ti.g];
@@ -710,7 +733,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
 #pragma unroll
           for (int j = 0; j < 32; ++j) asm volatile("" ::"r"(v[j]));
 #else
-          epilogue_chunk<EPI>(q, row, col0 + c * 32, v, lane, tile, pre[DELU ? c : 0]);
+          epilogue_chunk<EPI>(q, row, col0 + c * 32, v, lane, tile, pre[DELU ? c : 0], s_colsum);
 #endif
         }
       }
@@ -725,6 +748,18 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (DELU) {      // one flush per CTA and launch: (columns / 32) coalesced REDs instead of one per 32 x 32 chunk
+      asm volatile("bar.sync 1, %0;" ::"n"(K::EPI_WARPS * 32) : "memory");
+      for (int g = 0; g < P.num_problems; ++g) {
+        const DevProblem& q = P.p[g];
+        if (!q.colsum) continue;
+        for (int c = et; c < q.N; c += K::EPI_WARPS * 32) {
+          const float* sc = s_colsum_all + q.colsum_off + c;
+          const float v = ((sc[0] + sc[HG_MAX_COLSUM_COLS]) + sc[2 * HG_MAX_COLSUM_COLS]) + sc[3 * HG_MAX_COLSUM_COLS];
+          if (v != 0.f) atomicAdd(q.colsum + c, v);
+        }
+      }
     }
     }
   }
@@ -821,7 +856,7 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
   HG_CHECK(!fused_head || (block_n == 128 && cg == 1), "the fused-head epilogue needs block_n 128 and cta_group 1");
   memset(&gp, 0, sizeof(gp));
   gp.num_problems = n;
-  int tiles = 0;
+  int tiles = 0, colsum_cols = 0;
   for (int g = 0; g < n; ++g) {
     const HgGemmProblem& h = pr[g];
     DevProblem& q = gp.p[g];
@@ -845,6 +880,9 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
     q.tile_end = tiles;
     q.out = h.out; q.ldo = h.ldo; q.bias = h.bias;
     q.act = reinterpret_cast<const __nv_bfloat16*>(h.act); q.ldact = h.ldact; q.colsum = h.colsum;
+    q.colsum_off = colsum_cols;
+    if (epilogue == HG_EPI_DELU_BF16 && h.colsum) colsum_cols += (h.N + 31) & ~31;
+    HG_CHECK(colsum_cols <= HG_MAX_COLSUM_COLS, "problem %d: a DELU launch can column-sum at most %d columns in total", g, HG_MAX_COLSUM_COLS);
     if (epilogue == HG_EPI_BIAS_ELU_BF16 || epilogue == HG_EPI_DELU_BF16 || epilogue == HG_EPI_BIAS_BF16)
       HG_CHECK(h.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(h.out) & 15) == 0, "problem %d: bf16 output alignment", g);
     if (epilogue == HG_EPI_DELU_BF16)

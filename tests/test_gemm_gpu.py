@@ -63,8 +63,11 @@ def test_delu_backward_with_colsum(block_n, cg):
     hf = H.float()
     want = (dZ.float() @ W.float()) * torch.where(hf > 0, torch.ones_like(hf), hf + 1)
     ok1, m1 = report("delu", out.float(), want, atol=1e-6, rtol=1e-2)
-    ok2, m2 = report("colsum", colsum, want.sum(0), atol=1e-5, rtol=1e-3)
-    assert ok1 and ok2, m1 + " | " + m2
+    # the bias gradient is the column sum of the STORED (bf16-rounded) dZ, accumulated in fp32 on the tensor core: exact
+    # against the stored tensor up to summation order, and within bf16 rounding noise (2^-9 * |dZ| * sqrt(M)) of the fp32 sum
+    ok2, m2 = report("colsum vs stored dZ", colsum, out.float().sum(0), atol=2e-5, rtol=1e-4)
+    ok3, m3 = report("colsum vs fp32", colsum, want.sum(0), atol=5e-4, rtol=1e-3)
+    assert ok1 and ok2 and ok3, " | ".join((m1, m2, m3))
 
 
 @pytest.mark.parametrize("cg", [1, 2])
