@@ -171,7 +171,7 @@ class MLPEngine:
         if self.cta_group_override:
             return self.cta_group_override
         if epi == EPI_DELU_BF16:
-            return 1
+            return int(os.environ.get("HG_DX_CG", 1))
         if epi == EPI_ATOMIC_F32 and max(p.M for p in problems) <= 128 and os.environ.get("HG_DW_SMALL_CG", "2") == "1":
             return 1         # experiment: weight gradients of 128-row layers leave half of a 256-row pair tile empty
         if max(p.M for p in problems) >= 8192 or max(p.K for p in problems) >= 8192:
