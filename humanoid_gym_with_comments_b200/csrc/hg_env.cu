@@ -185,7 +185,7 @@ __device__ __forceinline__ void shift_store(float* __restrict__ dst, __nv_bfloat
     }
   }
 }
-constexpr int SHIFT_UNIT = 512;   // floats per streaming unit (16 loads per lane)
+constexpr int SHIFT_UNIT = 672;   // floats per streaming unit (21 loads per lane): the 658-float actor history of D = 12 is one unit
 
 // One thread per env for the scalar math (32 envs per block; the block's 4 warps split the work by role so the
 // dependent-latency chain per env is ~4x shorter), then all 128 threads stream the history rows.
@@ -222,12 +222,14 @@ __global__ void __launch_bounds__(ENV_THREADS, 2) env_step_kernel(const __grid_c
     // so these 12 warps stream the 14 old actor frames / 2 old critic frames while warps 0-3 do the per-env math.
     if (doB) {
       // Work units: the actor history of an env in slabs of SHIFT_UNIT floats, then its critic history in slabs of
-      // SHIFT_UNIT; units are dealt round-robin to the 12 streaming warps (16 envs x 3 units at D = 12: 4 round trips each).
+      // SHIFT_UNIT; units are dealt round-robin to the 12 streaming warps (16 envs x 2 units at D = 12: <= 3 round trips
+      // each, at most 2 of them long).  Eight role warps + eight streaming warps measured slower (17.6 vs 15.2 us): the
+      // streaming warps are the critical path of the block, not the per-env math.
       const int envs_here = min(ENV_PER_BLOCK, C.num_envs - n0);
       const int cnt_o = (C.frame_stack - 1) * So, cnt_p = (C.c_frame_stack - 1) * Sp;
       const int upo = (cnt_o + SHIFT_UNIT - 1) / SHIFT_UNIT, upe = upo + (cnt_p + SHIFT_UNIT - 1) / SHIFT_UNIT;
       for (int u = warp - ENV_ROLE_WARPS; u < envs_here * upe; u += ENV_THREADS / 32 - ENV_ROLE_WARPS) {
-        const int el = u / upe, part = u - el * upe;
+        const int part = u / envs_here, el = u - part * envs_here;   // part-major: every warp gets a mix of long and short units
         const int ne = n0 + el;
         const bool reset = env_base(C, B, ne, doA).reset;       // warp-uniform broadcast loads
         const bool actor = part < upo;
