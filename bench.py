@@ -249,6 +249,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the JSON line only (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=torch.device(dev))
     lib = _lib.load()
     N, T = a.envs, a.horizon
