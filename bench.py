@@ -67,6 +67,7 @@ def workload_config(a, world):
                         f"(BASELINE.json configs[1]); synthetic Isaac-Gym-shaped state, fused env step in the loop",
             "envs_per_gpu": a.envs, "horizon": a.horizon, "parallelism": f"env-sharded dp{world}",
             "rng": "in-kernel Philox4x32-10 keyed by (seed, step, row) for action and observation noise; --torch-rng switches to torch.randn",
+            "precision": "bf16 tensor-core GEMM operands with fp32 accumulation (hidden layers); output layers, losses, GAE, env math and Adam in fp32",
             "l2_policy": "per-iteration working set (storage 0.95 GB fp32 + 0.46 GB bf16) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -440,7 +441,7 @@ def run_ours(a):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16 tensor-core GEMMs with fp32 accumulate; fp32 elsewhere", "data": "synthetic",
+                "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(a, world), "clocks": clocks.summary(), "e2e": e2e,
                 "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
                 "roofline": roofline, "hbm_kernels": aux, "cpu_baseline": base}

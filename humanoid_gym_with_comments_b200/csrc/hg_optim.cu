@@ -1,5 +1,5 @@
 // Fused optimiser step on flat fp32 arenas: global grad-norm, clip, adaptive-KL learning rate, Adam, refresh of
-// the bf16 weight shadows the tensor-core layers read, and gradient zeroing -- three launches, no host sync.
+// the bf16 weight shadows the tensor-core layers read, and gradient zeroing -- two launches, no host sync.
 // Replaces nn.utils.clip_grad_norm_ + optimizer.step + the lr schedule of reference ppo.py:162-174,211-214
 // (~10 foreach kernels x 23 tensors + 3 host syncs per minibatch there).
 // HBM traffic: 4 B/param (norm) + 16 B read + 12 B written (+2 B shadow) per parameter.
@@ -12,31 +12,8 @@ struct ShadowTable {
   int n;
 };
 
-__global__ void grad_sumsq_kernel(const float* __restrict__ g, long long count, double* opt_state) {
-  pdl_trigger();
-  pdl_wait();
-  double acc = 0.0;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-    const float v = g[i];
-    acc += (double)v * (double)v;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  __shared__ double s[32];
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) t += s[w];
-    atomicAdd(&opt_state[2], t);
-  }
-}
-
 // One thread: everything the reference does on the host between backward() and optimizer.step().
-__global__ void opt_scalars_kernel(HgAdamArgs a) {
-  pdl_trigger();
-  pdl_wait();
+__device__ void opt_scalars(const HgAdamArgs& a, double sumsq) {
   const float* stats = a.grads + a.count;
   const double rows = (double)a.rows_global;
   double lr = a.opt_state[0];
@@ -48,7 +25,7 @@ __global__ void opt_scalars_kernel(HgAdamArgs a) {
   const double step = a.opt_state[1] + 1.0;
   const double bc1 = 1.0 - pow((double)a.beta1, step);
   const double bc2 = 1.0 - pow((double)a.beta2, step);
-  const float total = (float)sqrt(a.opt_state[2]);      // clip_grad_norm_: 2-norm over all parameters
+  const float total = (float)sqrt(sumsq);               // clip_grad_norm_: 2-norm over all parameters
   float coef = a.max_grad_norm / (total + 1e-6f);
   coef = coef > 1.0f ? 1.0f : coef;
   a.opt_state[0] = lr;
@@ -58,6 +35,7 @@ __global__ void opt_scalars_kernel(HgAdamArgs a) {
   a.opt_state[4] = lr / bc1;
   a.opt_state[5] = sqrt(bc2);
   a.opt_state[6] = (double)total;
+  a.opt_state[7] = 0.0;                                 // block ticket counter of grad_sumsq_kernel
   if (a.loss_log) {
     double* log = a.loss_log + (size_t)a.log_slot * 8;
     log[0] = (double)stats[0] / rows;
@@ -68,6 +46,36 @@ __global__ void opt_scalars_kernel(HgAdamArgs a) {
     log[5] = lr;
     log[6] = (double)total;
     log[7] = (double)coef;
+  }
+}
+
+// Global gradient sum of squares (double accumulation); the LAST block to finish (ticket in opt_state[7]) derives the
+// step's scalars -- clip coefficient, adaptive-KL learning rate, bias corrections -- so no separate one-thread launch.
+__global__ void grad_sumsq_kernel(HgAdamArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const float* __restrict__ g = a.grads;
+  double acc = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += stride) {
+    const float v = g[i];
+    acc += (double)v * (double)v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double s[32];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += s[w];
+    atomicAdd(&a.opt_state[2], t);
+    __threadfence();
+    const double ticket = atomicAdd(&a.opt_state[7], 1.0);
+    if (ticket == (double)(gridDim.x - 1)) {
+      __threadfence();
+      opt_scalars(a, atomicAdd(&a.opt_state[2], 0.0));   // every block's contribution is in (their adds precede their tickets)
+    }
   }
 }
 
@@ -98,7 +106,8 @@ __global__ void __launch_bounds__(256) adam_kernel(HgAdamArgs a, const __grid_co
     for (int s = 0; s < tab.n; ++s) {
       const long long off = i - tab.s[s].param_offset;
       if (off >= 0 && off < (long long)tab.s[s].rows * tab.s[s].cols) {
-        const int r = (int)(off / tab.s[s].cols), c = (int)(off - (long long)r * tab.s[s].cols);
+        const unsigned o32 = (unsigned)off, cols = (unsigned)tab.s[s].cols;      // a weight matrix has < 2^32 elements
+        const unsigned r = o32 / cols, c = o32 - r * cols;
         reinterpret_cast<__nv_bfloat16*>(tab.s[s].dst)[(long long)r * tab.s[s].ld + c] = __float2bfloat16_rn(p);
         break;
       }
@@ -125,12 +134,10 @@ extern "C" int hg_clip_adam_step(const HgAdamArgs* a, void* stream) {
   int blocks = (int)((a->count + 256 * 4 - 1) / (256 * 4));
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
   if (blocks < 1) blocks = 1;
-  HG_CUDA(launch_kernel(grad_sumsq_kernel, dim3(blocks), dim3(256), 0, s, 1, a->grads, a->count, a->opt_state));
-  HG_LAUNCH_CHECK();
-  HG_CUDA(launch_kernel(opt_scalars_kernel, dim3(1), dim3(1), 0, s, 1, dev));
+  HG_CUDA(launch_kernel(grad_sumsq_kernel, dim3(blocks), dim3(256), 0, s, 1, dev));
   HG_LAUNCH_CHECK();
   HG_CUDA(launch_kernel(adam_kernel, dim3(blocks), dim3(256), 0, s, 1, dev, tab));
   HG_LAUNCH_CHECK();
-  count_launch(3);
+  count_launch(2);
   return HG_OK;
 }

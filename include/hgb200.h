@@ -207,6 +207,8 @@ int hg_ppo_head_loss(const HgLossArgs* args_host, void* stream);
  *   grads: [count + HG_STATS_SLOTS] floats; grads[count + j] are the loss statistics of hg_ppo_head_loss.
  *   opt_state (device, 8 doubles): [0] lr  [1] step  [2] grad sum-sq (scratch, must start at 0)
  *                                  [3] clip coef  [4] step size lr/(1-b1^t)  [5] sqrt(1-b2^t)  [6] grad norm
+ *                                  [7] block ticket of the sum-of-squares launch (scratch, must start at 0)
+ *   Two launches: sum of squares (its last block derives the scalars), then clip + Adam + shadow refresh + zeroing.
  *   loss_log[log_slot*8 + {0..7}] = {value loss, surrogate loss, lin-vel loss, kl, entropy, lr, grad norm, clip coef}
  *   (means over rows_global rows) -- read back by the host once per update.
  */

@@ -80,6 +80,36 @@ def test_env_vs_oracle_4096(D):
     print("worst abs err", worst)
 
 
+@pytest.mark.parametrize("N,D", [(1, 12), (17, 12), (1003, 12), (1003, 18)])
+def test_env_ragged_env_counts(N, D):
+    """Env counts that are not a multiple of the 16-env block (ragged last block, a single env), with padded
+    destination rows (the learner's storage layout: fp32 row pitch = width, bf16 shadow pitch = 768 / 256 or 1024 / 320)."""
+    spec = eo.xbot_spec(D)
+    cfg = XBotMathConfig.for_dof(D, num_envs=N)
+    g = torch.Generator().manual_seed(5)
+    st = eo.EnvState(spec, N)
+    st.episode_length_buf = torch.randint(0, 2400, (N,), generator=g)
+    env = XBotEnvMath(cfg, DEV)
+    env.episode_length_buf.copy_(st.episode_length_buf)
+    ld_o, ld_p = (spec.num_obs + 63) // 64 * 64, (spec.num_priv + 63) // 64 * 64
+    for s in range(4):
+        sim = eo.synthetic_sim_state(spec, N, g, base_contact_frac=0.1)
+        noise = torch.randn(N, spec.So, generator=g)
+        want = eo.env_step(spec, st, sim, noise)
+        dsim = {k: sim[k].to(DEV).contiguous() for k in SIM_KEYS}
+        dsim["actions"] = sim["actions"].to(DEV)
+        o16 = torch.full((N, ld_o), 7.0, dtype=torch.bfloat16, device=DEV)
+        p16 = torch.full((N, ld_p), 7.0, dtype=torch.bfloat16, device=DEV)
+        obs, priv, rew, reset, tout = env.step(dsim, noise.to(DEV), obs16_out=o16, priv16_out=p16)
+        assert torch.equal(reset.cpu(), want["reset"]) and torch.equal(tout.cpu(), want["time_out"])
+        for name, got in (("obs", obs), ("priv", priv), ("rew", rew)):
+            ok, err = close(got.cpu(), want[name])
+            assert ok, f"N={N} D={D} step {s} {name}: {err}"
+        assert torch.equal(o16[:, :spec.num_obs].float(), obs.to(torch.bfloat16).float()), "bf16 shadow of obs"
+        assert torch.equal(p16[:, :spec.num_priv].float(), priv.to(torch.bfloat16).float()), "bf16 shadow of priv"
+        assert (o16[:, spec.num_obs:] == 7.0).all() and (p16[:, spec.num_priv:] == 7.0).all(), "padding columns untouched"
+
+
 def test_two_phase_equals_fused():
     """REWARD and OBS phases launched separately (as a real Isaac Gym env does around its gym reset calls)
     give the same result as the single fused launch."""
