@@ -231,7 +231,11 @@ __device__ __forceinline__ void tile_colsum_mma(uint32_t tile_addr, int lane, fl
 __device__ __forceinline__ void prefetch_act(const DevProblem& q, int row_base, int n0, int lane, uint4 (&pre)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
+#ifdef HG_DX_DIRECT_ACT      // A/B variant: every lane fetches its OWN row (no shared-memory staging, 4x the L1 wavefronts)
+    const int r = lane, piece = i;
+#else
     const int r = i * 8 + (lane >> 2), piece = lane & 3;
+#endif
     pre[i] = make_uint4(0, 0, 0, 0);
     if (n0 + 32 <= q.N && row_base + r < q.M)
       pre[i] = __ldg(reinterpret_cast<const uint4*>(q.act + (long long)(row_base + r) * q.ldact + n0) + piece);
@@ -303,17 +307,23 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
       // lane reads back its own row
       const uint32_t tb = smem_u32(tile);
       const int row_base = row - lane;
+#ifndef HG_DX_DIRECT_ACT
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + (lane >> 2), piece = lane & 3;
         sts128(tb + r * EPI_ROW_PITCH + piece * 16, pre[i]);
       }
       __syncwarp();
+#endif
       // dZ = dH * elu'(h), elu'(h) = 1 (h > 0) or h + 1 (h <= 0)  ==  fma(dH, min(h, 0), dH).  Rows past M need no
       // predicate: TMA zero-fills their A rows, so their accumulators are exactly 0.
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
+#ifdef HG_DX_DIRECT_ACT
+        const uint4 hw = pre[j >> 3];
+#else
         const uint4 hw = lds128(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16);
+#endif
         const uint32_t hv[4] = {hw.x, hw.y, hw.z, hw.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
