@@ -18,6 +18,7 @@
 //   MN-major: atoms of [64 k-rows x 64 mn] (k-row = 128 B, 8-row groups SBO=1024 B apart), atoms of
 //             successive 64-wide mn chunks LBO = 8192 B apart                      -> one TMA box {64,64} per atom
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "hg_common.cuh"
 
@@ -79,6 +80,10 @@ struct alignas(64) GroupParams {
   DevProblem p[HG_MAX_GROUP];
   int num_problems;
   int total_tiles;
+  // m_major (experiment switch, off by default): tiles numbered (m block, problem, n block) instead of (problem, m block,
+  // n block), possible when every problem has the same number of row blocks and no split-K: CTAs working side by side then
+  // sit on the SAME rows of different nets (an input shared by two nets is fetched from HBM once).
+  int m_major, tiles_per_m;
   // HG_EPI_BIAS_ELU_HEAD only: the fused output layers and the sampling stream of this launch
   HgFusedHead heads[HG_MAX_GROUP];
   const float* eps;
@@ -90,6 +95,17 @@ struct Tile {
 };
 
 __device__ __forceinline__ Tile decode_tile(const GroupParams& P, int t) {
+  if (P.m_major) {
+    Tile ti;
+    ti.m_blk = t / P.tiles_per_m;
+    int r = t - ti.m_blk * P.tiles_per_m, g = 0;
+    while (g + 1 < P.num_problems && r >= P.p[g].tiles_n) { r -= P.p[g].tiles_n; ++g; }
+    ti.g = g;
+    ti.n_blk = r;
+    ti.kb_begin = 0;
+    ti.kb_end = P.p[g].num_kb;
+    return ti;
+  }
   int g = 0;
   while (g + 1 < P.num_problems && t >= P.p[g].tile_end) ++g;
   const DevProblem& q = P.p[g];
@@ -906,6 +922,17 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
     if (rc != HG_OK) return rc;
   }
   gp.total_tiles = tiles;
+  gp.m_major = n > 1 ? 1 : 0;
+  gp.tiles_per_m = 0;
+  for (int g = 0; g < n; ++g) {
+    if (gp.p[g].tiles_m != gp.p[0].tiles_m || gp.p[g].k_splits != 1) gp.m_major = 0;
+    gp.tiles_per_m += gp.p[g].tiles_n;
+  }
+  // Measured on B200 (tools/phase_times.py, 4096 envs x 60): m-major leaves the update unchanged (5.29 vs 5.29 ms: the
+  // second read of obs was not the limiter) and slows the rollout launches (3.52 vs 3.38 ms), so problem-major stays the
+  // default; HG_TILE_ORDER=m selects m-major for experiments.
+  const char* order = getenv("HG_TILE_ORDER");
+  if (!(order && order[0] == 'm')) gp.m_major = 0;
   return HG_OK;
 }
 }  // namespace hg
