@@ -9,6 +9,11 @@ python tools/prof_iter.py > gpurun_out/prof_iter_plain.log 2>&1 || { echo "prof_
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launch_list_iteration.csv \
     python tools/prof_iter.py > gpurun_out/ncu_launch_list.log 2>&1
 python tools/launch_summary.py gpurun_out/launch_list_iteration.csv > gpurun_out/launch_list_iteration_summary.txt 2>&1
+# the same command the driver times, under the same single-metric pass (kernel SHARES of the step; absolutes are cold-cache)
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/bench_plain_steps2.json 2>/dev/null || { echo "bench failed without ncu"; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launch_list_bench_steps2.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch_list_bench.log 2>&1
+python tools/launch_summary.py gpurun_out/launch_list_bench_steps2.csv > gpurun_out/launch_list_bench_steps2_summary.txt 2>&1
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_kernel --launch-skip 183 -c 8 \
     -f -o gpurun_out/ncu_update_gemms python tools/prof_iter.py > gpurun_out/ncu_gemms.log 2>&1
 python tools/ncu_summary.py gpurun_out/ncu_update_gemms.ncu-rep > gpurun_out/ncu_update_gemms.txt 2>&1

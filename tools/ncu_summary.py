@@ -3,17 +3,23 @@ import csv, io, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, data = rows[0], rows[2:]
+hdr, units, data = rows[0], rows[1], rows[2:]
 def col(d, name):
     return d[hdr.index(name)] if name in hdr else "-"
+def mb(d, name):          # byte metrics come in varying units (Kbyte / Mbyte / Gbyte): always print MB
+    if name not in hdr:
+        return "-"
+    i = hdr.index(name)
+    scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(units[i], 1.0)
+    return "%.3f" % (float(d[i].replace(",", "")) * scale)
 for i, d in enumerate(data):
     print(i, col(d, "Kernel Name")[:44],
-          "us=%s" % col(d, "gpu__time_duration.sum")[:7],
+          "%s=%s" % (units[hdr.index("gpu__time_duration.sum")], col(d, "gpu__time_duration.sum")[:7]),
           "tensor%%=%s" % col(d, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")[:5],
           "inst=%s" % col(d, "smsp__inst_executed.sum")[:10],
           "lat/inst=%s" % col(d, "smsp__average_warp_latency_per_inst_issued.ratio")[:5],
           "warps%%=%s" % col(d, "sm__warps_active.avg.pct_of_peak_sustained_active")[:5],
-          "dramR=%s W=%s MB" % (col(d, "dram__bytes_read.sum")[:6], col(d, "dram__bytes_write.sum")[:6]),
+          "dramR=%s W=%s MB" % (mb(d, "dram__bytes_read.sum"), mb(d, "dram__bytes_write.sum")),
           "lts%%=%s" % col(d, "lts__throughput.avg.pct_of_peak_sustained_elapsed")[:5],
           "regs=%s" % col(d, "launch__registers_per_thread"))
 if len(sys.argv) > 2:

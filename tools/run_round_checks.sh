@@ -1,10 +1,11 @@
+#!/bin/bash
+# What the round-end driver runs, in one call on a GPU box: the -m gpu suite (one process per file), smoke(), the bench
+# (both arms), then the ncu evidence for profiles/ (tools/ncu_capture.sh).  Logs under gpurun_out/.
 set -x
 mkdir -p gpurun_out
-bash tools/gpu_suite.sh tests/test_gemm_gpu.py tests/test_learner_kernels_gpu.py tests/test_ppo_gpu.py > gpurun_out/suite.log 2>&1; echo "suite rc $?" >> gpurun_out/suite.log
-cat gpurun_out/suite.log | tail -5
-echo "== m-major"; HG_ITERS=8 timeout 300 python tools/phase_times.py 2>&1 | tail -1
-echo "== problem-major"; HG_TILE_ORDER=p HG_ITERS=8 timeout 300 python tools/phase_times.py 2>&1 | tail -1
-echo "== m-major"; HG_ITERS=8 timeout 300 python tools/phase_times.py 2>&1 | tail -1
-echo "== problem-major"; HG_TILE_ORDER=p HG_ITERS=8 timeout 300 python tools/phase_times.py 2>&1 | tail -1
-python bench.py --no-cpu-baseline --steps 20 > gpurun_out/bench_mmajor.json 2>/dev/null; python -c "
-import json; b=json.load(open('gpurun_out/bench_mmajor.json')); print(b['ms_per_step'], b['roofline']['by_kind'])"
+bash tools/gpu_suite.sh > gpurun_out/suite.log 2>&1; echo "suite rc $?" >> gpurun_out/suite.log
+cat gpurun_out/suite.log | tail -8
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc $?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>/dev/null; echo "reference rc $?"
+[ -n "$SKIP_NCU" ] || { bash tools/ncu_capture.sh > gpurun_out/ncu_capture.log 2>&1; tail -14 gpurun_out/ncu_capture.log; }
