@@ -413,7 +413,9 @@ class SyntheticXBotEnv:
                  callbacks: bool = False):
         """callbacks=True also runs `_post_physics_step_callback` (command resampling, heading command, pushes) and the
         command / extras["episode"] part of `reset_idx` every step: five launches per step instead of
-        one, commands and push buffers owned by the env instead of taken from the synthetic pool."""
+        one, commands and push buffers owned by the env instead of taken from the synthetic pool.  Works with
+        `bind_storage` like the fused path (the reward launch writes the transition record, the observation launch the
+        next storage slot)."""
         self.callbacks = callbacks
         self.cfg, self.device = cfg, torch.device(device)
         self.math = XBotEnvMath(cfg, device)
@@ -519,28 +521,25 @@ class SyntheticXBotEnv:
         noise = torch.randn(self.num_envs, self.cfg.num_single_obs, device=self.device) if (
             self.torch_rng_noise and self.cfg.add_noise) else None
         st = self._storage
+        kw = dict(raw_actions=actions)                  # clip(+-18) of step() (:633-635) fused in the kernel
+        if st is not None and st.step + 1 <= st.num_transitions_per_env:
+            o, p, o16, p16 = st.slot(st.step + 1)      # the env writes the learner's next storage slot (+ bf16 shadow) itself
+            kw.update(obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16)
+            if getattr(self, "_store_gamma", None) is not None:
+                t = st.step
+                kw["store"] = (st.values[t], st.rewards[t], st.dones[t], float(self._store_gamma))
+                st.env_stored = (t, self.math.rew_buf.data_ptr(), self.math.reset_buf.data_ptr(), float(self._store_gamma))
         if self.callbacks:
-            if st is not None:
-                raise _lib.HgError("callbacks=True runs the two-phase env step and cannot be bound to a RolloutStorage")
             if not hasattr(self, "_root_scratch"):
                 self._root_scratch = torch.empty_like(sim["root_states"])
             self._root_scratch.copy_(sim["root_states"])           # a push overwrites root velocities in place
             sim = dict(sim, root_states=self._root_scratch)
             ur = (lambda *sh: torch.rand(*sh, device=self.device)) if self.torch_rng_noise else (lambda *sh: None)
             *out, episode = self.math.step_with_callbacks(sim, noise, u_cmd=ur(self.num_envs, 3), u_push=ur(self.num_envs, 5),
-                                                          u_cmd_reset=ur(self.num_envs, 3), raw_actions=actions)
+                                                          u_cmd_reset=ur(self.num_envs, 3), **kw)
             self.extras["episode"] = episode
-        elif st is not None and st.step + 1 <= st.num_transitions_per_env:
-            o, p, o16, p16 = st.slot(st.step + 1)
-            store = None
-            if getattr(self, "_store_gamma", None) is not None:
-                t = st.step
-                store = (st.values[t], st.rewards[t], st.dones[t], float(self._store_gamma))
-                st.env_stored = (t, self.math.rew_buf.data_ptr(), self.math.reset_buf.data_ptr(), float(self._store_gamma))
-            out = self.math.step(sim, noise, obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16, raw_actions=actions,
-                                 store=store)
         else:
-            out = self.math.step(sim, noise, raw_actions=actions)   # clip(+-18) of step() (:633-635) fused in the kernel
+            out = self.math.step(sim, noise, **kw)
         if slot is not None and slot[1] == self._chunk - 1:     # last step of a chunk: hand its staging chunk back
             self._consumed[slot[0]].record(torch.cuda.current_stream())
             self._prefetch_upto((self._i - self._i0) // self._chunk + self._chunks)

@@ -242,17 +242,22 @@ def test_runner_style_loop_and_api_surface():
     assert torch.equal(batches[5][0], alg.storage.observations.flatten(0, 1)[perm[N * T // 4: N * T // 2]])
 
 
-def test_bound_env_writes_storage_slots_identically():
+@pytest.mark.parametrize("callbacks", [False, True])
+def test_bound_env_writes_storage_slots_identically(callbacks):
     """`SyntheticXBotEnv.bind_storage`: the env kernel writes obs (fp32 + bf16 shadow) straight into the next storage
     slot.  Must be bit-identical to the generic path (env buffer -> ingest kernel) for a whole rollout, including the
     carry-over of the last observation into the next iteration (slot T -> slot 0).  (After an update the two runs may
-    differ in the last bits: gradient sums use fp32 atomics.)"""
+    differ in the last bits: gradient sums use fp32 atomics.)  callbacks=True: the same through the two-phase env step
+    with command resampling, pushes and reset extras."""
     from humanoid_gym_with_comments_b200 import _lib
     N, T = 256, 6
     outs, launches = [], []
     for bound in (0, 1, 2):           # generic path | obs written into the slots | + transition record stored by the env kernel
         torch.manual_seed(7)
-        env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), DEV, seed=3)
+        env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), DEV, seed=3, callbacks=callbacks)
+        if callbacks:
+            env.math._callback_state()
+            env.math.common_step_counter = 396          # a push within the first rollout
         alg, cfg = make_alg(N, T)
         if bound:
             env.bind_storage(alg.storage, gamma=cfg.gamma if bound == 2 else None)
