@@ -266,6 +266,7 @@ class XBotEnvMath:
         self.step(sim, noise, phases=ENV_PHASE_REWARD, root_vel_prepush=pre, **kw)
         episode = self.reset_bookkeeping(u_cmd_reset)
         sim.pop("actions", None)                       # already copied into self.actions by the first launch
+        kw.pop("store", None)                          # the transition record belongs to the reward launch
         out = self.step(sim, noise, phases=ENV_PHASE_OBS, root_vel_prepush=pre, **kw)
         return (*out, episode)
 
