@@ -452,10 +452,28 @@ def run_ours(a):
 
 def main():
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    # stdout carries exactly ONE line, the JSON: anything a library prints there meanwhile (NCCL's version banner comes from
+    # C code on rank 0) is sent to stderr by pointing fd 1 at fd 2 until the line is written to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if a.impl == "reference":
+                run_reference(a)
+            else:
+                run_ours(a)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+        other = [l for l in buf.getvalue().splitlines() if l and not l.startswith("{")]
+        if other:
+            print("\n".join(other), file=sys.stderr)
+        if lines:
+            os.write(real_stdout, (lines[-1] + "\n").encode())
+        os.close(real_stdout)
 
 
 if __name__ == "__main__":
