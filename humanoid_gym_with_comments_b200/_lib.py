@@ -194,6 +194,8 @@ _SIGNATURES = {
     "hg_gemm_plan_destroy": (None, [C.c_void_p]),
     "hg_gemm_plan_create_heads": (C.c_int, [C.POINTER(HgGemmProblem), C.POINTER(HgFusedHead), C.c_int, C.POINTER(C.c_void_p)]),
     "hg_gemm_plan_run_heads": (C.c_int, [C.c_void_p, _P, C.c_uint64, C.c_uint64, _P]),
+    "hg_gemm_plan_create_tail": (C.c_int, [C.POINTER(HgGemmProblem), C.POINTER(HgGemmProblem), C.POINTER(HgFusedHead), C.c_int,
+                                           C.POINTER(C.c_void_p)]),
     "hg_gae_returns": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
     "hg_ingest_rows": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, C.c_int64, _P, C.c_int64, _P]),
     "hg_gather_rows_bf16": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P]),
@@ -229,7 +231,7 @@ def load(auto_build: bool = True) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.hg_abi_version() != 4:
+    if lib.hg_abi_version() != 5:
         raise HgError("libhgb200.so ABI mismatch")
     _lib = lib
     return lib

@@ -197,6 +197,35 @@ class MLPEngine:
         return (len(depth) == 1 and all(n.hidden[-1] <= 128 and n.hidden[-1] % 32 == 0 for n in nets)
                 and all(1 <= o <= 16 for o in n_outs))
 
+    @staticmethod
+    def can_fuse_tail(nets: Sequence[NetSpec]) -> bool:
+        """Layer 2 + layer 3 + head in one launch (`hg_gemm_plan_create_tail`): one or two nets with three hidden layers,
+        second width a multiple of 64 up to 256, third a multiple of 32 up to 128.  HG_ROLLOUT_TAIL=0 keeps two launches."""
+        if os.environ.get("HG_ROLLOUT_TAIL", "1") == "0" or not 1 <= len(nets) <= 2:
+            return False
+        return all(n.num_hidden == 3 and 64 <= n.hidden[1] <= 256 and n.hidden[1] % 64 == 0
+                   and 32 <= n.hidden[2] <= 128 and n.hidden[2] % 32 == 0 for n in nets)
+
+    def _tail_plan(self, nets: Sequence[NetSpec], ws: "Workspace", rows: int, heads) -> int:
+        l2, l3, hs = [], [], []
+        for net in nets:
+            h1 = ws.h[net.name][0]
+            lin2, lin3 = net.linears[1], net.linears[2]
+            w2, w3 = self.flat.w16[id(lin2.weight)], self.flat.w16[id(lin3.weight)]
+            l2.append(HgGemmProblem(A=ptr(h1), B=ptr(w2), lda=h1.stride(0), ldb=w2.stride(0), a_mn_major=0, b_mn_major=0,
+                                    M=rows, N=lin2.out_features, K=net.hidden[0], k_splits=1, out=0, ldo=0,
+                                    bias=ptr(lin2.bias.data), act=0, ldact=0, colsum=0))
+            l3.append(HgGemmProblem(A=0, B=ptr(w3), lda=0, ldb=w3.stride(0), a_mn_major=0, b_mn_major=0,
+                                    M=rows, N=lin3.out_features, K=net.hidden[1], k_splits=1, out=0, ldo=0,
+                                    bias=ptr(lin3.bias.data), act=0, ldact=0, colsum=0))
+            hs.append(heads[net.name])
+        a2, a3 = (HgGemmProblem * len(l2))(*l2), (HgGemmProblem * len(l3))(*l3)
+        harr = (_lib.HgFusedHead * len(hs))(*hs)
+        handle = C.c_void_p()
+        check(self.lib.hg_gemm_plan_create_tail(a2, a3, harr, len(l2), C.byref(handle)))
+        self._all_plans.append(handle.value)
+        return handle.value
+
     def run_head_plan(self, plan: int, eps, seed: int, counter: int) -> None:
         check(self.lib.hg_gemm_plan_run_heads(plan, ptr(eps), seed, counter, current_stream()))
 
@@ -224,7 +253,11 @@ class MLPEngine:
         output layer + sampling, `run_head_plan`); its activations are not written to ws.h."""
         plans = []
         depth = max(n.num_hidden for n in nets)
+        fuse_tail = (make_plans and heads is not None and self.can_fuse_tail(nets))
         for l in range(depth):
+            if fuse_tail and l == depth - 2:
+                plans.append(self._tail_plan(nets, ws, rows, heads))     # layers depth-1, depth and the heads: one launch
+                break
             probs, ns = [], []
             for net in nets:
                 if l >= net.num_hidden:

@@ -799,6 +799,283 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ rollout tail
+// Layer 2, layer 3 and the output layer of a net in ONE launch (rollout, three hidden layers): a CTA owns a 128-row
+// tile of one net, computes h2 = elu(h1 W2^T + b2) (128 x N2 <= 256, accumulator in TMEM columns 0..255), parks it as
+// bf16 in shared memory in the canonical K-major SWIZZLE_128B layout (exactly what a TMA load of an activation tile would
+// have produced), multiplies it by W3 (accumulator in TMEM columns 256..383) and finishes with the fused head of
+// HG_EPI_BIAS_ELU_HEAD.  h2 never travels through L2 and the step has one launch (ramp-up, prologue, drain) less.
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-19: the two epilogues
+namespace tail {
+#ifndef HG_TAIL_STAGES
+#define HG_TAIL_STAGES 3
+#endif
+constexpr int STAGES = HG_TAIL_STAGES;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;            // 16 KB: h1 tile 128 x 64
+constexpr int B_BYTES = 256 * BLOCK_K * 2;                // 32 KB: W2 tile 256 x 64
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int KB_BYTES = BLOCK_M * BLOCK_K * 2;           // 16 KB: one 64-wide k-block of h2 (128 rows) / of W3 (<= 128 rows)
+constexpr int H2_OFF = STAGES * STAGE_BYTES;              // 144 KB
+constexpr int BAR_OFF = H2_OFF + 4 * KB_BYTES;            // h2: 64 KB; the head's partial sums reuse it once layer 3 has read it
+constexpr int HEAD_OFF = BAR_OFF + 256;
+constexpr int HEAD_BYTES = (16 * 128 + 64) * 4;           // output weights [16][128] + bias / std
+constexpr int SMEM_TOTAL = HEAD_OFF + HEAD_BYTES + 1024;
+static_assert(4 * 128 * 17 * 4 <= 4 * KB_BYTES, "partial sums fit in the h2 tile");
+constexpr int THREADS = 128 + 32 * 16;
+constexpr int TMEM_COLS = 512;
+static_assert(SMEM_TOTAL <= 227 * 1024, "rollout tail: shared memory");
+}  // namespace tail
+
+struct TailNet {
+  CUtensorMap tma_h1, tma_w2, tma_w3;
+  int M, K1, N2, N3;
+  const float* b2;
+  const float* b3;
+  HgFusedHead head;
+};
+struct alignas(64) TailParams {
+  TailNet net[2];
+  int num_nets, tiles_m;
+  const float* eps;
+  unsigned long long seed, counter;
+};
+
+__global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __grid_constant__ TailParams P) {
+  using namespace tail;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* full_bar = bars;            // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;  // [STAGES]
+  uint64_t* acc1_full = bars + 2 * STAGES;       // layer-2 accumulator complete (MMA -> epilogue, producer)
+  uint64_t* h2_ready = bars + 2 * STAGES + 1;    // h2 tile written to shared memory (16 epilogue warps -> MMA)
+  uint64_t* w3_full = bars + 2 * STAGES + 2;     // W3 landed in the (idle) operand ring
+  uint64_t* acc2_full = bars + 2 * STAGES + 3;   // layer-3 accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* sm = reinterpret_cast<float*>(smem + HEAD_OFF);
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x / P.tiles_m, m_blk = blockIdx.x - g * P.tiles_m;
+  const TailNet& q = P.net[g];
+  const int num_kb1 = (q.K1 + BLOCK_K - 1) / BLOCK_K, num_kb2 = q.N2 / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&q.tma_h1);
+    tma_prefetch_desc(&q.tma_w2);
+    tma_prefetch_desc(&q.tma_w3);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(acc1_full), 1);
+    mbar_init(smem_u32(h2_ready), 16);
+    mbar_init(smem_u32(w3_full), 1);
+    mbar_init(smem_u32(acc2_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  pdl_wait();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t ring = smem_u32(smem), h2s = smem_u32(smem + H2_OFF);
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb1; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_arrive_expect_tx(fb, STAGE_BYTES);
+        tma_load_2d(ring + stage * STAGE_BYTES, &q.tma_h1, fb, kb * BLOCK_K, m_blk * BLOCK_M);
+        tma_load_2d(ring + stage * STAGE_BYTES + A_BYTES, &q.tma_w2, fb, kb * BLOCK_K, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      // W3 goes into the operand ring once every layer-2 MMA has retired (the ring is idle from then on)
+      mbar_wait(smem_u32(acc1_full), 0);
+      mbar_arrive_expect_tx(smem_u32(w3_full), num_kb2 * KB_BYTES);
+      for (int kb = 0; kb < num_kb2; ++kb) tma_load_2d(ring + kb * KB_BYTES, &q.tma_w3, smem_u32(w3_full), kb * BLOCK_K, 0);
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t desc_hi = (uint32_t)(desc_base() >> 32);
+      const uint32_t step = (UMMA_K * 2) >> 4;      // K-major operands: 32 bytes per 16-wide K slice
+      const int n2_mma = (q.N2 + 31) & ~31, n3_mma = (q.N3 + 31) & ~31;
+      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n2_mma >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+      const uint32_t idesc3 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n3_mma >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, accumulate = 0;
+      for (int kb = 0; kb < num_kb1; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t sa = ring + stage * STAGE_BYTES;
+        const uint32_t a_lo = (1u << 16) | ((sa & 0x3FFFFu) >> 4), b_lo = (1u << 16) | (((sa + A_BYTES) & 0x3FFFFu) >> 4);
+        const int k_left = q.K1 - kb * BLOCK_K;
+        const int nk = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
+        for (int k = 0; k < nk; ++k) {
+          umma_bf16(tmem_base, (uint64_t(desc_hi) << 32) | (a_lo + k * step), (uint64_t(desc_hi) << 32) | (b_lo + k * step),
+                    idesc2, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(smem_u32(acc1_full));
+      // layer 3: A = the h2 tile the epilogue warps wrote to shared memory, B = W3 in the ring
+      mbar_wait(smem_u32(w3_full), 0);
+      mbar_wait(smem_u32(h2_ready), 0);
+      tc_fence_after();
+      accumulate = 0;
+      for (int kb = 0; kb < num_kb2; ++kb) {
+        const uint32_t a_lo = (1u << 16) | (((h2s + kb * KB_BYTES) & 0x3FFFFu) >> 4);
+        const uint32_t b_lo = (1u << 16) | (((ring + kb * KB_BYTES) & 0x3FFFFu) >> 4);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          umma_bf16(tmem_base + 256, (uint64_t(desc_hi) << 32) | (a_lo + k * step), (uint64_t(desc_hi) << 32) | (b_lo + k * step),
+                    idesc3, accumulate);
+          accumulate = 1;
+        }
+      }
+      umma_commit(smem_u32(acc2_full));
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogues: warps 4..19
+    const int quad = warp & 3, slice = (warp - 4) >> 2;
+    const int et = (warp - 4) * 32 + lane;         // 0..511
+    const int rt = quad * 32 + lane;               // row inside the tile
+    const HgFusedHead& hd = q.head;
+    const int n_out = hd.n_out;
+    float* sW = sm;                    // [16][128]
+    float* sB = sm + 16 * 128;         // [16] output bias, [16] std
+    float* sAcc = reinterpret_cast<float*>(smem + H2_OFF);   // [4][128][17], over the h2 tile (dead once acc2_full fires)
+    // output-layer weights -> shared memory while the main loops run
+    for (int i = et; i < n_out * q.N3; i += 512) {
+      const int a = i / q.N3, k = i - a * q.N3;
+      sW[a * 128 + k] = __ldg(hd.W + i);
+    }
+    if (et < n_out) {
+      sB[et] = __ldg(hd.b + et);
+      sB[16 + et] = hd.kind == HG_HEAD_POLICY ? __ldg(hd.std + et) : 0.f;
+    }
+    // ---- epilogue 1: h2 = bf16(elu(acc + b2)) -> shared memory, K-major SWIZZLE_128B (16-byte chunk index XOR row % 8)
+    mbar_wait(smem_u32(acc1_full), 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int n0 = slice * 64 + c * 32;
+      if (n0 < q.N2) {                                     // N2 % 64 == 0: a live chunk is a full chunk
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + n0, v);
+        tmem_ld_wait();
+        const uint32_t row_addr = h2s + (n0 >> 6) * KB_BYTES + (rt >> 3) * 1024 + (rt & 7) * 128;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          float z[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float t = __uint_as_float(v[p * 8 + j]) + __ldg(q.b2 + n0 + p * 8 + j);
+            z[j] = t > 0.f ? t : exp2f_fast(t * 1.4426950408889634f) - 1.f;
+          }
+          const uint4 w = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
+          const int chunk = ((n0 & 63) >> 3) + p;          // 16-byte chunk of the row's 128-byte k-block line
+          sts128(row_addr + ((chunk ^ (rt & 7)) << 4), w);
+        }
+      }
+    }
+    tc_fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(h2_ready));
+    epi_bar_sync();                                                 // sW / sB staged by every epilogue thread
+
+    // ---- epilogue 2: fused head on the layer-3 accumulator (same math as head_epilogue)
+    mbar_wait(smem_u32(acc2_full), 0);
+    tc_fence_after();
+    const int n0 = slice * 32;
+    const bool live = n0 < q.N3;                  // N3 % 32 == 0
+    if (live) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + 256 + n0, v);
+      tmem_ld_wait();
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(v[j]) + (q.b3 ? __ldg(q.b3 + n0 + j) : 0.f);
+        const float e = x > 0.f ? x : exp2f_fast(x * 1.4426950408889634f) - 1.f;
+        z[j] = __bfloat162float(__float2bfloat16_rn(e));     // what the stored activation would hold
+      }
+      for (int a = 0; a < n_out; ++a) {
+        const float4* w4 = reinterpret_cast<const float4*>(sW + a * 128 + n0);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 wa = w4[j >> 2], wb = w4[(j >> 2) + 1];
+          s0 += z[j] * wa.x + z[j + 1] * wa.y + z[j + 2] * wa.z + z[j + 3] * wa.w;
+          s1 += z[j + 4] * wb.x + z[j + 5] * wb.y + z[j + 6] * wb.z + z[j + 7] * wb.w;
+        }
+        sAcc[(slice * 128 + rt) * 17 + a] = s0 + s1;
+      }
+    } else {
+      for (int a = 0; a < n_out; ++a) sAcc[(slice * 128 + rt) * 17 + a] = 0.f;
+    }
+    tc_fence_before();
+    epi_bar_sync();
+    const int row = m_blk * BLOCK_M + rt;
+    auto dot = [&](int a) {
+      return ((sAcc[rt * 17 + a] + sAcc[(128 + rt) * 17 + a]) + sAcc[(256 + rt) * 17 + a]) + sAcc[(384 + rt) * 17 + a];
+    };
+    const int per = (n_out + 3) >> 2, a_lo = slice * per, a_hi = min(n_out, a_lo + per);
+    float lp = 0.f;
+    if (row < q.M) {
+      if (hd.kind == HG_HEAD_POLICY) {
+        int have = -1;
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int a = a_lo; a < a_hi; ++a) {
+          if (P.eps == nullptr && (a >> 2) != have) {      // four normals per Philox call, keyed by (row, a / 4)
+            have = a >> 2;
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)have, (uint32_t)P.counter, (uint32_t)(P.counter >> 32)),
+                                          make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+            const float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
+            e[0] = n01.x; e[1] = n01.y; e[2] = n23.x; e[3] = n23.y;
+          }
+          const int k = a & 3;
+          const float m = dot(a) + sB[a], sd = sB[16 + a];
+          const float ee = P.eps ? __ldg(P.eps + (long long)row * n_out + a) : (k == 0 ? e[0] : k == 1 ? e[1] : k == 2 ? e[2] : e[3]);
+          const float act = m + sd * ee;
+          const float d = act - m;
+          lp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;
+          hd.actions[(long long)row * n_out + a] = act;
+          hd.out[(long long)row * n_out + a] = m;
+          hd.sigma[(long long)row * n_out + a] = sd;
+        }
+      } else {
+        for (int a = a_lo; a < a_hi; ++a) hd.out[(long long)row * n_out + a] = dot(a) + sB[a];
+      }
+    }
+    if (hd.kind == HG_HEAD_POLICY) {
+      epi_bar_sync();
+      sAcc[slice * 128 + rt] = lp;
+      epi_bar_sync();
+      if (slice == 0 && row < q.M) hd.log_prob[row] = ((sAcc[rt] + sAcc[128 + rt]) + sAcc[256 + rt]) + sAcc[384 + rt];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<tail::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -940,6 +1217,8 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
 struct HgGemmPlan {
   hg::GroupParams gp;
   int epilogue, block_n, cta_group;
+  bool tail = false;          // hg_gemm_plan_create_tail: layer 2 + layer 3 + head in one launch
+  hg::TailParams tp;
 };
 
 extern "C" int hg_gemm_grouped(const HgGemmProblem* pr, int n, int epilogue, int block_n, int cta_group, void* stream) {
@@ -1004,9 +1283,68 @@ extern "C" int hg_gemm_plan_create_heads(const HgGemmProblem* pr, const HgFusedH
   return HG_OK;
 }
 
+extern "C" int hg_gemm_plan_create_tail(const HgGemmProblem* l2, const HgGemmProblem* l3, const HgFusedHead* heads, int n,
+                                        HgGemmPlan** out) {
+  using namespace hg;
+  HG_CHECK(out && l2 && l3 && heads && n >= 1 && n <= 2, "hg_gemm_plan_create_tail: 1 or 2 nets, non-null arguments");
+  HgGemmPlan* plan = new HgGemmPlan();
+  plan->tail = true;
+  plan->epilogue = HG_EPI_BIAS_ELU_HEAD;
+  plan->block_n = 128;
+  plan->cta_group = 1;
+  TailParams& tp = plan->tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.num_nets = n;
+  int rc = HG_OK;
+  for (int g = 0; g < n && rc == HG_OK; ++g) {
+    const HgGemmProblem& a = l2[g];
+    const HgGemmProblem& b = l3[g];
+    const HgFusedHead& h = heads[g];
+    const bool ok = a.A && a.B && b.B && a.bias && a.M > 0 && a.K > 0 && !a.a_mn_major && !a.b_mn_major && !b.b_mn_major &&
+                    a.N >= 64 && a.N <= 256 && a.N % 64 == 0 && b.K == a.N && b.N >= 32 && b.N <= 128 && b.N % 32 == 0 &&
+                    a.M == l2[0].M && (h.kind == HG_HEAD_POLICY || h.kind == HG_HEAD_LINEAR) && h.n_out >= 1 && h.n_out <= 16 &&
+                    h.W && h.b && h.out && (h.kind != HG_HEAD_POLICY || (h.std && h.actions && h.sigma && h.log_prob));
+    if (!ok) {
+      set_error("hg_gemm_plan_create_tail: net %d: needs K-major operands, 64 <= N2 <= 256 (multiple of 64), K3 == N2, "
+                "32 <= N3 <= 128 (multiple of 32), equal M, a valid head", g);
+      rc = HG_ERR_INVALID;
+      break;
+    }
+    TailNet& q = tp.net[g];
+    q.M = a.M; q.K1 = a.K; q.N2 = a.N; q.N3 = b.N;
+    q.b2 = a.bias; q.b3 = b.bias; q.head = h;
+    rc = make_tmap(&q.tma_h1, a.A, a.K, a.M, a.lda, BLOCK_M);
+    if (rc == HG_OK) rc = make_tmap(&q.tma_w2, a.B, a.K, a.N, a.ldb, 256);
+    if (rc == HG_OK) rc = make_tmap(&q.tma_w3, b.B, b.K, b.N, b.ldb, 128);
+  }
+  if (rc != HG_OK) {
+    delete plan;
+    return rc;
+  }
+  tp.tiles_m = (l2[0].M + BLOCK_M - 1) / BLOCK_M;
+  *out = plan;
+  return HG_OK;
+}
+
 extern "C" int hg_gemm_plan_run_heads(const HgGemmPlan* plan, const float* eps, uint64_t seed, uint64_t counter, void* stream) {
   using namespace hg;
   HG_CHECK(plan != nullptr && plan->epilogue == HG_EPI_BIAS_ELU_HEAD, "hg_gemm_plan_run_heads: not a fused-head plan");
+  if (plan->tail) {
+    static bool configured = false;
+    if (!configured) {
+      HG_CUDA(cudaFuncSetAttribute(rollout_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail::SMEM_TOTAL));
+      configured = true;
+    }
+    TailParams tp = plan->tp;
+    tp.eps = eps;
+    tp.seed = seed;
+    tp.counter = counter;
+    HG_CUDA(launch_kernel(rollout_tail_kernel, dim3(tp.num_nets * tp.tiles_m), dim3(tail::THREADS), tail::SMEM_TOTAL,
+                          reinterpret_cast<cudaStream_t>(stream), 1, tp));
+    HG_LAUNCH_CHECK();
+    count_launch();
+    return HG_OK;
+  }
   GroupParams gp = plan->gp;
   gp.eps = eps;
   gp.seed = seed;

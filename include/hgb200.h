@@ -21,7 +21,7 @@ extern "C" {
 #define HG_ERR_INVALID (-1)
 #define HG_ERR_CUDA (-2)
 
-#define HG_ABI_VERSION 4
+#define HG_ABI_VERSION 5
 
 const char* hg_last_error(void);
 int hg_abi_version(void);
@@ -103,6 +103,15 @@ typedef struct HgFusedHead {
 int hg_gemm_plan_create_heads(const HgGemmProblem* problems_host, const HgFusedHead* heads_host, int num_problems,
                               HgGemmPlan** out);
 int hg_gemm_plan_run_heads(const HgGemmPlan* plan, const float* eps, uint64_t seed, uint64_t counter, void* stream);
+
+/* Rollout, nets with three hidden layers: layer 2, layer 3 and the output layer of up to two nets (actor, critic) in ONE
+ * launch -- what hg_gemm_plan_create (layer 2) + hg_gemm_plan_create_heads (layer 3 + head) do in two.  A CTA keeps its
+ * 128-row tile of h2 = elu(h1 W2^T + b2) in shared memory as the bf16 K-major operand of layer 3, so h2 is never stored.
+ *   layer2[g]: A = h1 [M,K1] bf16, B = W2 [N2,K1] bf16, bias = b2, M, N = N2 (64..256, multiple of 64), K = K1
+ *   layer3[g]: B = W3 [N3,N2] bf16, bias = b3, N = N3 (32..128, multiple of 32), K = N2      (A, M, out unused)
+ * Run it with hg_gemm_plan_run_heads; results are bit-identical to the two-launch path. */
+int hg_gemm_plan_create_tail(const HgGemmProblem* layer2_host, const HgGemmProblem* layer3_host, const HgFusedHead* heads_host,
+                             int num_nets, HgGemmPlan** out);
 
 /* ------------------------------------------------------------------------------------------
  * GAE: replaces RolloutStorage.compute_returns (humanoid/algo/ppo/rollout_storage.py:122-143).

@@ -362,3 +362,35 @@ def test_fused_rollout_head_matches_separate_head_kernel(N):
     a, mu, sigma, _, _ = outs[(True, "eps")]
     assert torch.allclose(a, mu + sigma * eps, atol=1e-6)
     assert float((outs[(True, "philox")][0] - outs[(True, "eps")][0]).abs().max()) > 0.1      # a different stream indeed
+
+
+@pytest.mark.parametrize("N", [200, 4096])
+def test_rollout_tail_launch_is_bit_identical_to_two_launches(N, monkeypatch):
+    """Layer 2 + layer 3 + heads in ONE launch (`hg_gemm_plan_create_tail`: h2 stays in shared memory as the K-major
+    bf16 operand of layer 3) against layer 2 and layer 3 + heads as two launches: same MMA shapes per output element,
+    same epilogue math -> every stored number must be identical, for external eps and for the Philox stream."""
+    g = torch.Generator(device=DEV).manual_seed(9)
+    obs = torch.randn(N, 705, device=DEV, generator=g)
+    priv = torch.randn(N, 219, device=DEV, generator=g)
+    eps = torch.randn(N, 12, device=DEV, generator=g)
+    outs = {}
+    for tail in ("1", "0"):
+        monkeypatch.setenv("HG_ROLLOUT_TAIL", tail)
+        for mode in ("eps", "philox"):
+            alg, _ = make_alg(N, 2, seed=3)
+            with torch.no_grad():
+                alg.actor_critic.std.fill_(0.7)
+            alg.torch_rng = False
+            alg.eps_override = (lambda t: eps) if mode == "eps" else None
+            alg._seed = 99
+            with torch.inference_mode():
+                a = alg.act(obs, priv).clone()
+            plans = alg._slot_plan(0)[0]
+            assert isinstance(plans, tuple) and len(plans[0]) == (1 if tail == "1" else 2)      # launches in front of the head launch
+            st = alg.storage
+            outs[(tail, mode)] = (a, st.mu[0].clone(), st.sigma[0].clone(), st.actions_log_prob[0].clone(), st.values[0].clone())
+    torch.cuda.synchronize()
+    for mode in ("eps", "philox"):
+        for name, x, y in zip(("actions", "mu", "sigma", "log_prob", "values"), outs[("1", mode)], outs[("0", mode)]):
+            assert torch.isfinite(x).all(), (mode, name)
+            assert torch.equal(x, y), (mode, name, float((x - y).abs().max()))
