@@ -2,11 +2,13 @@
 every tensor operation on sm_100a kernels and no host synchronisation inside rollout or update (one device->host
 read of the loss log at the end of `update()`).
 
-Per rollout step (`act` + `process_env_step`, ppo.py:116-138): 2 ingest launches, one grouped tcgen05 GEMM launch per
-hidden depth (actor + critic together), 1 fused head launch (output layers, Gaussian sample, log-prob, value, written
-straight into the storage slot), 1 reward/done launch.
+Per rollout step (`act` + `process_env_step`, ppo.py:116-138), generic path: 2 ingest launches, one grouped tcgen05 GEMM
+launch per hidden depth (actor + critic together), 1 fused head launch (output layers, Gaussian sample, log-prob, value,
+written straight into the storage slot), 1 reward/done launch.  With a bound env (`SyntheticXBotEnv.bind_storage`) and
+three-hidden-layer nets: the layer-1 launch + ONE launch for layer 2, layer 3, output layers and sampling; ingest and
+reward/done bookkeeping are done by the env kernel.
 Per minibatch (`update`, ppo.py:150-218): grouped forward GEMMs, 1 fused head+loss+head-backward launch, grouped
-dW / dX GEMMs, optional NCCL all-reduce of the flat gradient arena (+KL slot), 3 optimiser launches.
+dW / dX GEMMs, optional NCCL all-reduce of the flat gradient arena (+KL slot), 2 optimiser launches.
 """
 from __future__ import annotations
 

@@ -27,6 +27,6 @@ for i, d in enumerate(data):
                 "registers": int(val(d, "launch__registers_per_thread"))})
 r, w = sum(o["dram_read_bytes"] for o in out), sum(o["dram_write_bytes"] for o in out)
 print(json.dumps({"source": "ncu --set full --clock-control none, one minibatch (61,440 rows) of PPO.update at 4096 envs x 60: "
-                            "tools/ncu_capture.sh (tools/prof_iter.py, -k regex:gemm_kernel --launch-skip 183 -c 8; cold-cache, serialised replays)",
+                            "tools/ncu_capture.sh (tools/prof_iter.py, -k regex:gemm_kernel --launch-skip 63 -c 8; cold-cache, serialised replays)",
                   "launches": out, "traffic_bytes_per_launch": (r + w) / len(out), "dram_read_bytes_total": r,
                   "dram_write_bytes_total": w}, indent=1))
