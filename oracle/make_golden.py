@@ -162,6 +162,76 @@ def learner_case(N, T, seed, n_updates, store_inputs):
     return out, report
 
 
+def sym_case(N=16, T=8, seed=2):
+    """one `PPO.update()` of the reference WITH the mirror-symmetry loss (ppo.py:93-105,197-202) against
+    the oracle.  The reference builds its permutation matrices with `.cuda()` (ppo.py:96,103); in this CPU-only container
+    `Tensor.cuda` is replaced by the identity while the object is constructed -- nothing else is touched."""
+    import dataclasses
+    PPO, ActorCritic, _ = rh.load_learner()
+    obs_perm, act_perm = po.xbot_mirror_permutations()
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ac = ActorCritic(705, 219, 12, init_noise_std=1.0, **XBOT_NETS)
+    c = dataclasses.replace(po.xbot_ppo_config(), sym_loss=True, sym_coef=0.5, obs_permutation=obs_perm, act_permutation=act_perm,
+                            frame_stack=15)
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        alg = PPO(ac, num_learning_epochs=c.num_learning_epochs, num_mini_batches=c.num_mini_batches, clip_param=c.clip_param,
+                  gamma=c.gamma, lam=c.lam, value_loss_coef=c.value_loss_coef, entropy_coef=c.entropy_coef,
+                  learning_rate=c.learning_rate, max_grad_norm=c.max_grad_norm, use_clipped_value_loss=c.use_clipped_value_loss,
+                  schedule=c.schedule, desired_kl=c.desired_kl, device="cpu", sym_loss=True, obs_permutation=obs_perm,
+                  act_permutation=act_perm, frame_stack=15, sym_coef=c.sym_coef)
+    finally:
+        torch.Tensor.cuda = real_cuda
+    alg.init_storage(N, T, [705], [219], [12])
+    assert torch.equal(alg.obs_perm_mat, po.perm_matrix(po.stacked_obs_permutation(obs_perm, 15)))
+    assert torch.equal(alg.act_perm_mat, po.perm_matrix(act_perm))
+    assert float(alg.obs_perm_mat.abs().sum()) == 705 and float(alg.act_perm_mat.abs().sum()) == 12      # signed permutations
+    p = _oracle_params(seed)
+    gen = torch.Generator().manual_seed(77)
+    ro, last_c, inputs = po.synthetic_rollout(p, N, T, 705, 219, 12, c, gen, record_inputs=True)
+    with torch.inference_mode():
+        for t in range(T):
+            real_normal, eps = torch.normal, inputs[t]["eps"]
+            torch.normal = lambda mean, std, *a, **k: mean + std * eps
+            try:
+                alg.act(ro.observations[t], ro.privileged_observations[t])
+            finally:
+                torch.normal = real_normal
+            alg.process_env_step(inputs[t]["rew"], inputs[t]["dones"], {"time_outs": inputs[t]["time_outs"]})
+        alg.compute_returns(last_c)
+    torch.manual_seed(99)
+    perm = torch.randperm(N * T)
+    torch.manual_seed(99)
+    ref = alg.update()
+    rec = []
+    st = po.AdamState()
+    o = po.ppo_update(p, st, ro, perm, c, c.learning_rate, record=rec)
+    ref_sym = float(ref[2])                       # the LAST minibatch's symmetry loss (ppo.py:226 returns the tensor as is)
+    report = {"value.rel": abs(ref[0] - o[0]) / abs(ref[0]), "surrogate.abs": abs(ref[1] - o[1]), "lin_vel.rel": abs(ref[3] - o[2]) / abs(ref[3]),
+              "sym.rel": abs(ref_sym - rec[-1]["sym"]) / abs(ref_sym), "sym": ref_sym}
+    assert report["value.rel"] < 2e-5 and report["surrogate.abs"] < 2e-6 and report["lin_vel.rel"] < 2e-5 and report["sym.rel"] < 2e-5, report
+    assert ref_sym > 1e-3                          # the term is live
+    assert abs(alg.learning_rate - o[3]) < 1e-12
+    sd = alg.actor_critic.state_dict()
+    worst = max((sd[k] - p[k]).abs().max().item() for k in sd)
+    assert worst <= 2.5 * o[3], worst
+    report["param.maxabs"] = worst
+    out = dict(N=N, T=T, seed=seed, obs_permutation=np.array(obs_perm), act_permutation=np.array(act_perm), sym_coef=np.array(c.sym_coef),
+               perm=_np(perm).astype(np.int64), ref_losses=np.array([ref[0], ref[1], ref_sym, ref[3]], dtype=np.float64),
+               ref_lr=np.array(alg.learning_rate),
+               oracle_minibatch_log=np.array([[r["value"], r["surrogate"], r["lin_vel"], r["entropy"], r["kl"], r["lr"], r["grad_norm"], r["sym"]] for r in rec]))
+    for name in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "actions_log_prob", "mu", "sigma",
+                 "returns", "advantages"):
+        out[name] = _np(getattr(ro, name))
+    for k in sd:
+        pr, sm = _probe(sd[k])
+        out["param_probe." + k] = pr
+        out["param_sums." + k] = sm
+    return out, report
+
+
 def env_case(D, N=16, steps=20, seed=3):
     spec = eo.xbot_spec(D)
     g = torch.Generator().manual_seed(seed)
@@ -391,6 +461,8 @@ def main():
     save("pre_physics_d12.npz", d, rep)
     d, rep = callback_case()
     save("env_callback_d12.npz", d, rep)
+    d, rep = sym_case()
+    save("learner_sym_small.npz", d, rep)
     d, rep = onnx_probe()
     save("onnx_actor_probe.npz", d, rep)
     json.dump(manifest, open(os.path.join(GOLD, "MANIFEST.json"), "w"), indent=1, sort_keys=True)

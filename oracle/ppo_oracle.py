@@ -195,6 +195,12 @@ class PPOConfig:
     schedule: str = "fixed"
     desired_kl: Optional[float] = 0.01
     base_lin_vel_coef: float = 1.0
+    # mirror-symmetry loss (ppo.py:59-63,93-105,197-202): off in the shipped config
+    sym_loss: bool = False
+    sym_coef: float = 1.0
+    obs_permutation: Optional[List[float]] = None      # per single frame, signed indices (|p| = source column)
+    act_permutation: Optional[List[float]] = None
+    frame_stack: int = 0
     # torch.optim.Adam defaults (ppo.py:77)
     beta1: float = 0.9
     beta2: float = 0.999
@@ -224,8 +230,41 @@ def adaptive_lr(lr: float, kl_mean: float, desired_kl: float) -> float:
     return lr
 
 
+def perm_matrix(perm: List[float]) -> torch.Tensor:
+    """ppo.py:96-98 / 103-105: M[int(|p_i|)][i] = sign(p_i), so (x @ M)[i] = sign(p_i) * x[|p_i|].  (An index 0 has to be
+    written as +-0.0001 by the caller: np.sign(0) = 0 would zero the column -- reproduced as the reference behaves.)"""
+    import numpy as np
+    m = torch.zeros((len(perm), len(perm)))
+    for i, q in enumerate(perm):
+        m[int(abs(q))][i] = float(np.sign(q))
+    return m
+
+
+def stacked_obs_permutation(obs_permutation: List[float], frame_stack: int) -> List[float]:
+    """ppo.py:99-102: the per-frame permutation repeated for every stacked frame, offset by the frame width."""
+    import numpy as np
+    out = []
+    for i in range(frame_stack):
+        for q in obs_permutation:
+            out.append(float(np.sign(q) * (abs(q) + i * len(obs_permutation))))
+    return out
+
+
+def xbot_mirror_permutations():
+    """A left/right mirror of the 47-wide XBot-L frame and of its 12 actions, for tests (the reference ships no
+    permutation; `sym_loss` is off in humanoid_config.py).  Signs: hip roll / hip yaw / ankle roll flip."""
+    s = [-1, -1, 1, 1, 1, -1]
+    obs = [-0.0001, 1, 2, -3, -4]
+    for b in (5, 17, 29):
+        obs += [s[i] * (b + 6 + i) for i in range(6)] + [s[i] * (b + i) for i in range(6)]
+    obs += [-41, 42, -43, -44, 45, -46]
+    act = [s[i] * (6 + i) for i in range(6)] + [(s[i] * i if i else -0.0001) for i in range(6)]
+    assert sorted(int(abs(q)) for q in obs) == list(range(47)) and sorted(int(abs(q)) for q in act) == list(range(12))
+    return obs, act
+
+
 def minibatch_losses(p: Params, mb: Dict[str, torch.Tensor], cfg: PPOConfig) -> Dict[str, torch.Tensor]:
-    """Forward + the four loss terms of ppo.py:154-208 (symmetry loss off, its default)."""
+    """Forward + the loss terms of ppo.py:154-208 (the mirror-symmetry term only with cfg.sym_loss)."""
     mu = policy_mean(p, mb["obs"])
     std = p["std"]
     sigma = mu * 0.0 + std
@@ -245,10 +284,18 @@ def minibatch_losses(p: Params, mb: Dict[str, torch.Tensor], cfg: PPOConfig) -> 
         value_loss = torch.max((v - mb["returns"]).pow(2), (v_clipped - mb["returns"]).pow(2)).mean()
     else:
         value_loss = (mb["returns"] - v).pow(2).mean()
+    sym_loss = 0
+    if cfg.sym_loss:                                                            # ppo.py:197-202
+        obs_perm_mat = perm_matrix(stacked_obs_permutation(cfg.obs_permutation, cfg.frame_stack))
+        act_perm_mat = perm_matrix(cfg.act_permutation)
+        mirror_obs = torch.matmul(mb["obs"], obs_perm_mat)
+        mirror_act = policy_mean(p, mirror_obs)
+        m_mirror_act = torch.matmul(mirror_act, act_perm_mat)
+        sym_loss = (mu - m_mirror_act).pow(2).mean()
     lin_vel_loss = torch.nn.functional.mse_loss(lv, mb["lin_vel_target"])
-    loss = (surrogate_loss + cfg.value_loss_coef * value_loss - cfg.entropy_coef * ent.mean()
+    loss = (surrogate_loss + cfg.value_loss_coef * value_loss - cfg.entropy_coef * ent.mean() + cfg.sym_coef * sym_loss
             + cfg.base_lin_vel_coef * lin_vel_loss)
-    return dict(loss=loss, surrogate=surrogate_loss, value=value_loss, lin_vel=lin_vel_loss,
+    return dict(loss=loss, surrogate=surrogate_loss, value=value_loss, lin_vel=lin_vel_loss, sym=sym_loss,
                 entropy=ent.mean(), kl=kl_mean, mu=mu, v=v, lv=lv)
 
 
@@ -310,7 +357,7 @@ def ppo_update(p: Params, st: AdamState, ro: Rollout, perm: torch.Tensor, cfg: P
         if record is not None:
             record.append(dict(value=float(out["value"]), surrogate=float(out["surrogate"]),
                                lin_vel=float(out["lin_vel"]), entropy=float(out["entropy"]),
-                               kl=float(out["kl"]), lr=lr, grad_norm=gnorm))
+                               kl=float(out["kl"]), lr=lr, grad_norm=gnorm, sym=float(out["sym"])))
     return sums["value"] / n, sums["surrogate"] / n, sums["lin_vel"] / n, lr
 
 

@@ -146,6 +146,37 @@ def test_env_callback_golden(golden_dir):
     assert torch.equal(st.episode_sums, torch.tensor(z["final_episode_sums"]))
 
 
+def test_learner_symmetry_loss_golden(golden_dir):
+    """SURVEY 8f rank 4 (oracle side): one update WITH the mirror-symmetry loss (ppo.py:93-105,197-202) replays the
+    fixture recorded from the unmodified reference (sym_loss=True, sym_coef 0.5, the test mirror permutation)."""
+    import dataclasses
+    z = np.load(os.path.join(golden_dir, "learner_sym_small.npz"))
+    obs_perm, act_perm = po.xbot_mirror_permutations()
+    assert np.array_equal(z["obs_permutation"], np.array(obs_perm)) and np.array_equal(z["act_permutation"], np.array(act_perm))
+    m = po.perm_matrix(po.stacked_obs_permutation(obs_perm, 15))
+    assert m.shape == (705, 705) and float(m.abs().sum()) == 705 and torch.equal(m.abs().sum(0), torch.ones(705))
+    x = torch.randn(3, 705)
+    assert torch.allclose((x @ m) @ m, x)                          # a mirror applied twice is the identity
+    cfg = dataclasses.replace(po.xbot_ppo_config(), sym_loss=True, sym_coef=float(z["sym_coef"]), obs_permutation=obs_perm,
+                              act_permutation=act_perm, frame_stack=15)
+    torch.manual_seed(int(z["seed"]))
+    p = po.init_params(705, 219, 12, (512, 256, 128), (768, 256, 128), (128, 128), 1.0)
+    t = lambda k: torch.tensor(z[k])
+    ro = po.Rollout(t("observations"), t("privileged_observations"), t("actions"), t("rewards"), t("dones"), t("values"),
+                    t("actions_log_prob"), t("mu"), t("sigma"))
+    ro.returns, ro.advantages = t("returns"), t("advantages")
+    rec = []
+    v, s, lv, lr = po.ppo_update(p, po.AdamState(), ro, t("perm"), cfg, cfg.learning_rate, record=rec)
+    rv, rs, rsym, rlv = z["ref_losses"]
+    assert v == pytest.approx(rv, rel=1e-6) and s == pytest.approx(rs, rel=1e-5, abs=1e-8) and lv == pytest.approx(rlv, rel=1e-6)
+    assert rec[-1]["sym"] == pytest.approx(rsym, rel=1e-6) and rsym > 1e-3
+    assert lr == pytest.approx(float(z["ref_lr"]), rel=1e-12)
+    for k in po.state_dict_order(p):
+        flat = p[k].detach().reshape(-1)
+        idx = torch.linspace(0, flat.numel() - 1, min(64, flat.numel())).long()
+        assert np.allclose(flat[idx].numpy(), z["param_probe." + k], rtol=0, atol=2.5 * lr), k
+
+
 def test_quat_apply_heading_matches_euler_yaw():
     """`quat_apply` is restated from Isaac Gym (absent from the reference tree, parity unpinned): for a pure yaw rotation
     the heading atan2(forward_y, forward_x) must equal the yaw of `get_euler_xyz`, and the rotation must keep norms."""
