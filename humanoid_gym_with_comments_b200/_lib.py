@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("HG_LIB_PATH") or os.path.join(HERE, "libhgb200.so")   # HG_LIB_PATH: kernel-variant experiments (tools/build_variant.sh)
 BUILD_DIR = os.path.join(HERE, "csrc", "_build")
-SOURCES = ["hg_runtime.cu", "hg_gemm.cu", "hg_gae.cu", "hg_misc.cu", "hg_heads.cu", "hg_optim.cu", "hg_env.cu", "hg_env_aux.cu"]
+SOURCES = ["hg_runtime.cu", "hg_gemm.cu", "hg_gae.cu", "hg_misc.cu", "hg_heads.cu", "hg_optim.cu", "hg_env.cu", "hg_env_aux.cu", "hg_sym.cu"]
 EXTRA_FLAGS = {"hg_env.cu": ["-fmad=false"], "hg_env_aux.cu": ["-fmad=false"]}
 if os.environ.get("HG_EPI_WARPS"):
     EXTRA_FLAGS["hg_gemm.cu"] = ["-DHG_EPI_WARPS=" + os.environ["HG_EPI_WARPS"]]
@@ -209,6 +209,9 @@ _SIGNATURES = {
     "hg_cast_weight_bf16": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "hg_env_step": (C.c_int, [C.POINTER(HgEnvConfig), C.POINTER(HgEnvBuffers), _P]),
     "hg_action_torque": (C.c_int, [C.POINTER(HgActionArgs), _P]),
+    "hg_permute_cols_bf16": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P]),
+    "hg_sym_loss": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
+    "hg_head_backward": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P, _P]),
     "hg_command_step": (C.c_int, [C.POINTER(HgCommandArgs), _P]),
     "hg_episode_means": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
 }
@@ -231,7 +234,7 @@ def load(auto_build: bool = True) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.hg_abi_version() != 5:
+    if lib.hg_abi_version() != 6:
         raise HgError("libhgb200.so ABI mismatch")
     _lib = lib
     return lib

@@ -131,9 +131,6 @@ class PPO:
                  obs_permutation=None, act_permutation=None, frame_stack=0, sym_coef=1.0, base_lin_vel_coef=1.0):
         if torch.device(device).type != "cuda":
             raise _lib.HgError("PPO(device=...) must be a CUDA device: this implementation has no CPU fallback")
-        if sym_loss:
-            raise NotImplementedError("the mirror-symmetry loss (ppo.py:93-105,197-202) is off in the shipped config and "
-                                      "has no fused kernel yet (SURVEY 8f rank 4)")
         self.device = device
         self.desired_kl = desired_kl
         self.schedule = schedule
@@ -161,6 +158,20 @@ class PPO:
         self.base_lin_vel_coef = base_lin_vel_coef
         self.sym_loss = sym_loss
         self.sym_coef = sym_coef
+        self.last_sym_loss = 0.0
+        if self.sym_loss:      # signed permutations of ppo.py:95-105 kept as (source column, sign) instead of dense matrices
+            import numpy as np
+            if obs_permutation is None or act_permutation is None or frame_stack <= 0:
+                raise ValueError("sym_loss=True needs obs_permutation, act_permutation and frame_stack (ppo.py:59-63)")
+            stack = [np.sign(q) * (abs(q) + i * len(obs_permutation)) for i in range(frame_stack) for q in obs_permutation]
+            dev = self.device
+            as_src = lambda perm: torch.tensor([int(abs(q)) for q in perm], dtype=torch.int32, device=dev)
+            as_sign = lambda perm: torch.tensor([float(np.sign(q)) for q in perm], dtype=torch.float32, device=dev)
+            self._obs_src, self._obs_sign = as_src(stack), as_sign(stack)
+            self._act_src, self._act_sign = as_src(act_permutation), as_sign(act_permutation)
+            if len(act_permutation) != self.actor_critic.num_actions:
+                raise ValueError("act_permutation must have one entry per action")
+            self._sym_ws = None
 
         # implementation switches
         self.torch_rng = True        # draw eps / burn the update-time sample() through torch's generator (seed parity)
@@ -345,6 +356,7 @@ class PPO:
         ws = ac.workspace(M, with_grads=True)
         nets = (ac.net_actor, ac.net_critic, ac.net_linvel)
         n_updates = nep * nmb
+        self._sym_slot = None
         loss_log = torch.zeros(n_updates, 8, dtype=torch.float64, device=indices.device)
         adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
         slot = 0
@@ -358,6 +370,8 @@ class PPO:
                 inputs = {"actor": x, "critic": p, "base_lin_vel": x}
                 cols = {"actor": st.obs_cols, "critic": st.priv_cols, "base_lin_vel": st.obs_cols}
                 eng.forward_hidden(nets, inputs, cols, ws, M)
+                if self.sym_loss:
+                    sym = self._sym_forward(x, ws, M)
                 largs = HgLossArgs(
                     actor=self._head_net(ac.net_actor, ws, flat), critic=self._head_net(ac.net_critic, ws, flat),
                     linvel=self._head_net(ac.net_linvel, ws, flat), rows=M, A=A, idx=ptr(idx),
@@ -370,6 +384,8 @@ class PPO:
                     use_clipped_value_loss=1 if self.use_clipped_value_loss else 0,
                     inv_world=1.0 / self.world_size, stats=ptr(flat.stats))
                 check(lib.hg_ppo_head_loss(C.byref(largs), current_stream()))
+                if self.sym_loss:
+                    self._sym_backward(sym, ws, M)
                 eng.backward_hidden(nets, inputs, cols, ws, M)
                 if self.world_size > 1:
                     # the only collective of the path: SUM over ranks of [gradients | KL and loss sums]
@@ -388,4 +404,49 @@ class PPO:
         mean_surrogate_loss = float(log[:, 1].mean())
         mean_base_lin_vel_loss = float(log[:, 2].mean())
         st.clear()
-        return mean_value_loss, mean_surrogate_loss, 0, mean_base_lin_vel_loss
+        sym_loss = 0
+        if self.sym_loss:      # the reference returns the LAST minibatch's symmetry loss (ppo.py:226)
+            self.last_sym_losses = (self._sym_sums / (M * A)).cpu().tolist()
+            sym_loss = self.last_sym_loss = self.last_sym_losses[-1]
+        return mean_value_loss, mean_surrogate_loss, sym_loss, mean_base_lin_vel_loss
+
+    # ------------------------------------------------------------------ mirror-symmetry loss (ppo.py:197-202)
+    def _sym_forward(self, x, ws, M):
+        """mirror_obs = obs @ obs_perm_mat, mirror_act = actor(mirror_obs), sym_loss = mean((mu - mirror_act @ act_perm_mat)^2):
+        the mirrored rows go through the same grouped tcgen05 GEMMs as the batch; returns what `_sym_backward` needs."""
+        from .engine import Workspace
+        ac, st, lib = self.actor_critic, self.storage, self._lib
+        eng, A, dev = ac.engine(), ac.num_actions, x.device
+        if self._sym_ws is None or self._sym_ws[0].rows != M:
+            f32 = lambda *s: torch.empty(*s, device=dev)
+            self._sym_ws = (Workspace((ac.net_actor,), M, dev, True), torch.empty(M, st.obs_ld, dtype=torch.bfloat16, device=dev),
+                            f32(M, A), f32(M, A), f32(M, A), f32(M, A))
+        ws_m, xm, mu, mirror, dmu, dmirror = self._sym_ws
+        if getattr(self, "_sym_slot", None) is None or self._sym_slot >= self._sym_sums.numel():
+            self._sym_sums = torch.zeros(self.num_learning_epochs * self.num_mini_batches, dtype=torch.float64, device=dev)
+            self._sym_slot = 0
+        s = current_stream()
+        check(lib.hg_permute_cols_bf16(ptr(x), x.stride(0), M, st.obs_cols, ptr(self._obs_src), ptr(self._obs_sign), ptr(xm),
+                                       xm.stride(0), s))
+        eng.forward_hidden((ac.net_actor,), {"actor": xm}, {"actor": st.obs_cols}, ws_m, M)
+        la = ac.net_actor.linears[-1]
+        for h, out in ((ws.h["actor"][-1], mu), (ws_m.h["actor"][-1], mirror)):
+            check(lib.hg_head_forward(ptr(h), h.stride(0), h.shape[1], ptr(la.weight.data), ptr(la.bias.data), A, M, ptr(out), s))
+        scale = 2.0 * float(self.sym_coef) / (M * A * self.world_size)
+        check(lib.hg_sym_loss(ptr(mu), ptr(mirror), ptr(self._act_src), ptr(self._act_sign), M, A, scale, ptr(dmu), ptr(dmirror),
+                              self._sym_sums.data_ptr() + 8 * self._sym_slot, s))
+        self._sym_slot += 1
+        return ws_m, xm, dmu, dmirror
+
+    def _sym_backward(self, sym, ws, M):
+        """Adds the symmetry term's gradient: through the batch's own forward (d/d mu, accumulated onto the dZ the loss
+        kernel just wrote) and through the mirrored forward (its own backward pass over the actor)."""
+        ws_m, xm, dmu, dmirror = sym
+        ac, st, lib, flat = self.actor_critic, self.storage, self._lib, self.actor_critic.flat
+        la, top = ac.net_actor.linears[-1], ac.net_actor.linears[-2]
+        gW, gb, gbh = flat.grad_view(la.weight), flat.grad_view(la.bias), flat.grad_view(top.bias)
+        s = current_stream()
+        for h, d, dz, acc in ((ws.h["actor"][-1], dmu, ws.dz["actor"][-1], 1), (ws_m.h["actor"][-1], dmirror, ws_m.dz["actor"][-1], 0)):
+            check(lib.hg_head_backward(ptr(h), h.stride(0), h.shape[1], ptr(la.weight.data), ac.num_actions, ptr(d), M, acc,
+                                       ptr(dz), dz.stride(0), ptr(gW), ptr(gb), ptr(gbh), s))
+        ac.engine().backward_hidden((ac.net_actor,), {"actor": xm}, {"actor": st.obs_cols}, ws_m, M)

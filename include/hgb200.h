@@ -21,7 +21,7 @@ extern "C" {
 #define HG_ERR_INVALID (-1)
 #define HG_ERR_CUDA (-2)
 
-#define HG_ABI_VERSION 5
+#define HG_ABI_VERSION 6
 
 const char* hg_last_error(void);
 int hg_abi_version(void);
@@ -375,6 +375,24 @@ typedef struct HgActionArgs {
   float* torques;              /* [N,D] or NULL */
 } HgActionArgs;
 int hg_action_torque(const HgActionArgs* args_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mirror-symmetry loss of PPO.update (ppo.py:93-105,197-202; off in the shipped config).
+ * A signed permutation matrix P (P[|p_i|][i] = sign(p_i), ppo.py:96-105) is passed as src[i] = |p_i| and
+ * sign[i] in {-1, 0, +1} (np.sign(0) = 0 zeroes the column, as in the reference).
+ *   hg_permute_cols_bf16: dst[r, i] = sign[i] * src[r, src_col[i]]  = (obs_batch @ obs_perm_mat) on the bf16 rows (:199)
+ *   hg_sym_loss:          diff = mu - mirror_act @ act_perm_mat; loss_sum += sum diff^2 (:201-202);
+ *                         dmu = scale * diff, dmirror = -scale * diff @ act_perm_mat^T   (scale = 2 sym_coef / (rows A world))
+ *   hg_head_backward:     backward of an fp32 output layer out = h W^T + b for a given d/d out: dZ (+)= (dOut W) * elu'(h)
+ *                         (bf16, the top hidden layer's pre-activation gradient), gW += dOut^T h, gb += colsum(dOut),
+ *                         gb_hidden += colsum(dZ contribution).  n_out <= 16.
+ * The mirrored actor forward and the hidden-layer backward reuse the grouped GEMMs and hg_head_forward. */
+int hg_permute_cols_bf16(const void* src, int64_t ld_src, int rows, int cols, const int32_t* src_col, const float* sign,
+                         void* dst, int64_t ld_dst, void* stream);
+int hg_sym_loss(const float* mu, const float* mirror_act, const int32_t* act_src, const float* act_sign, int rows,
+                int num_actions, float scale, float* dmu, float* dmirror, double* loss_sum, void* stream);
+int hg_head_backward(const void* h, int64_t ld_h, int H, const float* W, int n_out, const float* d_out, int rows,
+                     int accumulate, void* dZ, int64_t ld_dz, float* gW, float* gb, float* gb_hidden, void* stream);
 
 /* The tensor math around the reward / observation kernels of post_physics_step, one launch each:
  *
