@@ -73,7 +73,7 @@ int hg_gemm_grouped(const HgGemmProblem* problems_host, int num_problems, int ep
                     void* stream);
 
 /* The same launch with the host-side preparation (argument checks, TMA tensor-map encoding, tile schedule) done
- * once: the rollout issues the identical three launches for every storage slot on every iteration, so the host
+ * once: the rollout issues the identical launches for every storage slot on every iteration, so the host
  * keeps one plan per (slot, depth) and replays it with a single cheap call. */
 typedef struct HgGemmPlan HgGemmPlan;
 int hg_gemm_plan_create(const HgGemmProblem* problems_host, int num_problems, int epilogue, int block_n, int cta_group,
