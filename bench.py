@@ -16,7 +16,10 @@ Isaac-Gym-shaped state tensors.  One JSON line is printed by rank 0.
            iteration reads its losses + mean reward back to the host
   roofline: the grouped tcgen05 GEMM launches (the dominant kernel), algorithmic FLOPs / CUDA-event time, against the
            measured bf16 peak of MEASURED_PEAKS.json
-  cpu_baseline: the oracle port (torch CPU fp32, all host threads) on a bounded sample of the same workload
+  cpu_baseline: the UNMODIFIED reference (oracle/_ref; the oracle port only if that is absent) on torch-CPU fp32, all host
+           threads, on a bounded sample of the same workload
+  reference_torch_cuda: the same unmodified reference on cuda:0 at the FULL workload (eager torch fp32, CUDA events)
+  --impl reference: the reference arm on the host cores; its config names the envs it actually ran
 """
 from __future__ import annotations
 
@@ -49,7 +52,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--horizon", type=int, default=60)
-    ap.add_argument("--cpu-sample-envs", type=int, default=256)
+    ap.add_argument("--cpu-sample-envs", type=int, default=256, help="envs of the cpu_baseline sample inside the product line")
+    ap.add_argument("--ref-envs", type=int, default=0, help="--impl reference: envs per iteration (0 = the full workload if "
+                    "steps + warmup iterations fit ~150 s on this host, else the largest power-of-two sample that does)")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the unmodified reference on cuda:0 (reference_torch_cuda)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--torch-rng", action="store_true",
@@ -145,75 +151,159 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
-# ------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_baseline(a, seconds_budget=20.0, iters=None, device="cpu", envs=None):
-    """The reference algorithm (oracle restatement: torch fp32, autograd backward, all host threads) on a bounded
-    sample: `cpu_sample_envs` envs x horizon steps, same nets / hyper-parameters / env math.  Returns env-steps/s.
-    device="cuda" (only `--impl reference --ref-device cuda`) runs the very same torch code on cuda:0 -- the torch-CUDA
-    figure of the reference's algorithm."""
-    import torch
-    with torch.device(device):
-        return _port_iterations(a, seconds_budget, iters, device, envs)
-
-
-def _port_iterations(a, seconds_budget, iters, device, envs):
+# ------------------------------------------------------------------------------------------ reference / CPU baseline
+# Two arms of the reference's algorithm, both test / baseline infrastructure (never on the product path):
+#   kind "reference": the UNMODIFIED reference -- humanoid/algo/ppo (PPO, ActorCritic, RolloutStorage) and the text of
+#                     humanoid/envs/custom/humanoid_env.py under the stub isaacgym of oracle/ref_harness.py -- loaded
+#                     from oracle/_ref/ (recipe oracle/build_ref.py; byte-identical copies, sha256 in its MANIFEST.json),
+#   kind "port":      the oracle restatement (oracle/{ppo,env}_oracle.py, pinned bit-exact to the reference), used only
+#                     when oracle/_ref/ is absent.
+# Either runs the loop of OnPolicyRunner.learn (on_policy_runner.py:128-168): T x (act, env tensor math, process_env_step),
+# compute_returns, update -- on the host cores (device "cpu") or, same code, on cuda:0 ("reference_torch_cuda").
+def _reference_loop(N, T, device):
+    """-> iteration() running ONE PPO iteration of the unmodified reference at N envs x T steps on `device`."""
     import torch
     from oracle import env_oracle as eo
     from oracle import ppo_oracle as po
-    torch.set_num_threads(os.cpu_count() or 1)
-    on_gpu = device != "cpu"
-    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
-    N, T = envs or a.cpu_sample_envs, a.horizon
-    cfg = po.xbot_ppo_config()
-    torch.manual_seed(0)
-    p = po.init_params(705, 219, 12, (512, 256, 128), (768, 256, 128), (128, 128), 1.0)
+    from oracle import ref_harness as rh
+    PPO, ActorCritic, _ = rh.load_learner()
+    c = po.xbot_ppo_config()
     spec = eo.xbot_spec(12)
-    est = eo.EnvState(spec, N)
-    g = torch.Generator(device=device).manual_seed(0)
-    pool = [eo.synthetic_sim_state(spec, N, g) for _ in range(4)]
-    st, lr = po.AdamState(), cfg.learning_rate
-    out = eo.env_step(spec, est, pool[0], torch.randn(N, spec.So, generator=g))
-    obs, priv = out["obs"], out["priv"]
+    with torch.device(device):
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ac = ActorCritic(705, 219, 12, init_noise_std=1.0, **NETS)
+        alg = PPO(ac, num_learning_epochs=c.num_learning_epochs, num_mini_batches=c.num_mini_batches, clip_param=c.clip_param,
+                  gamma=c.gamma, lam=c.lam, value_loss_coef=c.value_loss_coef, entropy_coef=c.entropy_coef,
+                  learning_rate=c.learning_rate, max_grad_norm=c.max_grad_norm, use_clipped_value_loss=True,
+                  schedule=c.schedule, desired_kl=c.desired_kl, device=device)
+        alg.init_storage(N, T, [705], [219], [12])
+        renv = rh.RefEnv(12, N, spec, device=device)
+        g = torch.Generator(device=device).manual_seed(0)
+        pool = [eo.synthetic_sim_state(spec, N, g) for _ in range(4)]
+        out = renv.step(pool[0], torch.randn(N, spec.So, generator=g))
+    state = {"obs": out["obs"], "priv": out["priv"], "i": 0}
 
-    def iteration(i):
-        nonlocal obs, priv, lr
-        z = torch.zeros
-        ro = po.Rollout(z(T, N, 705), z(T, N, 219), z(T, N, 12), z(T, N, 1), z(T, N, 1, dtype=torch.uint8), z(T, N, 1),
-                        z(T, N, 1), z(T, N, 12), z(T, N, 12))
-        with torch.no_grad():
-            for t in range(T):
-                m = po.policy_mean(p, obs)
-                act = po.sample_actions(m, p["std"], torch.randn(N, 12))
-                v = po.value(p, priv)
-                ro.observations[t], ro.privileged_observations[t], ro.actions[t], ro.values[t] = obs, priv, act, v
-                ro.actions_log_prob[t] = po.log_prob(m, p["std"], act).view(-1, 1)
-                ro.mu[t], ro.sigma[t] = m, m * 0 + p["std"]
-                sim = dict(pool[(i * T + t) % len(pool)])
-                sim["actions"] = act.clip(-18, 18)
-                out = eo.env_step(spec, est, sim, torch.randn(N, spec.So))
-                obs, priv = out["obs"], out["priv"]
-                ro.rewards[t] = po.bootstrap_rewards(out["rew"], v, out["time_out"], cfg.gamma).view(-1, 1)
-                ro.dones[t] = out["reset"].view(-1, 1)
-            ro.returns, ro.advantages = po.gae_returns(ro.rewards, ro.values, ro.dones, po.value(p, priv), cfg.gamma, cfg.lam)
-        _, _, _, lr = po.ppo_update(p, st, ro, torch.randperm(N * T), cfg, lr)
+    def iteration():
+        obs, critic_obs = state["obs"], state["priv"]
+        with torch.device(device):
+            with torch.inference_mode():
+                for t in range(T):
+                    actions = alg.act(obs, critic_obs)
+                    sim = dict(pool[(state["i"] * T + t) % len(pool)])
+                    sim["actions"] = torch.clip(actions, -18.0, 18.0)            # step() :633-635
+                    out = renv.step(sim, torch.randn(N, spec.So))
+                    obs, critic_obs = out["obs"], out["priv"]
+                    alg.process_env_step(out["rew"], out["reset"], {"time_outs": out["time_out"]})
+                alg.compute_returns(critic_obs)
+            alg.update()
+        state["obs"], state["priv"] = obs, critic_obs
+        state["i"] += 1
+    return iteration
 
-    iteration(0)                                   # warm-up
-    sync()
+
+def _port_loop(N, T, device):
+    """-> iteration() of the oracle restatement (fallback when oracle/_ref is absent)."""
+    import torch
+    from oracle import env_oracle as eo
+    from oracle import ppo_oracle as po
+    cfg = po.xbot_ppo_config()
+    with torch.device(device):
+        torch.manual_seed(0)
+        p = po.init_params(705, 219, 12, (512, 256, 128), (768, 256, 128), (128, 128), 1.0)
+        spec = eo.xbot_spec(12)
+        est = eo.EnvState(spec, N)
+        g = torch.Generator(device=device).manual_seed(0)
+        pool = [eo.synthetic_sim_state(spec, N, g) for _ in range(4)]
+        out = eo.env_step(spec, est, pool[0], torch.randn(N, spec.So, generator=g))
+    state = {"obs": out["obs"], "priv": out["priv"], "i": 0, "lr": cfg.learning_rate, "adam": po.AdamState()}
+
+    def iteration():
+        obs, priv = state["obs"], state["priv"]
+        with torch.device(device):
+            z = torch.zeros
+            ro = po.Rollout(z(T, N, 705), z(T, N, 219), z(T, N, 12), z(T, N, 1), z(T, N, 1, dtype=torch.uint8), z(T, N, 1),
+                            z(T, N, 1), z(T, N, 12), z(T, N, 12))
+            with torch.no_grad():
+                for t in range(T):
+                    m = po.policy_mean(p, obs)
+                    act = po.sample_actions(m, p["std"], torch.randn(N, 12))
+                    v = po.value(p, priv)
+                    ro.observations[t], ro.privileged_observations[t], ro.actions[t], ro.values[t] = obs, priv, act, v
+                    ro.actions_log_prob[t] = po.log_prob(m, p["std"], act).view(-1, 1)
+                    ro.mu[t], ro.sigma[t] = m, m * 0 + p["std"]
+                    sim = dict(pool[(state["i"] * T + t) % len(pool)])
+                    sim["actions"] = act.clip(-18, 18)
+                    out = eo.env_step(spec, est, sim, torch.randn(N, spec.So))
+                    obs, priv = out["obs"], out["priv"]
+                    ro.rewards[t] = po.bootstrap_rewards(out["rew"], v, out["time_out"], cfg.gamma).view(-1, 1)
+                    ro.dones[t] = out["reset"].view(-1, 1)
+                ro.returns, ro.advantages = po.gae_returns(ro.rewards, ro.values, ro.dones, po.value(p, priv), cfg.gamma, cfg.lam)
+            _, _, _, state["lr"] = po.ppo_update(p, state["adam"], ro, torch.randperm(N * T), cfg, state["lr"])
+        state["obs"], state["priv"] = obs, priv
+        state["i"] += 1
+    return iteration
+
+
+def reference_kind():
+    from oracle import build_ref
+    return "reference" if build_ref.available() or os.path.isdir("/root/reference/humanoid/algo/ppo") else "port"
+
+
+def time_reference(N, T, device="cpu", iters=None, warmup=1, seconds_budget=20.0, kind=None):
+    """Times `iters` iterations (or as many as fit `seconds_budget`, at least 1) of the reference's PPO iteration at
+    N envs x T steps on `device` after `warmup` untimed ones.  CPU: perf_counter, all host threads; CUDA: CUDA events.
+    Returns (cpu_baseline-shaped dict, seconds per iteration)."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    kind = kind or reference_kind()
+    iteration = (_reference_loop if kind == "reference" else _port_loop)(N, T, device)
+    on_gpu = device != "cpu"
+    for _ in range(max(1, warmup)):
+        iteration()
     times = []
-    t_end = time.perf_counter() + seconds_budget
-    i = 1
-    while (iters is None and time.perf_counter() < t_end and len(times) < 50) or (iters is not None and len(times) < iters):
-        t0 = time.perf_counter()
-        iteration(i)
-        sync()
-        times.append(time.perf_counter() - t0)
-        i += 1
+    if on_gpu:
+        torch.cuda.synchronize()
+        n = iters or 2
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record()
+        for i in range(n):
+            iteration()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        times = [evs[i].elapsed_time(evs[i + 1]) / 1e3 for i in range(n)]
+    else:
+        t_end = time.perf_counter() + seconds_budget
+        while (iters is None and (not times or time.perf_counter() < t_end) and len(times) < 50) or (iters is not None and len(times) < iters):
+            t0 = time.perf_counter()
+            iteration()
+            times.append(time.perf_counter() - t0)
     med = statistics.median(times)
-    where = "torch-CUDA fp32 (cuda:0, eager)" if on_gpu else "torch-CPU fp32"
-    return {"value": N * T / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "device": device,
+    what = ("the UNMODIFIED reference (humanoid/algo/ppo + humanoid_env.py tensor math under a stub isaacgym, from oracle/_ref)"
+            if kind == "reference" else "the oracle restatement (pinned bit-exact to the reference on CPU; oracle/_ref absent)")
+    where = "torch-CUDA fp32 eager on cuda:0, CUDA-event timed" if on_gpu else "torch-CPU fp32, all host threads"
+    return {"value": N * T / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "device": device,
+            "envs": N, "horizon": T, "ms_per_iteration": med * 1e3,
             "sample": f"{N} envs x {T} steps per iteration (env math + rollout + GAE + update), median of {len(times)} "
-                      f"iterations after 1 warm-up, {med * 1e3:.0f} ms/iteration; oracle = {where} restatement of the "
-                      f"reference pinned bit-exact to it on CPU (the reference itself is Python and is not present on this box)"}, med
+                      f"iterations after {max(1, warmup)} warm-up, {med * 1e3:.0f} ms/iteration; {what}; {where}"}, med
+
+
+def cpu_baseline(a, seconds_budget=20.0):
+    """Reported CPU baseline inside the product line: a bounded sample (`--cpu-sample-envs` envs x horizon) on the host."""
+    return time_reference(a.cpu_sample_envs, a.horizon, "cpu", seconds_budget=seconds_budget)
+
+
+def _reference_arm_envs(a, rate_guess, budget_s=150.0):
+    """Envs per iteration for the reference arm so that (steps + warmup) iterations end within `budget_s`: the FULL
+    workload when it fits, otherwise the largest power-of-two sample that does (never below 64)."""
+    iters = max(1, a.steps) + max(1, a.warmup)
+    fit = int(rate_guess * budget_s / (iters * a.horizon))
+    if fit >= a.envs:
+        return a.envs
+    n = 64
+    while n * 2 <= fit:
+        n *= 2
+    return min(n, a.envs)
 
 
 def run_reference(a):
@@ -221,13 +311,24 @@ def run_reference(a):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if a.ref_device == "cuda":      # the port on the GPU at the full workload (not the driver's arm: a one-off comparison)
-        base, med = cpu_baseline(a, iters=max(1, a.steps), seconds_budget=1e9, device="cuda", envs=a.envs)
-    else:
-        base, med = cpu_baseline(a, iters=max(1, a.steps) + 0, seconds_budget=1e9) if a.steps <= 20 else cpu_baseline(a, 60.0)
+    if a.ref_envs:
+        n = a.ref_envs
+    else:      # calibrate the host's rate on one small iteration, then size the sample (CPU throughput is ~flat in N from 256 envs on)
+        _, med = time_reference(256, a.horizon, a.ref_device, iters=1, warmup=1)
+        n = a.envs if a.ref_device == "cuda" else _reference_arm_envs(a, 256 * a.horizon / med)
+    base, med = time_reference(n, a.horizon, a.ref_device, iters=max(1, a.steps), warmup=max(1, a.warmup))
+    cfg = workload_config(a, world)
+    cfg["envs_per_gpu"] = n
+    cfg["sampled"] = n != a.envs
+    cfg["full_envs_per_gpu"] = a.envs
+    cfg["workload"] = cfg["workload"].replace(f"{a.envs} envs/GPU", f"{n} envs" + (f" (bounded sample of the {a.envs}-env workload)" if n != a.envs else ""))
+    cfg["parallelism"] = f"host cores x{base['cores']} (rank 0 only)" if a.ref_device == "cpu" else "cuda:0 eager"
+    cfg["rng"] = "torch default generator (torch.randn / Normal.sample / randperm), as the reference draws"
+    cfg["precision"] = "fp32 throughout (the reference enables neither TF32 nor AMP)"
+    cfg["l2_policy"] = "n/a (host arm)" if a.ref_device == "cpu" else "working set exceeds L2"
     line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(a, world), "cpu_baseline": base,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": base,
             "ref_device": a.ref_device,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -435,16 +536,27 @@ def run_ours(a):
     except Exception as e:       # never lose the headline line to an auxiliary measurement
         aux["error"] = repr(e)
 
-    base = None
+    base, ref_cuda = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         base, _ = cpu_baseline(a)
+    if rank == 0 and world == 1 and not a.no_ref_cuda:
+        # the denominator of north_star's ">= 50x the reference's torch-CUDA PPO iteration": the unmodified reference on this
+        # very GPU at the FULL workload (eager torch, fp32), 1 warm-up + 2 CUDA-event-timed iterations, after our own timing
+        try:
+            rc, _ = time_reference(N, T, dev, iters=2, warmup=1)
+            rc["speedup_of_value"] = value / rc["value"]
+            if e2e:
+                rc["speedup_of_e2e"] = e2e["value"] / rc["value"]
+            ref_cuda = rc
+        except Exception as e:
+            ref_cuda = {"error": repr(e)}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(a, world), "clocks": clocks.summary(), "e2e": e2e,
                 "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
-                "roofline": roofline, "hbm_kernels": aux, "cpu_baseline": base}
+                "roofline": roofline, "hbm_kernels": aux, "cpu_baseline": base, "reference_torch_cuda": ref_cuda}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

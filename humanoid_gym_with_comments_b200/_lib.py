@@ -62,21 +62,45 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(BUILD_DIR, exist_ok=True)
+    # One builder at a time (torchrun starts every rank at once): whoever gets the lock builds, the others wait and
+    # then find the library fresh.  Objects are rebuilt only when their source (or a header) is newer.
+    import fcntl
+    with open(os.path.join(BUILD_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            return _build_locked(verbose, force)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool, force: bool) -> str:
     nvcc = _nvcc()
+    tag = f".{os.getpid()}"
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "hgb200.h"))
+    flags_sig = " ".join(NVCC_FLAGS) + repr(sorted(EXTRA_FLAGS.items()))
 
     def compile_one(src):
         obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
+        sig = obj + ".flags"
+        deps = [os.path.join(CSRC, src), *headers]
+        if (not force and os.path.exists(obj) and os.path.exists(sig) and open(sig).read() == flags_sig
+                and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps)):
+            return obj
         cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise HgError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         if verbose and (r.stdout or r.stderr):
             print(r.stdout, r.stderr, file=sys.stderr)
+        open(sig, "w").write(flags_sig)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIB_PATH + ".tmp"
+    tmp = LIB_PATH + tag + ".tmp"
     r = subprocess.run([nvcc, "-shared", "-cudart", "static", "-o", tmp, *objs], capture_output=True, text=True)
     if r.returncode != 0:
         raise HgError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -60,6 +60,7 @@ class ActorCritic(nn.Module):
         self._x16: Dict[tuple, torch.Tensor] = {}
         self._mean = None
         self._rng_counter = 0
+        self._load_version = 0
 
     # ------------------------------------------------------------------ engine plumbing
     def _specs(self):
@@ -81,7 +82,13 @@ class ActorCritic(nn.Module):
         self.engine()
         return self._flat
 
+    @staticmethod
+    def philox_seed(rank: int = 0) -> int:
+        """64-bit key of the in-kernel Philox streams: torch's seed, mixed with the data-parallel rank."""
+        return (int(torch.initial_seed()) ^ (rank * 0x9E3779B97F4A7C15)) & (2 ** 64 - 1)
+
     def load_state_dict(self, state_dict, strict=True, **kw):
+        self._load_version += 1
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         if self._flat is not None and self._flat.attached():
             self._flat.refresh_shadows()
@@ -122,7 +129,8 @@ class ActorCritic(nn.Module):
             check(lib.hg_policy_head_rollout(
                 ptr(ha), ha.stride(0), ha.shape[1], ptr(la.weight.data), ptr(la.bias.data), ptr(self.std.data),
                 ptr(hc), hc.stride(0), hc.shape[1], ptr(lc.weight.data), ptr(lc.bias.data), ptr(eps),
-                int(torch.initial_seed()) & (2 ** 64 - 1), self._rng_counter, rows, A,
+                self.philox_seed(torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0),
+                self._rng_counter, rows, A,
                 ptr(out["actions"]), ptr(out["mu"]), ptr(out["sigma"]), ptr(out["log_prob"]), ptr(out["values"]),
                 current_stream()))
         else:

@@ -34,6 +34,7 @@ class FusedAdam(optim.Adam):
         super().__init__(actor_critic.parameters(), lr=lr)
         self._ac = actor_critic
         self._flat = None
+        self._load_version = 0
         # device scalars: [0] lr [1] step [2] grad sumsq [3] clip coef [4] step size [5] sqrt(1-b2^t) [6] grad norm
         self.opt_state = None
 
@@ -78,6 +79,7 @@ class FusedAdam(optim.Adam):
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
+        self._load_version += 1
         flat = self._ac.flat
         self._flat = None
         loaded = {id(p): self.state.get(p) for p in flat.params}
@@ -164,29 +166,60 @@ class PPO:
             if obs_permutation is None or act_permutation is None or frame_stack <= 0:
                 raise ValueError("sym_loss=True needs obs_permutation, act_permutation and frame_stack (ppo.py:59-63)")
             stack = [np.sign(q) * (abs(q) + i * len(obs_permutation)) for i in range(frame_stack) for q in obs_permutation]
+            # the reference multiplies by dense [O,O] / [A,A] matrices and fails on a shape mismatch; the kernels index,
+            # so the same mistakes are rejected here instead of becoming out-of-range reads
+            O, A_ = self.actor_critic.num_actor_obs, self.actor_critic.num_actions
+            if len(stack) != O:
+                raise ValueError(f"len(obs_permutation) * frame_stack = {len(stack)} must equal num_actor_obs = {O}")
+            if len(act_permutation) != A_:
+                raise ValueError("act_permutation must have one entry per action")
+            if max(int(abs(q)) for q in stack) >= O or max(int(abs(q)) for q in act_permutation) >= A_:
+                raise ValueError("permutation index out of range")
+            if len({int(abs(q)) for q in act_permutation}) != A_ or len({int(abs(q)) for q in stack}) != O:
+                raise ValueError("obs_permutation / act_permutation must be true (signed) permutations: the symmetry "
+                                 "kernels scatter d/d(mirror) through the index, duplicates would drop gradient")
             dev = self.device
             as_src = lambda perm: torch.tensor([int(abs(q)) for q in perm], dtype=torch.int32, device=dev)
             as_sign = lambda perm: torch.tensor([float(np.sign(q)) for q in perm], dtype=torch.float32, device=dev)
             self._obs_src, self._obs_sign = as_src(stack), as_sign(stack)
             self._act_src, self._act_sign = as_src(act_permutation), as_sign(act_permutation)
-            if len(act_permutation) != self.actor_critic.num_actions:
-                raise ValueError("act_permutation must have one entry per action")
             self._sym_ws = None
 
         # implementation switches
         self.torch_rng = True        # draw eps / burn the update-time sample() through torch's generator (seed parity)
-        self.world_size = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.world_size = torch.distributed.get_world_size() if dist_on else 1
+        self.rank = torch.distributed.get_rank() if dist_on else 0
         self.last_update_log = None  # [epochs*minibatches, 8] per-minibatch statistics of the last update()
         self._perm_bufs = None
         self._lr_synced = learning_rate
         # test hooks: replay externally drawn randomness (parity tests feed the oracle's eps / permutation)
         self._lib = _lib.load()
         self._slot_plans, self._plans_owner, self._plans_storage = {}, None, None
-        self._seed = int(torch.initial_seed()) & (2 ** 64 - 1)
+        # Philox key of the action-noise stream: torch's seed mixed with the rank, so that data-parallel replicas (built under
+        # the SAME torch seed to get identical weights) explore independently -- (seed, step, local row) alone would give
+        # every rank bit-identical eps for the same local env row
+        self._seed = self.actor_critic.philox_seed(self.rank)
+        self._replica_versions = None
+        if self.world_size > 1:
+            self.sync_replicas()
         self._gamma_f = float(gamma)
         self.eps_override = None     # callable(step) -> [N, A] standard-normal draws
         self.fuse_rollout_head = os.environ.get("HG_FUSE_HEAD", "1") != "0"   # last hidden layer + output layer + sampling in one launch
         self.perm_override = None    # int64 [num_mini_batches * mini_batch_size] permutation
+
+    def sync_replicas(self):
+        """world_size > 1: the update all-reduces gradients only, so parameters, Adam moments and lr / step must be
+        identical on every rank.  Broadcast them from rank 0 (construction, and again after either load_state_dict) and
+        re-cast the bf16 weight shadows."""
+        flat, opt = self.actor_critic.flat, self.optimizer
+        opt.bind()
+        for t in (flat.p, flat.m, flat.v, opt.opt_state):
+            torch.distributed.broadcast(t, src=0)
+        flat.refresh_shadows()
+        opt.sync_host()
+        self.learning_rate = self._lr_synced = float(opt.param_groups[0]["lr"])
+        self._replica_versions = (self.actor_critic._load_version, opt._load_version)
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
@@ -333,6 +366,8 @@ class PPO:
         lib = _lib.load()
         t_host0 = time.perf_counter()
         self.optimizer.bind()
+        if self.world_size > 1 and self._replica_versions != (ac._load_version, self.optimizer._load_version):
+            self.sync_replicas()                                # a checkpoint was loaded since the last broadcast
         if abs(self.learning_rate - self._lr_synced) > 0:       # user changed alg.learning_rate by hand
             self.optimizer.set_lr(self.learning_rate)
         nmb, nep = self.num_mini_batches, self.num_learning_epochs

@@ -420,6 +420,7 @@ class SyntheticXBotEnv:
         self.callbacks = callbacks
         self.cfg, self.device = cfg, torch.device(device)
         self.math = XBotEnvMath(cfg, device)
+        self.math.seed = (seed * 0x9E3779B97F4A7C15 + 0x5EED) & (2 ** 64 - 1)     # Philox key of the env's noise: per env instance / rank
         self.num_envs = cfg.num_envs
         self.num_obs = cfg.num_observations
         self.num_privileged_obs = cfg.num_privileged_obs
@@ -431,6 +432,10 @@ class SyntheticXBotEnv:
                                                          device=self.device))
         self.torch_rng_noise = torch_rng_noise
         self.extras = {}
+        # OnPolicyRunner.learn reads env.course_gain / env.course_ratio (on_policy_runner.py:160-162); only LeggedRobot
+        # defines them (legged_robot.py:84-85), XBotLFreeEnv does not -- a VecEnv that wants to be driven by the
+        # unmodified runner has to carry them
+        self.course_gain, self.course_ratio = 1.0, 1.0
         self._i = 0
         self._storage = None
         self._host_pool = None

@@ -1,5 +1,7 @@
-"""Loads the UNMODIFIED reference from /root/reference (this container only; the GPU box has no
-copy) so `make_golden.py` can pin the oracle.  TEST INFRASTRUCTURE ONLY.
+"""Loads the UNMODIFIED reference -- from /root/reference in the build container, from the byte-identical copy
+`oracle/_ref/` (recipe: oracle/build_ref.py, git-ignored, travels with the snapshot) on the GPU box -- so that
+`make_golden.py` can pin the oracle and `bench.py --impl reference` / the runner test can execute the real thing.
+TEST / BASELINE INFRASTRUCTURE ONLY.
 
 * learner: `humanoid.algo.ppo` imports cleanly (needs wandb + tensorboard, both present).
 * env math: `humanoid_env.py` imports `isaacgym` (closed, absent) and broken package __init__s,
@@ -20,11 +22,30 @@ from collections import deque
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get("HG_REFERENCE_ROOT", "/root/reference")
+def _find_ref_root() -> str:
+    here = os.path.dirname(os.path.abspath(__file__))
+    cands = [os.environ.get("HG_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "humanoid", "algo", "ppo")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_ref_root()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "humanoid", "algo", "ppo"))
+
+
+def load_runner():
+    """-> the reference's `humanoid.algo.ppo.on_policy_runner` module (imports wandb + tensorboard)."""
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import importlib       # (`from .ppo import *` in humanoid/algo/__init__.py shadows the package attribute)
+        opr = importlib.import_module("humanoid.algo.ppo.on_policy_runner")
+    return opr
 
 
 def load_learner():
@@ -124,7 +145,14 @@ class RefEnv:
     """The reference env math bound to synthetic tensors (no Isaac Gym).  `step(sim, noise)` runs
     exactly the tensor part of `post_physics_step` (:780-806) + the clips of `step` (:654-657)."""
 
-    def __init__(self, D: int, N: int, spec):
+    def __init__(self, D: int, N: int, spec, device="cpu"):
+        """device="cuda:0": the same unmodified text on torch-CUDA (every factory call below and in the reference's
+        methods lands on `device` through torch's default-device context / `self.device`)."""
+        self.device = device
+        with torch.device(device):
+            self._init(D, N, spec, device)
+
+    def _init(self, D, N, spec, device):
         cls, Cfg = load_env_class(D)
         self.cls = cls
         e = types.SimpleNamespace()
@@ -132,7 +160,7 @@ class RefEnv:
         cfg.env.num_actions = D
         cfg.env.num_single_obs = spec.So
         cfg.env.single_num_privileged_obs = spec.Sp
-        e.cfg, e.num_envs, e.device, e.dt, e.num_dof, e.num_actions = cfg, N, "cpu", spec.dt, D, D
+        e.cfg, e.num_envs, e.device, e.dt, e.num_dof, e.num_actions = cfg, N, device, spec.dt, D, D
         e.obs_scales = cfg.normalization.obs_scales
         e.max_episode_length = np.ceil(cfg.env.episode_length_s / e.dt)
         from humanoid.utils.helpers import class_to_dict
@@ -180,6 +208,10 @@ class RefEnv:
         self._randn = None
 
     def step(self, sim, noise, callback=None):
+        with torch.device(self.device):
+            return self._step(sim, noise, callback)
+
+    def _step(self, sim, noise, callback=None):
         """callback = dict(u_cmd [N,3], u_push [N,5], u_cmd_reset [N,3]): also run the reference's
         `_post_physics_step_callback` (with `_resample_commands`, `_push_robots`) and the command resampling + episode
         means of `reset_idx`, replaying the given uniform draws; commands / push buffers then persist in the env."""

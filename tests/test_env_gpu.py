@@ -277,3 +277,109 @@ def test_synthetic_env_with_callbacks_is_a_complete_vecenv():
         assert set(extras) >= {"time_outs", "episode"} and len(extras["episode"]) == 22
         assert all(torch.isfinite(v) for v in extras["episode"].values())
     assert seen_push and torch.isfinite(obs).all() and (env.math.commands[:, 2].abs() <= 1).all()
+
+
+# ---------------------------------------------------------------------------------- fp32 phase precision
+def _one_step(cfg, ep_after, D=12):
+    """One fused step at N = len(ep_after) envs whose episode length AFTER the increment of :780 is `ep_after`; no
+    contacts on the base (no termination).  Returns (obs, priv) on the CPU and the sim dict."""
+    N = len(ep_after)
+    env = XBotEnvMath(cfg, DEV)
+    env.episode_length_buf.copy_(torch.as_tensor(ep_after, dtype=torch.long) - 1)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    sim = synthetic_sim_state(cfg, g, DEV, base_contact_frac=0.0)
+    sim["actions"] = torch.randn(N, D, device=DEV, generator=g)
+    obs, priv, rew, reset, tout = env.step(sim, None if not cfg.add_noise else torch.zeros(N, cfg.num_single_obs, device=DEV))
+    assert not bool(reset.any())
+    return obs.cpu(), priv.cpu(), {k: v.cpu() for k, v in sim.items()}
+
+
+def test_phase_mul_reciprocal_reproduces_torch_cuda_division():
+    """`phase = episode_length_buf * dt / cycle_time` (:692): torch-CPU divides, torch-CUDA multiplies by the fp32
+    reciprocal of the Python scalar -- a <= 1-ulp difference in the phase that sin/cos amplify to ~2e-5 at phase ~37.
+    `phase_mul_reciprocal=False` must follow the CPU semantics (the oracle's), `True` the CUDA ones: checked against
+    torch's own CUDA kernels evaluating the reference's expression on this GPU, for EVERY episode length 1..2399."""
+    ep = torch.arange(1, 2400)
+    outs = {}
+    for mode in (False, True):
+        cfg = XBotMathConfig(num_envs=len(ep), add_noise=False, phase_mul_reciprocal=mode)
+        obs, _, _ = _one_step(cfg, ep)
+        outs[mode] = obs[:, -47:-45].clone()                      # newest frame: sin, cos
+    cpu_phase = ep * 0.01 / 0.64                                  # torch-CPU: int64 * float -> fp32, true division
+    cuda_phase = ep.to(DEV) * 0.01 / 0.64                         # torch-CUDA: the reference's expression on the device
+    want = {False: torch.stack((torch.sin(2 * torch.pi * cpu_phase), torch.cos(2 * torch.pi * cpu_phase)), 1),
+            True: torch.stack((torch.sin(2 * torch.pi * cuda_phase), torch.cos(2 * torch.pi * cuda_phase)), 1).cpu()}
+    n_phase_differs = int((cpu_phase != cuda_phase.cpu()).sum())
+    print(f"episode lengths whose fp32 phase differs between torch-CPU and torch-CUDA: {n_phase_differs} of {len(ep)}")
+    for mode in (False, True):
+        err = float((outs[mode] - want[mode]).abs().max())
+        print(f"phase_mul_reciprocal={mode}: max |sin/cos - torch-{'CUDA' if mode else 'CPU'}| = {err:.3e}")
+        assert err <= 3e-7, (mode, err)                           # sinf / cosf implementations: <= 2 ulp
+    cross = float((outs[True] - want[False]).abs().max())
+    print(f"cross-check (CUDA semantics vs CPU reference): {cross:.3e}")
+    if n_phase_differs:                                           # the two semantics are really different computations
+        assert cross > 1e-6 and not torch.equal(outs[False], outs[True])
+
+
+def test_dead_band_decisions_at_adversarial_phases():
+    """The |sin| < 0.1 dead band (:713, :742) and the sin >= 0 / < 0 split (:707-711) flip whole rows of `ref_dof_pos` and
+    the stance mask.  For cycle times chosen so that an integer episode length lands on the fp32 phases NEAREST to a
+    band edge (both sides, within a few ulp of the phase), the kernel's decisions must (a) equal the oracle's and (b) be
+    exactly the function of the sin value the kernel itself reports: stance, ref_dof_pos (through priv's q - ref columns)."""
+    import math
+    cases = []
+    for ep_t, k in ((7, 0), (37, 1), (411, 12), (1999, 61)):      # edge theta = k*pi + asin(0.1): early, mid and late in an episode
+        t32 = np.float32(ep_t) * np.float32(0.01)
+        theta = k * math.pi + (math.asin(0.1) if k % 2 == 0 else -math.asin(0.1))
+        c0 = np.float32(2 * math.pi * float(t32) / theta)
+        cs = [c0]
+        up, dn = c0, c0
+        for _ in range(256):
+            up, dn = np.nextafter(up, np.float32(10)), np.nextafter(dn, np.float32(0))
+            cs += [up, dn]
+        cs = np.array(cs, dtype=np.float32)
+        s = torch.sin(torch.tensor(np.float32(6.2831855) * (t32 / cs)))          # the oracle's arithmetic (:692, :705)
+        margin = (s.abs() - 0.1).abs()
+        order = torch.argsort(margin)[:24]                         # the 24 cycle times whose sin is closest to the edge
+        assert float(margin[order[0]]) < 2e-5
+        cases += [(ep_t, float(cs[i])) for i in order.tolist()]
+    below = above = exempt = 0
+    for ep_t, c in cases:
+        spec = eo.xbot_spec(12)
+        spec.cycle_time, spec.add_noise = c, False
+        cfg = XBotMathConfig(num_envs=4, add_noise=False, cycle_time=c)
+        eps = [ep_t, ep_t, ep_t + 32, ep_t + 1]
+        obs, priv, sim = _one_step(cfg, eps)
+        st = eo.EnvState(spec, 4)
+        st.episode_length_buf = torch.tensor(eps) - 1
+        sim_o = dict(sim)
+        D = 12
+        sim_o["dof_pos"], sim_o["dof_vel"] = sim["dof_state"].view(4, D, 2)[..., 0], sim["dof_state"].view(4, D, 2)[..., 1]
+        want = eo.env_step(spec, st, sim_o, None)
+        pf, wf = priv[:, -73:], want["priv"][:, -73:]              # newest critic frame
+        s_gpu = pf[:, 0]
+        assert torch.allclose(s_gpu, wf[:, 0], atol=3e-7), (ep_t, c)
+        # (a) same decisions as the oracle -- except where the CPU's own sin is within 2 ulp of the edge value: there
+        # CUDA sinf and glibc sinf (each <= 2 ulp) may legitimately land on different sides
+        far = ((wf[:, 0].abs() - 0.1).abs() > 1.6e-8)
+        exempt += int((~far).sum())
+        assert torch.equal(pf[far, 69:71], wf[far, 69:71]), f"stance mask differs from the oracle at ep {ep_t}, cycle_time {c!r}"
+        assert torch.allclose(pf[far, 41:53], wf[far, 41:53], atol=1e-6), f"q - ref differs at ep {ep_t}, cycle_time {c!r}"
+        # (b) decisions are exactly the function of the kernel's own sin value
+        dead = s_gpu.abs() < 0.1
+        stance = torch.stack(((s_gpu >= 0) | dead, (s_gpu < 0) | dead), 1).float()
+        assert torch.equal(pf[:, 69:71], stance)
+        q = sim["dof_state"].view(4, D, 2)[..., 0]
+        ref = q - pf[:, 41:53]
+        sl, sr = torch.clamp(s_gpu, max=0.0), torch.clamp(s_gpu, min=0.0)
+        exp = torch.zeros(4, D)
+        exp[:, 2], exp[:, 3], exp[:, 4] = sl * 0.17, sl * 0.34, sl * 0.17
+        exp[:, 8], exp[:, 9], exp[:, 10] = sr * 0.17, sr * 0.34, sr * 0.17
+        exp[dead] = 0.0
+        assert torch.allclose(ref, exp, atol=2e-7), (ep_t, c)
+        assert torch.equal(ref[dead], torch.zeros_like(ref[dead]) + 0.0) or float(ref[dead].abs().max()) < 2e-7
+        below += int(dead[0])
+        above += int(~dead[0])
+    print(f"{len(cases)} adversarial (episode length, cycle time) cases: {below} inside the dead band, {above} outside, "
+          f"{exempt} env rows exactly on the edge (oracle comparison skipped, self-consistency still checked)")
+    assert below >= 8 and above >= 8

@@ -137,7 +137,7 @@ def test_config1_update_vs_oracle():
     w0 = oracle_params()["actor.0.weight"]
     cos = torch.nn.functional.cosine_similarity((w_got - w0).flatten(), (w_ref - w0).flatten(), dim=0)
     print("cosine(update direction) actor.0.weight:", float(cos))
-    assert float(cos) > 0.9
+    assert float(cos) > 0.999
 
 
 def test_config2_iteration_vs_oracle():
@@ -169,6 +169,55 @@ def test_config2_iteration_vs_oracle():
     assert rel(v, ov) <= 1e-3 and rel(lv, olv) <= 1e-3
     assert rel(s, os_) <= 1e-3 or abs(s - os_) <= 2e-5
     assert alg.learning_rate == pytest.approx(olr, rel=1e-12)
+
+
+def test_config2_five_iterations_vs_oracle():
+    """BASELINE config 2 (4096 x 60), FIVE consecutive PPO iterations: both sides keep their own weights and Adam state
+    from iteration to iteration (so bf16-gradient differences accumulate), every iteration sees the same observations,
+    eps, rewards, dones and permutation.  north_star's tolerance -- 1e-3 relative on the per-iteration value, surrogate,
+    entropy (and lin-vel) losses -- must hold on EVERY iteration, the adaptive-lr sequence (40 decisions) must be identical.
+    Surrogate: a near-cancelling mean of -A * ratio terms (A normalised to mean 0); its error is measured relative to the
+    mean |per-minibatch surrogate| of the iteration -- the scale of the terms that are averaged -- as well as to its own value."""
+    N, T, ITER = 4096, 60, 5
+    alg, cfg = make_alg(N, T)
+    p = oracle_params()
+    adam, lr = po.AdamState(), cfg.learning_rate
+    gen = torch.Generator().manual_seed(29)
+    worst = dict(value=0.0, lin_vel=0.0, entropy=0.0, surr_rel=0.0, surr_scaled=0.0)
+    for it in range(ITER):
+        ro, last_c, inputs = po.synthetic_rollout(p, N, T, 705, 219, 12, cfg, gen, record_inputs=True)
+        alg.eps_override = lambda t, inputs=inputs: inputs[t]["eps"]
+        with torch.inference_mode():
+            for t in range(T):
+                alg.act(ro.observations[t].to(DEV), ro.privileged_observations[t].to(DEV))
+                alg.process_env_step(inputs[t]["rew"].to(DEV), inputs[t]["dones"].to(DEV), {"time_outs": inputs[t]["time_outs"].to(DEV)})
+            alg.compute_returns(last_c.to(DEV))
+        perm = torch.randperm(N * T, generator=gen)
+        alg.perm_override = perm.to(DEV)
+        rec = []
+        ov, os_, olv, lr = po.ppo_update(p, adam, ro, perm, cfg, lr, record=rec)
+        v, s, _, lv = alg.update()
+        log = alg.last_update_log.numpy()
+        oent = float(np.mean([r["entropy"] for r in rec]))
+        ent = float(log[:, 4].mean())
+        scale = float(np.mean([abs(r["surrogate"]) for r in rec]))
+        e = dict(value=rel(v, ov), lin_vel=rel(lv, olv), entropy=rel(ent, oent), surr_rel=rel(s, os_), surr_scaled=abs(s - os_) / scale)
+        print(f"iteration {it}: value {v:.6f}/{ov:.6f} ({e['value']:.1e})  surrogate {s:+.4e}/{os_:+.4e} (rel {e['surr_rel']:.1e}, "
+              f"/mean|mb| {e['surr_scaled']:.1e})  lin-vel {lv:.6f}/{olv:.6f} ({e['lin_vel']:.1e})  entropy {ent:.6f}/{oent:.6f} "
+              f"({e['entropy']:.1e})  lr {alg.learning_rate:.4e}/{lr:.4e}  kl {log[-1, 3]:.3e}/{rec[-1]['kl']:.3e}")
+        assert [float(x) for x in log[:, 5]] == pytest.approx([r["lr"] for r in rec], rel=1e-12), f"iteration {it}: lr sequence"
+        assert e["value"] <= 1e-3 and e["lin_vel"] <= 1e-3 and e["entropy"] <= 1e-3, (it, e)
+        assert e["surr_scaled"] <= 1e-3, (it, e)
+        for k in worst:
+            worst[k] = max(worst[k], e[k])
+    print("worst over", ITER, "iterations:", {k: f"{x:.2e}" for k, x in worst.items()})
+    assert worst["surr_rel"] <= 5e-3      # relative to its own (near-cancelling) value: stated bound, see docstring
+    sd = alg.actor_critic.state_dict()
+    torch.manual_seed(0)
+    w0 = oracle_params()["actor.0.weight"]
+    cos = torch.nn.functional.cosine_similarity((sd["actor.0.weight"].cpu() - w0).flatten(), (p["actor.0.weight"] - w0).flatten(), dim=0)
+    print("cosine(total update over 5 iterations) actor.0.weight:", float(cos))
+    assert float(cos) > 0.99
 
 
 def test_shipped_18dof_layout_update_vs_oracle():
@@ -444,4 +493,4 @@ def test_symmetry_loss_update_vs_oracle():
     w0 = oracle_params()["actor.0.weight"]
     cos = torch.nn.functional.cosine_similarity((sd["actor.0.weight"].cpu() - w0).flatten(), (p["actor.0.weight"] - w0).flatten(), dim=0)
     print("cosine(update direction) actor.0.weight:", float(cos))
-    assert float(cos) > 0.9
+    assert float(cos) > 0.999
