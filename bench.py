@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--torch-rng", action="store_true",
                     help="draw action / observation noise with torch.randn (stream parity with the reference on the same device) instead of the in-kernel Philox4x32-10")
     ap.add_argument("--unbound-env", action="store_true", help="env writes its own buffers; PPO.act ingests them (generic drop-in path)")
+    ap.add_argument("--stacked", action="store_true", help="bound env writes whole stacked rows (round-1 format) instead of the history ring")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' runs the same torch port on cuda:0 at the FULL workload (the torch-CUDA "
                          "figure north_star's target is quoted against); the default and the driver's arm is 'cpu'")
@@ -74,7 +75,9 @@ def workload_config(a, world):
             "envs_per_gpu": a.envs, "horizon": a.horizon, "parallelism": f"env-sharded dp{world}",
             "rng": "in-kernel Philox4x32-10 keyed by (seed, step, row) for action and observation noise; --torch-rng switches to torch.randn",
             "precision": "bf16 tensor-core GEMM operands with fp32 accumulation (hidden layers); output layers, losses, GAE, env math and Adam in fp32",
-            "l2_policy": "per-iteration working set (storage 0.95 GB fp32 + 0.46 GB bf16) exceeds the 126 MB L2; no explicit flush"}
+            "l2_policy": "per-iteration working set (history rings 0.34 GB, permuted bf16 minibatch rows 0.46 GB, activations / "
+                         "gradients ~0.6 GB, all rewritten every iteration) exceeds the 126 MB L2; no explicit flush",
+            "obs_format": "history ring (one new 47 / 73-wide frame per env step; SURVEY 8f rank 3)"}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -367,7 +370,7 @@ def run_ours(a):
     torch.manual_seed(1000 + rank)               # per-rank env / sampling streams
     env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, pool=4, seed=rank, torch_rng_noise=a.torch_rng)
     if not a.unbound_env:
-        env.bind_storage(alg.storage, gamma=alg.gamma)
+        env.bind_storage(alg.storage, gamma=alg.gamma, ring=not a.stacked)
     obs, critic_obs = env.get_observations(), env.get_privileged_observations()
     state = {"obs": obs, "critic_obs": critic_obs}
     h2d_bytes_per_env_step = sum(v.numel() * v.element_size() for v in env.pool[0].values())
@@ -375,11 +378,12 @@ def run_ours(a):
     def iteration(e2e: bool):
         obs, critic_obs = state["obs"], state["critic_obs"]
         with torch.inference_mode():
-            for i in range(T):
-                actions = alg.act(obs, critic_obs)
-                obs, privileged_obs, rewards, dones, infos = env.step(actions)
-                critic_obs = privileged_obs if privileged_obs is not None else obs
-                alg.process_env_step(rewards, dones, infos)
+            with _lib.nvtx_range("hg.rollout"):
+                for i in range(T):
+                    actions = alg.act(obs, critic_obs)
+                    obs, privileged_obs, rewards, dones, infos = env.step(actions)
+                    critic_obs = privileged_obs if privileged_obs is not None else obs
+                    alg.process_env_step(rewards, dones, infos)
             alg.compute_returns(critic_obs)
         losses = alg.update()                    # reads the loss log back (D2H) once per iteration
         state["obs"], state["critic_obs"] = obs, critic_obs
@@ -529,10 +533,13 @@ def run_ours(a):
             env.step(acts)
             st.env_stored = None
         us = time_calls(env_once, min(T - 1, 40))
-        env_bytes = (4.0 * (47 * 29 + 73 * 5) + 900.0) * N        # SURVEY 8d K-a: history shift + state, D = 12
+        if st.ring_enabled:      # history ring: newest frame only -- fp32 live + fp32 archive + bf16 live, actor and critic, + ~0.9 KB state
+            env_bytes = (2 * 4.0 * (47 + 73) + 2.0 * (48 + 80) + 900.0) * N
+        else:                    # SURVEY 8d K-a: history shift + state, D = 12
+            env_bytes = (4.0 * (47 * 29 + 73 * 5) + 900.0) * N
         st.step = 0
         aux["env_step"] = {"us": us, "bytes": env_bytes, "gbs": env_bytes / us / 1e3, "frac": env_bytes / us / 1e3 / hbm_peak,
-                           "launches_per_call": 1}
+                           "launches_per_call": 1, "format": "history ring" if st.ring_enabled else "stacked"}
     except Exception as e:       # never lose the headline line to an auxiliary measurement
         aux["error"] = repr(e)
 

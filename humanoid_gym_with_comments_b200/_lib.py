@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("HG_LIB_PATH") or os.path.join(HERE, "libhgb200.so")   # HG_LIB_PATH: kernel-variant experiments (tools/build_variant.sh)
 BUILD_DIR = os.path.join(HERE, "csrc", "_build")
-SOURCES = ["hg_runtime.cu", "hg_gemm.cu", "hg_gae.cu", "hg_misc.cu", "hg_heads.cu", "hg_optim.cu", "hg_env.cu", "hg_env_aux.cu", "hg_sym.cu"]
+SOURCES = ["hg_runtime.cu", "hg_gemm.cu", "hg_gae.cu", "hg_misc.cu", "hg_heads.cu", "hg_optim.cu", "hg_env.cu", "hg_env_aux.cu", "hg_sym.cu", "hg_ring.cu"]
 EXTRA_FLAGS = {"hg_env.cu": ["-fmad=false"], "hg_env_aux.cu": ["-fmad=false"]}
 if os.environ.get("HG_EPI_WARPS"):
     EXTRA_FLAGS["hg_gemm.cu"] = ["-DHG_EPI_WARPS=" + os.environ["HG_EPI_WARPS"]]
@@ -113,7 +113,8 @@ class HgGemmProblem(C.Structure):
     _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("lda", C.c_int64), ("ldb", C.c_int64),
                 ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32), ("M", C.c_int32), ("N", C.c_int32),
                 ("K", C.c_int32), ("k_splits", C.c_int32), ("out", C.c_void_p), ("ldo", C.c_int64),
-                ("bias", C.c_void_p), ("act", C.c_void_p), ("ldact", C.c_int64), ("colsum", C.c_void_p)]
+                ("bias", C.c_void_p), ("act", C.c_void_p), ("ldact", C.c_int64), ("colsum", C.c_void_p),
+                ("out_frame_src", C.c_int32), ("out_frame_dst", C.c_int32)]
 
 
 class HgFusedHead(C.Structure):
@@ -141,7 +142,7 @@ class HgLossArgs(C.Structure):
 
 class HgBf16Shadow(C.Structure):
     _fields_ = [("param_offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("dst", C.c_void_p),
-                ("ld", C.c_int64)]
+                ("ld", C.c_int64), ("src_frame", C.c_int32), ("dst_frame", C.c_int32)]
 
 
 class HgAdamArgs(C.Structure):
@@ -169,6 +170,11 @@ class HgEnvConfig(C.Structure):
                 ("phase_mul_reciprocal", C.c_int32), ("phases", C.c_int32)]
 
 
+class HgHistoryRing(C.Structure):
+    _fields_ = [("live32", C.c_void_p), ("live16", C.c_void_p), ("arch32", C.c_void_p), ("width", C.c_int32),
+                ("pitch16", C.c_int32), ("frames", C.c_int32), ("slots", C.c_int32)]
+
+
 class HgEnvBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("root_states", "dof_state", "contact_forces", "rigid_state", "commands", "torques",
@@ -185,7 +191,9 @@ class HgEnvBuffers(C.Structure):
                 ("priv16_next", C.c_void_p), ("priv16_next_ld", C.c_int64)] + \
                [(n, C.c_void_p) for n in ("rew_buf", "reset_buf", "time_out_buf", "reward_terms", "store_values",
                                           "store_rewards", "store_dones")] + [("store_gamma", C.c_float),
-                                                                              ("root_vel_prepush", C.c_void_p)]
+                                                                              ("root_vel_prepush", C.c_void_p)] + \
+               [("ring_obs", HgHistoryRing), ("ring_priv", HgHistoryRing), ("ring_row", C.c_int32),
+                ("ring_first_valid", C.c_void_p), ("ring_hist_start", C.c_void_p)]
 
 
 class HgActionArgs(C.Structure):
@@ -230,7 +238,9 @@ _SIGNATURES = {
     "hg_store_rewards_dones": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P]),
     "hg_ppo_head_loss": (C.c_int, [C.POINTER(HgLossArgs), _P]),
     "hg_clip_adam_step": (C.c_int, [C.POINTER(HgAdamArgs), _P]),
-    "hg_cast_weight_bf16": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, _P]),
+    "hg_cast_weight_bf16": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, C.c_int, C.c_int, _P]),
+    "hg_ring_gather": (C.c_int, [C.POINTER(HgHistoryRing), C.c_int, _P, _P, C.c_int64, _P, C.c_int64, C.c_int, _P, C.c_int, _P]),
+    "hg_ring_rollover": (C.c_int, [C.POINTER(HgHistoryRing), C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "hg_env_step": (C.c_int, [C.POINTER(HgEnvConfig), C.POINTER(HgEnvBuffers), _P]),
     "hg_action_torque": (C.c_int, [C.POINTER(HgActionArgs), _P]),
     "hg_permute_cols_bf16": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P]),
@@ -258,7 +268,7 @@ def load(auto_build: bool = True) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.hg_abi_version() != 6:
+    if lib.hg_abi_version() != 7:
         raise HgError("libhgb200.so ABI mismatch")
     _lib = lib
     return lib
@@ -278,6 +288,30 @@ def require_cuda(*tensors) -> None:
 
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+# NVTX ranges per phase (the reference has no profiler hooks): HG_NVTX=1 turns them on for nsys / ncu --nvtx runs;
+# off by default so that the enqueue path pays nothing.
+NVTX = os.environ.get("HG_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 _raw_stream = None

@@ -97,11 +97,36 @@ class FlatParams:
                 ld = round_up(w.shape[1], LD_ALIGN)
                 sh = torch.zeros(w.shape[0], ld, dtype=torch.bfloat16, device=dev)
                 self.w16[id(w)] = sh
-                self._shadow_list.append(HgBf16Shadow(self.offsets[id(w)], w.shape[0], w.shape[1], sh.data_ptr(), ld))
-        if len(self._shadow_list) > _lib.HG_MAX_SHADOWS:
-            raise NotImplementedError("too many hidden layers for one optimiser launch")
-        self.shadow_array = (HgBf16Shadow * len(self._shadow_list))(*self._shadow_list)
+                self._shadow_list.append(HgBf16Shadow(self.offsets[id(w)], w.shape[0], w.shape[1], sh.data_ptr(), ld, 0, 0))
+        # frame-pitched shadows of first-layer weights (history-ring operands), created on demand: (id(w), width, pitch) -> bf16
+        self.w16_framed: Dict[tuple, torch.Tensor] = {}
+        self._framed_specs: List[tuple] = []
+        self._rebuild_shadow_array()
         self.refresh_shadows()
+
+    def _rebuild_shadow_array(self) -> None:
+        if len(self._shadow_list) > _lib.HG_MAX_SHADOWS:
+            raise NotImplementedError("too many bf16 weight shadows for one optimiser launch")
+        self.shadow_array = (HgBf16Shadow * len(self._shadow_list))(*self._shadow_list)
+
+    def framed_shadow(self, w: nn.Parameter, width: int, pitch: int) -> torch.Tensor:
+        """bf16 copy of a first-layer weight [out, frames*width] with every frame of `width` columns moved to a pitch of
+        `pitch` columns (pad columns zero): the B operand for input rows read straight out of the history ring, whose
+        bf16 frames sit at a 16-byte-aligned pitch.  Kept in step with the fp32 master by the optimiser launch."""
+        key = (id(w), width, pitch)
+        sh = self.w16_framed.get(key)
+        if sh is None:
+            if w.shape[1] % width != 0:
+                raise _lib.HgError(f"first-layer width {w.shape[1]} is not a whole number of {width}-wide frames")
+            frames = w.shape[1] // width
+            ld = round_up(frames * pitch, LD_ALIGN)
+            sh = torch.zeros(w.shape[0], ld, dtype=torch.bfloat16, device=self.device)
+            self.w16_framed[key] = sh
+            self._framed_specs.append((w, sh, width, pitch))
+            self._shadow_list.append(HgBf16Shadow(self.offsets[id(w)], w.shape[0], w.shape[1], sh.data_ptr(), ld, width, pitch))
+            self._rebuild_shadow_array()
+            check(_lib.load().hg_cast_weight_bf16(ptr(w.data), w.shape[0], w.shape[1], ptr(sh), ld, width, pitch, current_stream()))
+        return sh
 
     # -- views ------------------------------------------------------------------------------
     def grad_view(self, p: nn.Parameter) -> torch.Tensor:
@@ -125,7 +150,9 @@ class FlatParams:
             for lin in net.linears[:-1]:
                 w = lin.weight
                 sh = self.w16[id(w)]
-                check(lib.hg_cast_weight_bf16(ptr(w.data), w.shape[0], w.shape[1], ptr(sh), sh.shape[1], st))
+                check(lib.hg_cast_weight_bf16(ptr(w.data), w.shape[0], w.shape[1], ptr(sh), sh.shape[1], 0, 0, st))
+        for w, sh, width, pitch in self._framed_specs:
+            check(lib.hg_cast_weight_bf16(ptr(w.data), w.shape[0], w.shape[1], ptr(sh), sh.shape[1], width, pitch, st))
 
 
 class Workspace:
@@ -214,10 +241,10 @@ class MLPEngine:
             w2, w3 = self.flat.w16[id(lin2.weight)], self.flat.w16[id(lin3.weight)]
             l2.append(HgGemmProblem(A=ptr(h1), B=ptr(w2), lda=h1.stride(0), ldb=w2.stride(0), a_mn_major=0, b_mn_major=0,
                                     M=rows, N=lin2.out_features, K=net.hidden[0], k_splits=1, out=0, ldo=0,
-                                    bias=ptr(lin2.bias.data), act=0, ldact=0, colsum=0))
+                                    bias=ptr(lin2.bias.data), act=0, ldact=0, colsum=0, out_frame_src=0, out_frame_dst=0))
             l3.append(HgGemmProblem(A=0, B=ptr(w3), lda=0, ldb=w3.stride(0), a_mn_major=0, b_mn_major=0,
                                     M=rows, N=lin3.out_features, K=net.hidden[1], k_splits=1, out=0, ldo=0,
-                                    bias=ptr(lin3.bias.data), act=0, ldact=0, colsum=0))
+                                    bias=ptr(lin3.bias.data), act=0, ldact=0, colsum=0, out_frame_src=0, out_frame_dst=0))
             hs.append(heads[net.name])
         a2, a3 = (HgGemmProblem * len(l2))(*l2), (HgGemmProblem * len(l3))(*l3)
         harr = (_lib.HgFusedHead * len(hs))(*hs)
@@ -245,12 +272,14 @@ class MLPEngine:
 
     # -- forward of all hidden layers ---------------------------------------------------------
     def forward_hidden(self, nets: Sequence[NetSpec], inputs: Dict[str, torch.Tensor], in_cols: Dict[str, int],
-                       ws: Workspace, rows: int, make_plans: bool = False, heads=None):
+                       ws: Workspace, rows: int, make_plans: bool = False, heads=None, frames: Optional[Dict[str, tuple]] = None):
         """inputs[name]: bf16 [rows, ld] (ld multiple of 8; only the first in_cols[name] columns are read).
         Fills ws.h[name][l] = elu(W_l h_{l-1} + b_l) for every hidden layer, one grouped launch per depth.
         With make_plans=True nothing is launched: the prepared launches are returned for `run_plans`.
         heads (plans only): {net name: HgFusedHead} -- the LAST depth becomes one fused launch (last hidden layer +
-        output layer + sampling, `run_head_plan`); its activations are not written to ws.h."""
+        output layer + sampling, `run_head_plan`); its activations are not written to ws.h.
+        frames: {net name: (width, pitch)} -- the input rows of that net are history-ring frames of `width` columns at a
+        pitch of `pitch` (in_cols = frames * pitch): layer 1 reads the frame-pitched weight shadow."""
         plans = []
         depth = max(n.num_hidden for n in nets)
         fuse_tail = (make_plans and heads is not None and self.can_fuse_tail(nets))
@@ -265,12 +294,13 @@ class MLPEngine:
                 lin = net.linears[l]
                 a = inputs[net.name] if l == 0 else ws.h[net.name][l - 1]
                 k = in_cols[net.name] if l == 0 else net.hidden[l - 1]
-                w16 = self.flat.w16[id(lin.weight)]
+                fr = frames.get(net.name) if (frames and l == 0) else None
+                w16 = self.flat.framed_shadow(lin.weight, *fr) if fr else self.flat.w16[id(lin.weight)]
                 out = ws.h[net.name][l]
                 probs.append(HgGemmProblem(
                     A=ptr(a), B=ptr(w16), lda=a.stride(0), ldb=w16.stride(0), a_mn_major=0, b_mn_major=0,
                     M=rows, N=lin.out_features, K=k, k_splits=1, out=ptr(out), ldo=out.stride(0),
-                    bias=ptr(lin.bias.data), act=0, ldact=0, colsum=0))
+                    bias=ptr(lin.bias.data), act=0, ldact=0, colsum=0, out_frame_src=0, out_frame_dst=0))
                 ns.append(lin.out_features)
             if make_plans and heads is not None and l == depth - 1:
                 hs = [heads[net.name] for net in nets if l < net.num_hidden]
@@ -287,7 +317,7 @@ class MLPEngine:
 
     # -- backward of all hidden layers ----------------------------------------------------------
     def backward_hidden(self, nets: Sequence[NetSpec], inputs: Dict[str, torch.Tensor], in_cols: Dict[str, int],
-                        ws: Workspace, rows: int) -> None:
+                        ws: Workspace, rows: int, frames: Optional[Dict[str, tuple]] = None) -> None:
         """Expects ws.dz[name][-1] (top hidden layer pre-activation gradient) and its bias gradient to be
         already produced by the head kernel.  Accumulates weight gradients into the gradient arena and
         bias gradients of the lower layers, walking down one layer per step, grouped across nets."""
@@ -303,11 +333,13 @@ class MLPEngine:
                 below = inputs[net.name] if j == 0 else ws.h[net.name][j - 1]
                 k_in = in_cols[net.name] if j == 0 else net.hidden[j - 1]
                 gw = self.flat.grad_view(lin.weight)
-                # dW_j [out, in] += dZ_j^T [out, rows] * H_{j-1} [rows, in]     (both operands MN-major)
+                fr = frames.get(net.name) if (frames and j == 0) else None
+                # dW_j [out, in] += dZ_j^T [out, rows] * H_{j-1} [rows, in]     (both operands MN-major); frame-pitched input
+                # columns (history ring) are mapped back to the packed columns of the weight gradient by the epilogue
                 dw.append(HgGemmProblem(
                     A=ptr(dz), B=ptr(below), lda=dz.stride(0), ldb=below.stride(0), a_mn_major=1, b_mn_major=1,
-                    M=lin.out_features, N=k_in, K=rows, k_splits=1, out=ptr(gw), ldo=k_in,
-                    bias=0, act=0, ldact=0, colsum=0))
+                    M=lin.out_features, N=k_in, K=rows, k_splits=1, out=ptr(gw), ldo=lin.in_features,
+                    bias=0, act=0, ldact=0, colsum=0, out_frame_src=fr[1] if fr else 0, out_frame_dst=fr[0] if fr else 0))
                 dw_n.append(k_in)
                 if j >= 1:
                     # dZ_{j-1} = (dZ_j [rows,out] * W_j [out,in]) . elu'(H_{j-1});  b-grad of layer j-1 = colsum
@@ -317,7 +349,7 @@ class MLPEngine:
                     dx.append(HgGemmProblem(
                         A=ptr(dz), B=ptr(w16), lda=dz.stride(0), ldb=w16.stride(0), a_mn_major=0, b_mn_major=1,
                         M=rows, N=k_in, K=lin.out_features, k_splits=1, out=ptr(out), ldo=out.stride(0),
-                        bias=0, act=ptr(below), ldact=below.stride(0), colsum=ptr(gb)))
+                        bias=0, act=ptr(below), ldact=below.stride(0), colsum=ptr(gb), out_frame_src=0, out_frame_dst=0))
                     dx_n.append(k_in)
             if dw:
                 bn = self._block_n(dw_n, "dw")

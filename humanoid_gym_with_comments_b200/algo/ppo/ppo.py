@@ -21,8 +21,10 @@ import torch
 import torch.optim as optim
 
 from ... import _lib
-from ..._lib import HgAdamArgs, HgHeadNet, HgLossArgs, check, current_stream, ptr
+from ..._lib import HgAdamArgs, HgHeadNet, HgLossArgs, check, current_stream, nvtx_range, ptr
 from .actor_critic import ActorCritic
+from .engine import LD_ALIGN
+from .engine import round_up as _round_up
 from .rollout_storage import RolloutStorage
 
 
@@ -192,10 +194,11 @@ class PPO:
         self.rank = torch.distributed.get_rank() if dist_on else 0
         self.last_update_log = None  # [epochs*minibatches, 8] per-minibatch statistics of the last update()
         self._perm_bufs = None
+        self._lv_targets = None
         self._lr_synced = learning_rate
         # test hooks: replay externally drawn randomness (parity tests feed the oracle's eps / permutation)
         self._lib = _lib.load()
-        self._slot_plans, self._plans_owner, self._plans_storage = {}, None, None
+        self._slot_plans, self._plans_owner, self._plans_storage, self._plans_ring = {}, None, None, None
         # Philox key of the action-noise stream: torch's seed mixed with the rank, so that data-parallel replicas (built under
         # the SAME torch seed to get identical weights) explore independently -- (seed, step, local row) alone would give
         # every rank bit-identical eps for the same local env row
@@ -236,13 +239,20 @@ class PPO:
         (TMA tensor maps encoded, tile schedule laid out), the head launch arguments and the slot views."""
         ac, st = self.actor_critic, self.storage
         eng = ac.engine()
-        if self._plans_owner is not eng or self._plans_storage is not st:
+        ring = st.ring_enabled
+        if self._plans_owner is not eng or self._plans_storage is not st or self._plans_ring != (st._ring_obs if ring else None):
             self._slot_plans = {}
-            self._plans_owner, self._plans_storage = eng, st
+            self._plans_owner, self._plans_storage, self._plans_ring = eng, st, (st._ring_obs if ring else None)
         plan = self._slot_plans.get(t)
         if plan is None:
             N, A = st.num_envs, ac.num_actions
-            _, _, o16, p16 = st.slot(t)
+            if ring:      # layer 1 reads the history ring's bf16 window of row t in place (TMA over the strided view)
+                o16, p16 = st._ring_obs.view16(t), st._ring_priv.view16(t)
+                in_cols = {"actor": st._ring_obs.K16, "critic": st._ring_priv.K16}
+                frames = {"actor": (st._ring_obs.width, st._ring_obs.pitch16), "critic": (st._ring_priv.width, st._ring_priv.pitch16)}
+            else:
+                _, _, o16, p16 = st.slot(t)
+                in_cols, frames = {"actor": st.obs_cols, "critic": st.priv_cols}, None
             ws = ac.workspace(N)
             la, lc = ac.net_actor.linears[-1], ac.net_critic.linears[-1]
             heads = None
@@ -252,8 +262,8 @@ class PPO:
                                                    sigma=ptr(st.sigma[t]), log_prob=ptr(st.actions_log_prob[t])),
                          "critic": _lib.HgFusedHead(kind=_lib.HEAD_LINEAR, n_out=1, W=ptr(lc.weight.data), b=ptr(lc.bias.data),
                                                     out=ptr(st.values[t]))}
-            gemms = eng.forward_hidden((ac.net_actor, ac.net_critic), {"actor": o16, "critic": p16},
-                                       {"actor": st.obs_cols, "critic": st.priv_cols}, ws, N, make_plans=True, heads=heads)
+            gemms = eng.forward_hidden((ac.net_actor, ac.net_critic), {"actor": o16, "critic": p16}, in_cols, ws, N,
+                                       make_plans=True, heads=heads, frames=frames)
             if heads is not None:
                 gemms = (gemms[:-1], gemms[-1])          # (plain plans, fused last-layer + head plan)
             ha, hc = ws.h["actor"][-1], ws.h["critic"][-1]
@@ -334,16 +344,24 @@ class PPO:
         self.actor_critic.reset(dones)
 
     def compute_returns(self, last_critic_obs):
+        with nvtx_range("hg.ppo.compute_returns"):
+            return self._compute_returns(last_critic_obs)
+
+    def _compute_returns(self, last_critic_obs):
         ac, st = self.actor_critic, self.storage
         eng = ac.engine()
         N = last_critic_obs.shape[0]
         T = st.num_transitions_per_env
-        if st._priv_all is not None and N == st.num_envs and last_critic_obs.data_ptr() == st._priv_all[T].data_ptr():
+        k_in, frames = last_critic_obs.shape[1], None
+        if st.ring_enabled and N == st.num_envs and last_critic_obs.data_ptr() == st._ring_priv.ptr32(st.step):
+            rp = st._ring_priv                        # the critic window of the last row, read in place from the ring
+            c16, k_in, frames = rp.view16(st.step), rp.K16, {"critic": (rp.width, rp.pitch16)}
+        elif st._priv_all is not None and N == st.num_envs and last_critic_obs.data_ptr() == st._priv_all[T].data_ptr():
             c16 = st.slot(T)[3]                       # written (with its shadow) by a bound env
         else:
             c16 = ac._to_bf16(last_critic_obs, "last_critic")
         ws = ac.workspace(N)
-        eng.forward_hidden((ac.net_critic,), {"critic": c16}, {"critic": last_critic_obs.shape[1]}, ws, N)
+        eng.forward_hidden((ac.net_critic,), {"critic": c16}, {"critic": k_in}, ws, N, frames=frames)
         last_values = torch.empty(N, 1, device=st.values.device)
         ac._head_rollout(ws, N, False, None, dict(values=last_values))
         st.compute_returns(last_values, self.gamma, self.lam)
@@ -360,6 +378,10 @@ class PPO:
                          gb_hidden=ptr(flat.grad_view(top.bias)))
 
     def update(self):
+        with nvtx_range("hg.ppo.update"):
+            return self._update()
+
+    def _update(self):
         ac, st = self.actor_critic, self.storage
         eng = ac.engine()
         flat = ac.flat
@@ -376,18 +398,38 @@ class PPO:
         if self.perm_override is not None:
             indices = self.perm_override.to(indices.device).long().contiguous()
         total = nmb * M
+        ring = st.ring_enabled
         # gather the bf16 observation rows of all minibatches once (both epochs reuse them)
-        if self._perm_bufs is None or self._perm_bufs[0].shape[0] != total:
-            self._perm_bufs = (torch.empty(total, st.obs_ld, dtype=torch.bfloat16, device=indices.device),
-                               torch.empty(total, st.priv_ld, dtype=torch.bfloat16, device=indices.device)
-                               if st.privileged_observations is not None else None)
-        xperm, pperm = self._perm_bufs
-        check(lib.hg_gather_rows_bf16(ptr(st.obs16), st.obs_ld, ptr(indices), total, ptr(xperm), current_stream()))
-        if pperm is not None:
-            check(lib.hg_gather_rows_bf16(ptr(st.priv16), st.priv_ld, ptr(indices), total, ptr(pperm), current_stream()))
+        if ring:
+            ro, rp = st._ring_obs, st._ring_priv
+            k_obs, k_priv = ro.K16, rp.K16
+            ld_o, ld_p = _round_up(k_obs, LD_ALIGN), _round_up(k_priv, LD_ALIGN)
+            frames = {"actor": (ro.width, ro.pitch16), "critic": (rp.width, rp.pitch16), "base_lin_vel": (ro.width, ro.pitch16)}
         else:
+            k_obs, k_priv, ld_o, ld_p, frames = st.obs_cols, st.priv_cols, st.obs_ld, st.priv_ld, None
+        if self._perm_bufs is None or self._perm_bufs[0].shape != (total, ld_o) or (self._perm_bufs[1] is not None and self._perm_bufs[1].shape[1] != ld_p):
+            self._perm_bufs = (torch.zeros(total, ld_o, dtype=torch.bfloat16, device=indices.device),
+                               torch.zeros(total, ld_p, dtype=torch.bfloat16, device=indices.device) if st._has_priv else None)
+        xperm, pperm = self._perm_bufs
+        if ring:
+            # rows straight out of the archive ring: window of (t, n), frames older than the row's last reset zero, bf16 at the
+            # frame pitch; the lin-vel regression targets critic_obs[:, 53:56] (rollout_storage.py:164) in storage order
+            T_, N_ = st.num_transitions_per_env, st.num_envs
+            if self._lv_targets is None or self._lv_targets.shape[0] != T_ * N_:
+                self._lv_targets = torch.empty(T_ * N_, 4, device=indices.device)
+            fv = ptr(st.ring_first_valid)
+            check(lib.hg_ring_gather(C.byref(ro.c), N_, fv, ptr(indices), total, ptr(xperm), ld_o, 1, None, 0, current_stream()))
+            check(lib.hg_ring_gather(C.byref(rp.c), N_, fv, ptr(indices), total, ptr(pperm), ld_p, 1, None, 0, current_stream()))
+            check(lib.hg_ring_gather(C.byref(rp.c), N_, fv, None, T_ * N_, None, 0, 0, ptr(self._lv_targets), 53, current_stream()))
+            cobs_ptr, ld_cobs, lv_col = ptr(self._lv_targets), 4, 0
+        else:
+            check(lib.hg_gather_rows_bf16(ptr(st.obs16), st.obs_ld, ptr(indices), total, ptr(xperm), current_stream()))
+            if pperm is not None:
+                check(lib.hg_gather_rows_bf16(ptr(st.priv16), st.priv_ld, ptr(indices), total, ptr(pperm), current_stream()))
+            cobs = st.privileged_observations if st._has_priv else st.observations
+            cobs_ptr, ld_cobs, lv_col = ptr(cobs), cobs.shape[-1], 53
+        if pperm is None:
             pperm = xperm
-        cobs = st.privileged_observations if st.privileged_observations is not None else st.observations
         ws = ac.workspace(M, with_grads=True)
         nets = (ac.net_actor, ac.net_critic, ac.net_linvel)
         n_updates = nep * nmb
@@ -397,22 +439,24 @@ class PPO:
         slot = 0
         for epoch in range(nep):
             for i in range(nmb):
+                if _lib.NVTX:
+                    torch.cuda.nvtx.range_push(f"hg.minibatch e{epoch} m{i}")
                 x = xperm[i * M:(i + 1) * M]
                 p = pperm[i * M:(i + 1) * M]
                 idx = indices[i * M:(i + 1) * M]
                 if self.torch_rng:
                     torch.randn(M, A, device=indices.device)     # the reference's unused sample() (ppo.py:154) burns RNG
                 inputs = {"actor": x, "critic": p, "base_lin_vel": x}
-                cols = {"actor": st.obs_cols, "critic": st.priv_cols, "base_lin_vel": st.obs_cols}
-                eng.forward_hidden(nets, inputs, cols, ws, M)
+                cols = {"actor": k_obs, "critic": k_priv, "base_lin_vel": k_obs}
+                eng.forward_hidden(nets, inputs, cols, ws, M, frames=frames)
                 if self.sym_loss:
-                    sym = self._sym_forward(x, ws, M)
+                    sym = self._sym_forward(x, ws, M, frames)
                 largs = HgLossArgs(
                     actor=self._head_net(ac.net_actor, ws, flat), critic=self._head_net(ac.net_critic, ws, flat),
                     linvel=self._head_net(ac.net_linvel, ws, flat), rows=M, A=A, idx=ptr(idx),
                     actions=ptr(st.actions), old_mu=ptr(st.mu), old_sigma=ptr(st.sigma),
                     old_log_prob=ptr(st.actions_log_prob), advantages=ptr(st.advantages), returns=ptr(st.returns),
-                    old_values=ptr(st.values), critic_obs=ptr(cobs), ld_cobs=cobs.shape[-1], lv_col=53,
+                    old_values=ptr(st.values), critic_obs=cobs_ptr, ld_cobs=ld_cobs, lv_col=lv_col,
                     std=ptr(ac.std.data), g_std=ptr(flat.grad_view(ac.std)), clip_param=float(self.clip_param),
                     value_loss_coef=float(self.value_loss_coef), entropy_coef=float(self.entropy_coef),
                     lin_vel_coef=float(self.base_lin_vel_coef),
@@ -420,14 +464,16 @@ class PPO:
                     inv_world=1.0 / self.world_size, stats=ptr(flat.stats))
                 check(lib.hg_ppo_head_loss(C.byref(largs), current_stream()))
                 if self.sym_loss:
-                    self._sym_backward(sym, ws, M)
-                eng.backward_hidden(nets, inputs, cols, ws, M)
+                    self._sym_backward(sym, ws, M, frames)
+                eng.backward_hidden(nets, inputs, cols, ws, M, frames=frames)
                 if self.world_size > 1:
                     # the only collective of the path: SUM over ranks of [gradients | KL and loss sums]
                     torch.distributed.all_reduce(flat.g)
                 self.optimizer.fused_step(rows_global=M * self.world_size, max_grad_norm=self.max_grad_norm,
                                           adaptive=adaptive, desired_kl=self.desired_kl, loss_log=loss_log, log_slot=slot)
                 slot += 1
+                if _lib.NVTX:
+                    torch.cuda.nvtx.range_pop()
         self.last_update_enqueue_ms = (time.perf_counter() - t_host0) * 1e3    # host time to enqueue the whole update
         log = loss_log.cpu()                                      # the single host sync of update()
         self.last_update_log = log
@@ -446,24 +492,44 @@ class PPO:
         return mean_value_loss, mean_surrogate_loss, sym_loss, mean_base_lin_vel_loss
 
     # ------------------------------------------------------------------ mirror-symmetry loss (ppo.py:197-202)
-    def _sym_forward(self, x, ws, M):
+    def _sym_perm(self, frames):
+        """(source column, sign) of the mirrored observation row, in the column layout of the minibatch rows: packed
+        (f*width + c) for the stacked format, frame-pitched (f*pitch + c, pad columns -> 0) for the history ring."""
+        if frames is None:
+            return self._obs_src, self._obs_sign, self.storage.obs_cols
+        width, pitch = frames["actor"]
+        key = (width, pitch)
+        if getattr(self, "_sym_pitched", None) is None or self._sym_pitched[0] != key:
+            src, sign = self._obs_src.cpu().tolist(), self._obs_sign.cpu().tolist()
+            nf = len(src) // width
+            psrc, psign = list(range(nf * pitch)), [0.0] * (nf * pitch)
+            for j, (sj, gj) in enumerate(zip(src, sign)):
+                f, c = divmod(j, width)
+                fs, cs = divmod(sj, width)
+                psrc[f * pitch + c], psign[f * pitch + c] = fs * pitch + cs, gj
+            dev = self._obs_src.device
+            self._sym_pitched = (key, torch.tensor(psrc, dtype=torch.int32, device=dev), torch.tensor(psign, dtype=torch.float32, device=dev), nf * pitch)
+        return self._sym_pitched[1:]
+
+    def _sym_forward(self, x, ws, M, frames=None):
         """mirror_obs = obs @ obs_perm_mat, mirror_act = actor(mirror_obs), sym_loss = mean((mu - mirror_act @ act_perm_mat)^2):
         the mirrored rows go through the same grouped tcgen05 GEMMs as the batch; returns what `_sym_backward` needs."""
         from .engine import Workspace
         ac, st, lib = self.actor_critic, self.storage, self._lib
         eng, A, dev = ac.engine(), ac.num_actions, x.device
-        if self._sym_ws is None or self._sym_ws[0].rows != M:
+        obs_src, obs_sign, k_obs = self._sym_perm(frames)
+        if self._sym_ws is None or self._sym_ws[0].rows != M or self._sym_ws[1].shape[1] != x.shape[1]:
             f32 = lambda *s: torch.empty(*s, device=dev)
-            self._sym_ws = (Workspace((ac.net_actor,), M, dev, True), torch.empty(M, st.obs_ld, dtype=torch.bfloat16, device=dev),
+            self._sym_ws = (Workspace((ac.net_actor,), M, dev, True), torch.zeros(M, x.shape[1], dtype=torch.bfloat16, device=dev),
                             f32(M, A), f32(M, A), f32(M, A), f32(M, A))
         ws_m, xm, mu, mirror, dmu, dmirror = self._sym_ws
         if getattr(self, "_sym_slot", None) is None or self._sym_slot >= self._sym_sums.numel():
             self._sym_sums = torch.zeros(self.num_learning_epochs * self.num_mini_batches, dtype=torch.float64, device=dev)
             self._sym_slot = 0
         s = current_stream()
-        check(lib.hg_permute_cols_bf16(ptr(x), x.stride(0), M, st.obs_cols, ptr(self._obs_src), ptr(self._obs_sign), ptr(xm),
-                                       xm.stride(0), s))
-        eng.forward_hidden((ac.net_actor,), {"actor": xm}, {"actor": st.obs_cols}, ws_m, M)
+        check(lib.hg_permute_cols_bf16(ptr(x), x.stride(0), M, k_obs, ptr(obs_src), ptr(obs_sign), ptr(xm), xm.stride(0), s))
+        afr = {"actor": frames["actor"]} if frames else None
+        eng.forward_hidden((ac.net_actor,), {"actor": xm}, {"actor": k_obs}, ws_m, M, frames=afr)
         la = ac.net_actor.linears[-1]
         for h, out in ((ws.h["actor"][-1], mu), (ws_m.h["actor"][-1], mirror)):
             check(lib.hg_head_forward(ptr(h), h.stride(0), h.shape[1], ptr(la.weight.data), ptr(la.bias.data), A, M, ptr(out), s))
@@ -473,7 +539,7 @@ class PPO:
         self._sym_slot += 1
         return ws_m, xm, dmu, dmirror
 
-    def _sym_backward(self, sym, ws, M):
+    def _sym_backward(self, sym, ws, M, frames=None):
         """Adds the symmetry term's gradient: through the batch's own forward (d/d mu, accumulated onto the dZ the loss
         kernel just wrote) and through the mirrored forward (its own backward pass over the actor)."""
         ws_m, xm, dmu, dmirror = sym
@@ -484,4 +550,6 @@ class PPO:
         for h, d, dz, acc in ((ws.h["actor"][-1], dmu, ws.dz["actor"][-1], 1), (ws_m.h["actor"][-1], dmirror, ws_m.dz["actor"][-1], 0)):
             check(lib.hg_head_backward(ptr(h), h.stride(0), h.shape[1], ptr(la.weight.data), ac.num_actions, ptr(d), M, acc,
                                        ptr(dz), dz.stride(0), ptr(gW), ptr(gb), ptr(gbh), s))
-        ac.engine().backward_hidden((ac.net_actor,), {"actor": xm}, {"actor": st.obs_cols}, ws_m, M)
+        k_obs = self._sym_perm(frames)[2]
+        ac.engine().backward_hidden((ac.net_actor,), {"actor": xm}, {"actor": k_obs}, ws_m, M,
+                                    frames={"actor": frames["actor"]} if frames else None)

@@ -1,13 +1,16 @@
 // Fused env-step tensor math: one launch replaces the several hundred ATen launches of
 // XBotLFreeEnv.post_physics_step (reference humanoid/envs/custom/humanoid_env.py:780-806 and callees).
 //
-// 32 envs per 128-thread block.  The scalar math runs one THREAD per env (32x fewer warp instructions than a
-// warp per env), split over the block's four warps by role (observation frames / joint rewards / feet rewards /
-// base-motion rewards) so each env's dependent-latency chain is short; the new frames are assembled in shared
-// memory and all four warps then stream the history shift obs_next[n,:] = clip([obs_prev[n,So:], new_frame])
-// with fully coalesced 128-byte accesses (15 x So floats written, 14 x So read per env; same for the 3-frame
-// critic stack).
-// Algorithmic HBM bytes per env-step (D=12): 4*(47*29 + 73*5) = 6,912 B history + ~0.9 KB state.
+// The scalar math runs one THREAD per env (32x fewer warp instructions than a warp per env), split over four "role"
+// warps of the block (observation frames / joint rewards / feet rewards / base-motion rewards) so each env's
+// dependent-latency chain is short; the new frames are assembled in shared memory.  Two history formats:
+//   * stacked (generic API, `obs_prev` -> `obs_next`): 16 envs per 512-thread block; warps 4-15 stream the history
+//     shift obs_next[n,:] = clip([obs_prev[n,So:], new_frame]) with coalesced 128-byte accesses while warps 0-3 do the
+//     math (15 x So floats written, 14 x So read per env; same for the 3-frame critic stack).
+//     Algorithmic HBM bytes per env-step (D=12): 4*(47*29 + 73*5) = 6,912 B history + ~0.9 KB state.
+//   * history ring (`ring_obs` / `ring_priv`): 16 or 32 envs per 128-thread block; only the NEWEST frame
+//     is written (fp32 live + fp32 archive + bf16 live), nothing is shifted or re-read; a reset zeroes the env's live
+//     frames in place.  Algorithmic bytes per env-step (D=12): 2*4*(47+73) + 2*(48+80) = 1,216 B frames + ~0.9 KB state.
 //
 // Compiled with -fmad=false: every +,-,*,/ is a separately rounded IEEE op in the reference's order, so all
 // threshold decisions (contacts, resets, dead-bands, feet clearance) are bit-identical to torch-CPU; only
@@ -16,9 +19,7 @@
 
 namespace hg {
 
-constexpr int ENV_PER_BLOCK = 16;       // 16 envs per block -> 256 blocks at 4096 envs (two per SM): twice the loads in flight
-constexpr int ENV_THREADS = 512;       // warps 0-3: per-env math by role; warps 4-15: history streaming
-constexpr int ENV_ROLE_WARPS = 4;
+constexpr int ENV_ROLE_WARPS = 4;       // warps 0-3: per-env math by role; the other warps (stacked format only): history streaming
 constexpr int MAX_FRAME = 160;          // >= So, Sp for D <= 32
 constexpr float TWO_PI_F = 6.2831855f;  // fp32(2*pi)
 constexpr float PI_F = 3.1415927f;
@@ -191,8 +192,9 @@ constexpr int SHIFT_UNIT = 672;   // floats per streaming unit (21 loads per lan
 // dependent-latency chain per env is ~4x shorter), then all 128 threads stream the history rows.
 //   warp 0: observation frames (phase, euler, base-frame velocities, joint terms)      compute_observations :818-887
 //   warp 1: joint-space rewards     warp 2: feet / contact rewards (+ their state)     warp 3: base-motion rewards
-__global__ void __launch_bounds__(ENV_THREADS, 2) env_step_kernel(const __grid_constant__ HgEnvConfig C,
-                                                               const __grid_constant__ HgEnvBuffers B) {
+template <int ENV_PER_BLOCK, int ENV_THREADS, bool RING>
+__global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(const __grid_constant__ HgEnvConfig C,
+                                                                            const __grid_constant__ HgEnvBuffers B) {
   extern __shared__ __align__(16) float s_env[];
   pdl_trigger();
   pdl_wait();
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(ENV_THREADS, 2) env_step_kernel(const __grid_c
   float* T = s_terms + lane;                          // T[k * ENV_PER_BLOCK]
 #define HG_TERM(k, val) T[(k) * ENV_PER_BLOCK] = (val) * C.reward_scale_dt[k]
 
-  if (warp >= ENV_ROLE_WARPS) {
+  if (!RING && warp >= ENV_ROLE_WARPS) {
     // ---------------------------------------------------------------- history shift (:883-887): needs only the reset flag,
     // so these 12 warps stream the 14 old actor frames / 2 old critic frames while warps 0-3 do the per-env math.
     if (doB) {
@@ -494,33 +496,68 @@ __global__ void __launch_bounds__(ENV_THREADS, 2) env_step_kernel(const __grid_c
     B.last_root_vel[(size_t)(n0 + el) * 6 + d] = __ldg(B.root_states + (size_t)(n0 + el) * 13 + 7 + d);
   }
 
-  // ---------------------------------------------------------------- newest frame (+ noise :877) + clip (:654-657), all 16 warps
+  // ---------------------------------------------------------------- newest frame (+ noise :877) + clip (:654-657), all warps
   for (int el = warp; el < envs_here; el += ENV_THREADS / 32) {
     const int ne = n0 + el;
-    {
-      float* next = B.obs_next + (size_t)ne * B.obs_next_ld + (C.frame_stack - 1) * So;
-      const float* fo = s_fobs + el * So;
-      for (int j = lane; j < So; j += 32) {
-        float v = fo[j];
-        const float nv = __ldg(B.noise_scale_vec + j);
-        if (C.noise_level != 0.f) {
-          const float e = B.noise ? __ldg(B.noise + (size_t)ne * So + j) : (nv != 0.f ? env_philox_normal(B.seed, B.counter, ne, j) : 0.f);
-          v = v + e * nv * C.noise_level;
-        }
-        v = clampf(v, -C.clip_obs, C.clip_obs);
-        next[j] = v;
-        if (B.obs16_next)
-          reinterpret_cast<__nv_bfloat16*>(B.obs16_next)[(size_t)ne * B.obs16_next_ld + (C.frame_stack - 1) * So + j] = __float2bfloat16_rn(v);
+    float* fo = s_fobs + el * So;
+    float* fp = s_fpriv + el * Sp;
+    for (int j = lane; j < So; j += 32) {       // final values back into the shared frame (each lane re-reads only its own)
+      float v = fo[j];
+      const float nv = __ldg(B.noise_scale_vec + j);
+      if (C.noise_level != 0.f) {
+        const float e = B.noise ? __ldg(B.noise + (size_t)ne * So + j) : (nv != 0.f ? env_philox_normal(B.seed, B.counter, ne, j) : 0.f);
+        v = v + e * nv * C.noise_level;
       }
+      fo[j] = clampf(v, -C.clip_obs, C.clip_obs);
     }
-    {
-      float* next = B.priv_next + (size_t)ne * B.priv_next_ld + (C.c_frame_stack - 1) * Sp;
-      const float* fp = s_fpriv + el * Sp;
+    for (int j = lane; j < Sp; j += 32) fp[j] = clampf(fp[j], -C.clip_obs, C.clip_obs);
+    __syncwarp();
+    if constexpr (!RING) {
+      float* next = B.obs_next + (size_t)ne * B.obs_next_ld + (C.frame_stack - 1) * So;
+      for (int j = lane; j < So; j += 32) {
+        next[j] = fo[j];
+        if (B.obs16_next)
+          reinterpret_cast<__nv_bfloat16*>(B.obs16_next)[(size_t)ne * B.obs16_next_ld + (C.frame_stack - 1) * So + j] = __float2bfloat16_rn(fo[j]);
+      }
+      float* pnext = B.priv_next + (size_t)ne * B.priv_next_ld + (C.c_frame_stack - 1) * Sp;
       for (int j = lane; j < Sp; j += 32) {
-        const float v = clampf(fp[j], -C.clip_obs, C.clip_obs);
-        next[j] = v;
+        pnext[j] = fp[j];
         if (B.priv16_next)
-          reinterpret_cast<__nv_bfloat16*>(B.priv16_next)[(size_t)ne * B.priv16_next_ld + (C.c_frame_stack - 1) * Sp + j] = __float2bfloat16_rn(v);
+          reinterpret_cast<__nv_bfloat16*>(B.priv16_next)[(size_t)ne * B.priv16_next_ld + (C.c_frame_stack - 1) * Sp + j] = __float2bfloat16_rn(fp[j]);
+      }
+    } else {
+      // history ring: the newest frame into slot ring_row + frames - 1 of live32 / arch32 (fp32) and live16 (bf16 pairs, pad
+      // columns zero); a reset env first gets its previous frames - 1 live slots zeroed (reset_idx :1159-1163) -- the archive
+      // keeps them for the rows of the iteration that still need them (first_valid marks where this row's history starts)
+      const bool reset = s_reset[el] != 0;
+      auto put = [&](const HgHistoryRing& R, const float* frame) {
+        const size_t env_base = (size_t)ne * R.slots;
+        const int slot = B.ring_row + R.frames - 1;
+        if (reset) {
+          float* z32 = R.live32 + (env_base + B.ring_row) * R.width;
+          for (int j = lane; j < (R.frames - 1) * R.width; j += 32) z32[j] = 0.f;
+          uint32_t* z16 = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(R.live16) + (env_base + B.ring_row) * R.pitch16);
+          for (int j = lane; j < (R.frames - 1) * R.pitch16 / 2; j += 32) z16[j] = 0u;
+        }
+        float* l32 = R.live32 + (env_base + slot) * R.width;
+        float* a32 = R.arch32 + (env_base + slot) * R.width;
+        for (int j = lane; j < R.width; j += 32) {
+          const float v = frame[j];
+          l32[j] = v;
+          a32[j] = v;
+        }
+        uint32_t* l16 = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(R.live16) + (env_base + slot) * R.pitch16);
+        for (int j = lane; j < R.pitch16 / 2; j += 32) {
+          const float lo = 2 * j < R.width ? frame[2 * j] : 0.f, hi = 2 * j + 1 < R.width ? frame[2 * j + 1] : 0.f;
+          l16[j] = pack_bf16x2(lo, hi);
+        }
+      };
+      put(B.ring_obs, fo);
+      put(B.ring_priv, fp);
+      if (lane == 0) {
+        const int hs = reset ? B.ring_row : B.ring_hist_start[ne];
+        B.ring_hist_start[ne] = hs;
+        B.ring_first_valid[(size_t)B.ring_row * C.num_envs + ne] = hs;
       }
     }
   }
@@ -576,21 +613,41 @@ extern "C" int hg_env_step(const HgEnvConfig* cfg, const HgEnvBuffers* buf, void
            "hg_env_step: at most 4 termination / penalised bodies");
   HG_CHECK(cfg->frame_stack >= 1 && cfg->c_frame_stack >= 1, "hg_env_step: frame stacks");
   HG_CHECK((cfg->phases & (HG_ENV_PHASE_REWARD | HG_ENV_PHASE_OBS)) != 0, "hg_env_step: phases must select REWARD and/or OBS");
-  HG_CHECK(buf->obs_prev != buf->obs_next && buf->priv_prev != buf->priv_next, "hg_env_step: history in/out must not alias");
+  const bool ring = buf->ring_obs.live32 != nullptr;
+  HG_CHECK(ring || (buf->obs_prev != buf->obs_next && buf->priv_prev != buf->priv_next), "hg_env_step: history in/out must not alias");
   HG_CHECK(buf->root_states && buf->dof_state && buf->contact_forces && buf->rigid_state && buf->commands && buf->torques &&
                buf->rand_push_force && buf->rand_push_torque && buf->env_frictions && buf->body_mass && buf->default_dof_pos &&
                buf->noise_scale_vec && buf->actions && buf->last_actions && buf->last_last_actions && buf->last_dof_vel &&
                buf->last_root_vel && buf->feet_air_time && buf->last_contacts && buf->feet_height && buf->last_feet_z &&
-               buf->ref_dof_pos && buf->episode_length_buf && buf->episode_sums && buf->obs_prev && buf->priv_prev &&
-               buf->obs_next && buf->priv_next && buf->rew_buf && buf->reset_buf && buf->time_out_buf,
+               buf->ref_dof_pos && buf->episode_length_buf && buf->episode_sums && buf->rew_buf && buf->reset_buf && buf->time_out_buf,
            "hg_env_step: null buffer");
+  HG_CHECK(ring || (buf->obs_prev && buf->priv_prev && buf->obs_next && buf->priv_next), "hg_env_step: null history buffer");
+  const int So_ = 11 + 3 * cfg->D, Sp_ = 25 + 4 * cfg->D;
+  if (ring) {
+    const HgHistoryRing* rr[2] = {&buf->ring_obs, &buf->ring_priv};
+    const int width[2] = {So_, Sp_}, frames[2] = {cfg->frame_stack, cfg->c_frame_stack};
+    for (int i = 0; i < 2; ++i) {
+      const HgHistoryRing& R = *rr[i];
+      HG_CHECK(R.live32 && R.live16 && R.arch32, "hg_env_step: history ring %d: null buffer", i);
+      HG_CHECK(R.width == width[i] && R.frames == frames[i] && R.pitch16 >= R.width && R.pitch16 % 8 == 0,
+               "hg_env_step: history ring %d: width %d / frames %d / pitch16 %d do not match the env layout", i, R.width, R.frames, R.pitch16);
+      HG_CHECK(buf->ring_row >= 1 && buf->ring_row + R.frames - 1 < R.slots, "hg_env_step: ring_row %d outside the ring (%d slots)", buf->ring_row, R.slots);
+    }
+    HG_CHECK(buf->ring_first_valid && buf->ring_hist_start, "hg_env_step: the history ring needs first_valid and hist_start");
+  }
   HG_CHECK((buf->store_rewards != nullptr) == (buf->store_dones != nullptr) && (buf->store_rewards != nullptr) == (buf->store_values != nullptr),
            "hg_env_step: store_values / store_rewards / store_dones go together");
   HG_CHECK(!buf->store_rewards || (cfg->phases & HG_ENV_PHASE_REWARD), "hg_env_step: the transition store needs the reward phase");
-  const int blocks = (cfg->num_envs + ENV_PER_BLOCK - 1) / ENV_PER_BLOCK;
-  const int So = 11 + 3 * cfg->D, Sp = 25 + 4 * cfg->D;
-  const size_t smem = (size_t)(ENV_PER_BLOCK * (So + Sp) + HG_NUM_REWARDS * ENV_PER_BLOCK + 4 * ENV_PER_BLOCK) * 4;
-  HG_CUDA(launch_kernel(env_step_kernel, dim3(blocks), dim3(ENV_THREADS), smem, reinterpret_cast<cudaStream_t>(stream), 1, *cfg, *buf));
+  const int So = So_, Sp = Sp_;
+  auto smem_for = [&](int epb) { return (size_t)(epb * (So + Sp) + HG_NUM_REWARDS * epb + 4 * epb) * 4; };
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!ring) {
+    HG_CUDA(launch_kernel(env_step_kernel<16, 512, false>, dim3((cfg->num_envs + 15) / 16), dim3(512), smem_for(16), st, 1, *cfg, *buf));
+  } else if (cfg->num_envs <= 2 * 16 * num_sms()) {      // up to ~two blocks per SM: 16 envs per block (more SMs, shorter per-SM chains)
+    HG_CUDA(launch_kernel(env_step_kernel<16, 128, true>, dim3((cfg->num_envs + 15) / 16), dim3(128), smem_for(16), st, 1, *cfg, *buf));
+  } else {                                               // many envs: 32 per block (every lane of the role warps busy)
+    HG_CUDA(launch_kernel(env_step_kernel<32, 128, true>, dim3((cfg->num_envs + 31) / 32), dim3(128), smem_for(32), st, 1, *cfg, *buf));
+  }
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;

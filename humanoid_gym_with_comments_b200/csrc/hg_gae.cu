@@ -4,15 +4,16 @@
 // Layout: all tensors are [T, N] with N contiguous, so one thread per env gives perfectly coalesced
 // 128-byte warp accesses at every time step.  The recurrence is sequential in t by construction (and
 // must stay so to be bit-exact with the reference's fp32 op order), so latency is hidden by staging a
-// whole [CHUNK_T x 128] slab of rewards/values/dones in shared memory with cp.async before each run of
-// CHUNK_T dependent steps.  HBM traffic: 9 B read + 8 B written per (t, env) in the scan, 4 B + 4 B in
-// the normalisation pass.
+// whole [CHUNK_T x block] slab of rewards/values/dones in shared memory with cp.async before each run of
+// CHUNK_T dependent steps: with CHUNK_T = 64 the XBot horizon (60) is ONE global round trip per thread.  Blocks are a
+// single warp until there are enough envs to give every SM several warps (4096 envs: 128 blocks instead of the 32
+// 128-thread blocks of round 1, which left 116 of the 148 SMs idle).  HBM traffic: 9 B read + 8 B written per (t, env)
+// in the scan, 4 B + 4 B in the normalisation pass.
 #include "hg_common.cuh"
 
 namespace hg {
 
-constexpr int GAE_THREADS = 128;
-constexpr int GAE_CHUNK = 16;
+constexpr int GAE_CHUNK = 64;
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
@@ -21,6 +22,7 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+template <int GAE_THREADS>
 __global__ void __launch_bounds__(GAE_THREADS) gae_scan_kernel(const float* __restrict__ rewards,
                                                                const float* __restrict__ values,
                                                                const uint8_t* __restrict__ dones,
@@ -124,7 +126,10 @@ extern "C" int hg_gae_returns(const float* rewards, const float* values, const u
   HG_CHECK((reinterpret_cast<uintptr_t>(advantages) & 15) == 0, "advantages must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   HG_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), s));
-  HG_CUDA(launch_kernel(gae_scan_kernel, dim3((N + GAE_THREADS - 1) / GAE_THREADS), dim3(GAE_THREADS), 0, s, 1, rewards, values, dones, last_values, gamma, lam, T, N, returns, advantages, scratch));
+  if (N <= 32 * 4 * num_sms())       // up to 4 warps per SM: one warp per block, as many SMs as possible
+    HG_CUDA(launch_kernel(gae_scan_kernel<32>, dim3((N + 31) / 32), dim3(32), 0, s, 1, rewards, values, dones, last_values, gamma, lam, T, N, returns, advantages, scratch));
+  else
+    HG_CUDA(launch_kernel(gae_scan_kernel<64>, dim3((N + 63) / 64), dim3(64), 0, s, 1, rewards, values, dones, last_values, gamma, lam, T, N, returns, advantages, scratch));
   HG_LAUNCH_CHECK();
   const long long count = (long long)T * N;
   long long blocks = (count / 4 + 255) / 256;

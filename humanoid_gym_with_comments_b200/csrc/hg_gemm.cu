@@ -72,6 +72,7 @@ struct DevProblem {
   long long ldact;
   float* colsum;
   int colsum_off;      // first slot of this problem in the CTA's shared column-sum array
+  int out_fs, out_fd;  // HG_EPI_ATOMIC_F32: frame remap of the output columns (0 = off), see HgGemmProblem
 };
 
 struct alignas(64) GroupParams {
@@ -277,11 +278,17 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
     for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
     __syncwarp();
     const int row_base = row - lane;
-    const bool col_ok = n0 + lane < q.N;
+    bool col_ok = n0 + lane < q.N;
+    int ocol = n0 + lane;
+    if (q.out_fs) {      // frame-pitched input columns -> the packed columns of the weight gradient; pad columns are dropped
+      const int f = ocol / q.out_fs, c = ocol - f * q.out_fs;
+      col_ok = col_ok && c < q.out_fd;
+      ocol = f * q.out_fd + c;
+    }
 #pragma unroll 8
     for (int i = 0; i < 32; ++i) {
       if (col_ok && row_base + i < q.M)
-        atomicAdd(reinterpret_cast<float*>(q.out) + (long long)(row_base + i) * q.ldo + n0 + lane, tile[i * 33 + lane]);
+        atomicAdd(reinterpret_cast<float*>(q.out) + (long long)(row_base + i) * q.ldo + ocol, tile[i * 33 + lane]);
     }
     __syncwarp();
   } else if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16) {
@@ -1184,6 +1191,10 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
     q.out = h.out; q.ldo = h.ldo; q.bias = h.bias;
     q.act = reinterpret_cast<const __nv_bfloat16*>(h.act); q.ldact = h.ldact; q.colsum = h.colsum;
     q.colsum_off = colsum_cols;
+    HG_CHECK((h.out_frame_src == 0 && h.out_frame_dst == 0) ||
+                 (epilogue == HG_EPI_ATOMIC_F32 && h.out_frame_dst >= 1 && h.out_frame_src >= h.out_frame_dst),
+             "problem %d: out_frame_src / out_frame_dst need the atomic epilogue and src >= dst >= 1", g);
+    q.out_fs = h.out_frame_src; q.out_fd = h.out_frame_dst;
     if (epilogue == HG_EPI_DELU_BF16 && h.colsum) colsum_cols += (h.N + 31) & ~31;
     HG_CHECK(colsum_cols <= HG_MAX_COLSUM_COLS, "problem %d: a DELU launch can column-sum at most %d columns in total", g, HG_MAX_COLSUM_COLS);
     if (epilogue == HG_EPI_BIAS_ELU_BF16 || epilogue == HG_EPI_DELU_BF16 || epilogue == HG_EPI_BIAS_BF16)

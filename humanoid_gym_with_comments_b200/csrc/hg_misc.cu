@@ -44,13 +44,18 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ src, int chunks_per
 }
 
 __global__ void cast_weight_kernel(const float* __restrict__ src, int rows, int cols, __nv_bfloat16* __restrict__ dst,
-                                   long long ld) {
+                                   long long ld, int src_frame, int dst_frame) {
   pdl_trigger();
   pdl_wait();
   const long long total = (long long)rows * ld;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / ld), c = (int)(i % ld);
-    dst[i] = __float2bfloat16_rn(c < cols ? src[(long long)r * cols + c] : 0.f);
+    int sc = c;                       // source column of destination column c (-1: padding)
+    if (src_frame) {
+      const int f = c / dst_frame, k = c - f * dst_frame;
+      sc = k < src_frame ? f * src_frame + k : -1;
+    }
+    dst[i] = __float2bfloat16_rn(sc >= 0 && sc < cols ? src[(long long)r * cols + sc] : 0.f);
   }
 }
 
@@ -99,13 +104,16 @@ extern "C" int hg_gather_rows_bf16(const void* src, int64_t ld, const int64_t* i
   return HG_OK;
 }
 
-extern "C" int hg_cast_weight_bf16(const float* src, int rows, int cols, void* dst, int64_t ld, void* stream) {
+extern "C" int hg_cast_weight_bf16(const float* src, int rows, int cols, void* dst, int64_t ld, int src_frame, int dst_frame, void* stream) {
   using namespace hg;
   HG_CHECK(src && dst && rows > 0 && cols > 0 && ld >= cols, "hg_cast_weight_bf16: bad arguments");
+  HG_CHECK((src_frame == 0 && dst_frame == 0) || (src_frame >= 1 && dst_frame >= src_frame && cols % src_frame == 0 &&
+                                                  ld >= (int64_t)(cols / src_frame) * dst_frame),
+           "hg_cast_weight_bf16: bad frame remap %d -> %d for %d columns (ld %lld)", src_frame, dst_frame, cols, (long long)ld);
   const long long total = (long long)rows * ld;
   int blocks = (int)((total + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  HG_CUDA(launch_kernel(cast_weight_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, src, rows, cols, reinterpret_cast<__nv_bfloat16*>(dst), ld));
+  HG_CUDA(launch_kernel(cast_weight_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1, src, rows, cols, reinterpret_cast<__nv_bfloat16*>(dst), (long long)ld, src_frame, dst_frame));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;

@@ -107,9 +107,14 @@ __global__ void __launch_bounds__(256) adam_kernel(HgAdamArgs a, const __grid_co
       const long long off = i - tab.s[s].param_offset;
       if (off >= 0 && off < (long long)tab.s[s].rows * tab.s[s].cols) {
         const unsigned o32 = (unsigned)off, cols = (unsigned)tab.s[s].cols;      // a weight matrix has < 2^32 elements
-        const unsigned r = o32 / cols, c = o32 - r * cols;
+        const unsigned r = o32 / cols;
+        unsigned c = o32 - r * cols;
+        if (tab.s[s].src_frame) {      // frame-pitched copy (history-ring first layers): f*src_frame + k -> f*dst_frame + k
+          const unsigned f = c / (unsigned)tab.s[s].src_frame;
+          c += f * (unsigned)(tab.s[s].dst_frame - tab.s[s].src_frame);
+        }
         reinterpret_cast<__nv_bfloat16*>(tab.s[s].dst)[(long long)r * tab.s[s].ld + c] = __float2bfloat16_rn(p);
-        break;
+        // no break: a first-layer weight has two shadows (packed and frame-pitched)
       }
     }
   }

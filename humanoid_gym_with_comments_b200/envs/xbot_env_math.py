@@ -330,7 +330,7 @@ class XBotEnvMath:
              obs_out: Optional[torch.Tensor] = None, priv_out: Optional[torch.Tensor] = None,
              obs16_out: Optional[torch.Tensor] = None, priv16_out: Optional[torch.Tensor] = None,
              raw_actions: Optional[torch.Tensor] = None, clip_actions: float = 18.0, store=None,
-             root_vel_prepush: Optional[torch.Tensor] = None):
+             root_vel_prepush: Optional[torch.Tensor] = None, ring=None):
         """One fused post-physics step on the Isaac-Gym-shaped tensors in `sim` (keys: root_states, dof_state,
         contact_forces, rigid_state, commands, torques, rand_push_force, rand_push_torque, env_frictions, body_mass;
         optional `actions` [N,D] = the actions applied this step, copied into `self.actions` first).
@@ -339,22 +339,36 @@ class XBotEnvMath:
         next storage slot, instead of the internal double buffer.
         `store` = (values, rewards_out, dones_out, gamma): also write the learner's transition record
         rewards_out = rew + gamma * values * time_out, dones_out = reset (what PPO.process_env_step would store).
+        `ring` = (storage, row): history-ring format -- only the newest frames are written, into the
+        learner storage's rings as the last slot of `row`'s window; the returned observations are strided VIEWS of the
+        live ring (the reference's obs_buf / privileged_obs_buf, bit for bit), nothing is shifted or copied.
         Returns (obs_buf, privileged_obs_buf, rew_buf, reset_buf, time_out_buf)."""
         acts = sim.get("actions")
         if acts is not None:
             self.actions.copy_(acts)
         nxt = 1 - self._cur
-        obs_next = obs_out if obs_out is not None else self._obs[nxt]
-        priv_next = priv_out if priv_out is not None else self._priv[nxt]
         b = self._buffers_for(sim)
+        if ring is not None:
+            st, row = ring
+            b.ring_obs, b.ring_priv, b.ring_row = st._ring_obs.c, st._ring_priv.c, row
+            b.ring_first_valid, b.ring_hist_start = ptr(st.ring_first_valid), ptr(st.ring_hist_start)
+            obs_next, priv_next = st._ring_obs.view32(row), st._ring_priv.view32(row)
+            obs_out = obs_next                      # (not the internal double buffer: `_cur` stays)
+            if phases & 2:
+                st._ring_version += 1
+        else:
+            b.ring_obs.live32 = None
+            obs_next = obs_out if obs_out is not None else self._obs[nxt]
+            priv_next = priv_out if priv_out is not None else self._priv[nxt]
         b.noise = ptr(noise)
         b.actions_in, b.clip_actions = ptr(raw_actions), clip_actions   # fused clip of step() (:633-635)
         self.step_counter += 1
         b.counter = self.step_counter
-        b.obs_prev, b.obs_prev_ld = ptr(self.obs_buf), self.obs_buf.stride(0)
-        b.priv_prev, b.priv_prev_ld = ptr(self.privileged_obs_buf), self.privileged_obs_buf.stride(0)
-        b.obs_next, b.obs_next_ld = obs_next.data_ptr(), obs_next.stride(0)
-        b.priv_next, b.priv_next_ld = priv_next.data_ptr(), priv_next.stride(0)
+        if ring is None:
+            b.obs_prev, b.obs_prev_ld = ptr(self.obs_buf), self.obs_buf.stride(0)
+            b.priv_prev, b.priv_prev_ld = ptr(self.privileged_obs_buf), self.privileged_obs_buf.stride(0)
+            b.obs_next, b.obs_next_ld = obs_next.data_ptr(), obs_next.stride(0)
+            b.priv_next, b.priv_next_ld = priv_next.data_ptr(), priv_next.stride(0)
         if obs16_out is not None:
             b.obs16_next, b.obs16_next_ld = obs16_out.data_ptr(), obs16_out.stride(0)
         else:
@@ -438,6 +452,7 @@ class SyntheticXBotEnv:
         self.course_gain, self.course_ratio = 1.0, 1.0
         self._i = 0
         self._storage = None
+        self._ring = False
         self._host_pool = None
         self.obs_buf, self.privileged_obs_buf = self.math.obs_buf, self.math.privileged_obs_buf
         self.rew_buf, self.reset_buf = self.math.rew_buf, self.math.reset_buf
@@ -492,14 +507,32 @@ class SyntheticXBotEnv:
                 self._copy_done[slot].record(self._copy_stream)
                 self._next_chunk += 1
 
-    def bind_storage(self, storage, gamma: Optional[float] = None):
-        """Let `step()` write the next observations (fp32 + bf16 shadow) straight into the learner's next storage
-        slot: `PPO.act` then finds them in place and launches no ingest / copy (replaces, together with the env
-        kernel, rollout_storage.py:90-91).  With `gamma` (the learner's discount) the env kernel also stores the
-        transition's bootstrapped reward and done flag (ppo.py:129-133), and `PPO.process_env_step` launches nothing
-        when it is handed this env's reward / reset buffers.  Pass None to unbind."""
+    def bind_storage(self, storage, gamma: Optional[float] = None, ring: bool = True):
+        """Let `step()` write the next observations straight into the learner's storage: `PPO.act` then finds them in
+        place and launches no ingest / copy (replaces, together with the env kernel, rollout_storage.py:90-91).
+        ring=True (default): history-ring format -- the storage keeps ONE copy of every frame
+        (`RolloutStorage.enable_ring`), the env writes only the newest frame per step and returns strided views of the
+        ring; ring=False: the stacked format (fp32 slot + bf16 shadow of the whole 705 / 219-wide row every step).
+        With `gamma` (the learner's discount) the env kernel also stores the transition's bootstrapped reward and done
+        flag (ppo.py:129-133), and `PPO.process_env_step` launches nothing when it is handed this env's reward / reset
+        buffers.  Pass None to unbind."""
+        old = self._storage
+        if old is not None and old.ring_enabled and (storage is not old or not ring):
+            # hand the current window back to the env's own stacked buffers before leaving the ring
+            self.math._obs[self.math._cur].copy_(self.obs_buf)
+            self.math._priv[self.math._cur].copy_(self.privileged_obs_buf)
+            self.math.obs_buf, self.math.privileged_obs_buf = self.math._obs[self.math._cur], self.math._priv[self.math._cur]
+            self.obs_buf, self.privileged_obs_buf = self.math.obs_buf, self.math.privileged_obs_buf
+            old.disable_ring()
         self._storage = storage
         self._store_gamma = gamma
+        self._ring = bool(ring) and storage is not None
+        if self._ring and not storage.ring_enabled:
+            cfg = self.cfg
+            storage.enable_ring(cfg.num_single_obs, cfg.frame_stack, cfg.single_num_privileged_obs, cfg.c_frame_stack)
+            storage.ring_import(self.obs_buf, self.privileged_obs_buf, row=storage.step)     # the env's history so far
+            self.obs_buf = self.math.obs_buf = storage._ring_obs.view32(storage.step)
+            self.privileged_obs_buf = self.math.privileged_obs_buf = storage._ring_priv.view32(storage.step)
 
     def get_observations(self):
         return self.obs_buf
@@ -529,8 +562,11 @@ class SyntheticXBotEnv:
         st = self._storage
         kw = dict(raw_actions=actions)                  # clip(+-18) of step() (:633-635) fused in the kernel
         if st is not None and st.step + 1 <= st.num_transitions_per_env:
-            o, p, o16, p16 = st.slot(st.step + 1)      # the env writes the learner's next storage slot (+ bf16 shadow) itself
-            kw.update(obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16)
+            if self._ring:
+                kw.update(ring=(st, st.step + 1))      # one new frame into the learner's history rings
+            else:
+                o, p, o16, p16 = st.slot(st.step + 1)  # the env writes the learner's next storage slot (+ bf16 shadow) itself
+                kw.update(obs_out=o, priv_out=p, obs16_out=o16, priv16_out=p16)
             if getattr(self, "_store_gamma", None) is not None:
                 t = st.step
                 kw["store"] = (st.values[t], st.rewards[t], st.dones[t], float(self._store_gamma))

@@ -21,7 +21,7 @@ extern "C" {
 #define HG_ERR_INVALID (-1)
 #define HG_ERR_CUDA (-2)
 
-#define HG_ABI_VERSION 6
+#define HG_ABI_VERSION 7
 
 const char* hg_last_error(void);
 int hg_abi_version(void);
@@ -64,6 +64,10 @@ typedef struct HgGemmProblem {
   const void* act;    /* bf16 [M,ldact] (HG_EPI_DELU_BF16) */
   int64_t ldact;
   float* colsum;      /* [N] or NULL (HG_EPI_DELU_BF16) */
+  /* HG_EPI_ATOMIC_F32 only, 0 = off: the N columns are frames of out_frame_src columns of which the first out_frame_dst
+   * are real (the rest is padding): column f*out_frame_src + c goes to out[., f*out_frame_dst + c], c >= out_frame_dst is
+   * dropped.  (Weight gradient of a first layer whose input rows come from the frame-pitched history ring.) */
+  int32_t out_frame_src, out_frame_dst;
 } HgGemmProblem;
 
 /* block_n: 128 or 256 (UMMA N of one accumulator tile).
@@ -228,6 +232,9 @@ typedef struct HgBf16Shadow {   /* refresh of one bf16 weight copy after the ste
   int32_t rows, cols;
   void* dst;                    /* bf16 [rows, ld] */
   int64_t ld;
+  /* 0 = plain copy.  Otherwise the cols are frames of src_frame columns and land at a pitch of dst_frame columns:
+   * column f*src_frame + c -> dst column f*dst_frame + c (first-layer weights for the frame-pitched history ring). */
+  int32_t src_frame, dst_frame;
 } HgBf16Shadow;
 
 typedef struct HgAdamArgs {
@@ -244,8 +251,9 @@ typedef struct HgAdamArgs {
 
 int hg_clip_adam_step(const HgAdamArgs* args_host, void* stream);
 
-/* fp32 [rows, cols] (row stride cols) -> bf16 [rows, ld], zero pad; used once at start-up. */
-int hg_cast_weight_bf16(const float* src, int rows, int cols, void* dst, int64_t ld, void* stream);
+/* fp32 [rows, cols] (row stride cols) -> bf16 [rows, ld], zero pad; used once at start-up.  src_frame / dst_frame as in
+ * HgBf16Shadow (0, 0 = plain). */
+int hg_cast_weight_bf16(const float* src, int rows, int cols, void* dst, int64_t ld, int src_frame, int dst_frame, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Env tensor math: one fused launch per env step.  Replaces, in humanoid/envs/custom/humanoid_env.py,
@@ -287,6 +295,26 @@ typedef struct HgEnvConfig {
 #define HG_ENV_PHASE_REWARD 1
 #define HG_ENV_PHASE_OBS 2
 #define HG_ENV_PHASE_ALL 3
+
+/* O(1) history ring (reference: the obs_history / critic_history deques, humanoid_env.py:880-887, and
+ * their zeroing in reset_idx :1159-1163).  Env-major, time-contiguous: the stacked observation of storage row r of env n
+ * is the WINDOW [n, r .. r+frames-1, :] -- a strided view, never re-stacked.  Per env step only the newest frame is
+ * written (slot r+frames-1 for row r): three copies,
+ *   live32  the history exactly as the reference's deque holds it: a reset zeroes the env's previous frames-1 slots in
+ *           place, so live32 windows ARE the reference's obs_buf / privileged_obs_buf (API-visible views);
+ *   live16  the same in bf16 at a 16-byte-aligned frame pitch (pad columns zero): the TMA source of the first layer during
+ *           the rollout (tensor map base = live16 + r*pitch16, row stride = slots*pitch16, extent = frames*pitch16);
+ *   arch32  never zeroed: together with first_valid[r, n] (frames older than that time read as zero) it reproduces
+ *           every row of the iteration for the update's minibatch gather (hg_ring_gather), after later resets too. */
+typedef struct HgHistoryRing {
+  float* live32;    /* [N, slots, width] */
+  void* live16;     /* [N, slots, pitch16] bf16 */
+  float* arch32;    /* [N, slots, width] */
+  int32_t width;    /* So / Sp */
+  int32_t pitch16;  /* width rounded up to 8 */
+  int32_t frames;   /* F / Fc */
+  int32_t slots;    /* rows + frames - 1 */
+} HgHistoryRing;
 
 typedef struct HgEnvBuffers {
   /* Isaac-Gym-shaped inputs */
@@ -346,9 +374,29 @@ typedef struct HgEnvBuffers {
    * the robots (humanoid_env.py:785-791), while base_acc and last_root_vel read the pushed values (:803,1385-1391).
    * NULL: the base-frame velocities come from root_states (no push this step). */
   const float* root_vel_prepush;
+  /* optional history ring (ring_obs.live32 != NULL selects it; obs_prev / obs_next / *16_next are then unused): the
+   * newest frames go to slot ring_row + frames - 1, first_valid[ring_row, n] and hist_start[n] are updated */
+  HgHistoryRing ring_obs, ring_priv;
+  int32_t ring_row;             /* storage row this step produces (1 .. rows-1) */
+  int32_t* ring_first_valid;    /* [rows, N]: first valid frame time of each row (a frame's time = the row it is newest in) */
+  int32_t* ring_hist_start;     /* [N]: first valid frame time of the env's current episode */
 } HgEnvBuffers;
 
 int hg_env_step(const HgEnvConfig* cfg_host, const HgEnvBuffers* buf_host, void* stream);
+
+/* Rows of the iteration out of the history ring (replaces the index gathers of mini_batch_generator,
+ * rollout_storage.py:176-189, and the re-stacking of :880-887 for the API-visible [T, N, F*width] view):
+ *   out row i = stacked frames of flat row idx[i] = r*N + n (idx NULL: i itself), frames older than first_valid[r, n] zero.
+ *   dst_bf16 = 1: bf16 [rows_out, ld_dst] at frame pitch ring->pitch16 (pad columns zero) -- the minibatch operand;
+ *   dst_bf16 = 0: fp32 [rows_out, ld_dst] packed (frame pitch = width) -- the reference's layout.
+ *   lv_out (optional, fp32 [rows_out, 4]): columns lv_col .. lv_col+2 of the packed row (the lin-vel regression target
+ *   critic_obs[:, 53:56], rollout_storage.py:164); dst may then be NULL (targets only). */
+int hg_ring_gather(const HgHistoryRing* ring_host, int num_envs, const int32_t* first_valid, const int64_t* idx,
+                   int64_t rows_out, void* dst, int64_t ld_dst, int dst_bf16, float* lv_out, int lv_col, void* stream);
+/* Start of the next iteration: the window of row `from_row` becomes row 0 (slots [from_row, from_row+frames-1] ->
+ * [0, frames-1] in live32 / live16 / arch32 of every ring), hist_start -= from_row, first_valid[0, n] = hist_start[n]. */
+int hg_ring_rollover(const HgHistoryRing* rings_host, int num_rings, int num_envs, int from_row, int32_t* hist_start,
+                     int32_t* first_valid_row0, void* stream);
 
 /* Pre-physics tensor math of XBotLFreeEnv.step (humanoid_env.py:624-635) and the PD law of _compute_torques
  * (:910-925), the step immediately in front of the hot path, one launch:

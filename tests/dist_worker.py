@@ -10,6 +10,7 @@ Checks the PRODUCT's N > 1 path -- `PPO.update()` with `world_size` ranks, envs 
 Backend: NCCL with one GPU per rank when the box has enough GPUs, otherwise gloo with every rank on cuda:0 (the all-reduce
 call in ppo.py is the same; only the transport differs)."""
 import contextlib
+import datetime
 import io
 import os
 import sys
@@ -25,10 +26,13 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 nccl = torch.cuda.device_count() >= world
 dev = f"cuda:{local}" if nccl else "cuda:0"
 torch.cuda.set_device(dev)
+_timeout = datetime.timedelta(seconds=int(os.environ.get("HG_DIST_TIMEOUT_S", "120")))     # a lost peer raises instead of hanging
 if nccl:
-    dist.init_process_group("nccl", device_id=torch.device(dev))
+    dist.init_process_group("nccl", device_id=torch.device(dev), timeout=_timeout)
 else:
-    dist.init_process_group("gloo")
+    dist.init_process_group("gloo", timeout=_timeout)
+if rank == 0:
+    print("process group up:", "nccl" if nccl else "gloo", flush=True)
 NL, T, A = 512, 8, 12            # envs per rank
 N = NL * world
 

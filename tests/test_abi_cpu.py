@@ -30,7 +30,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hgb200.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes prototypes and header disagree"
-    assert lib.hg_abi_version() == 6
+    assert lib.hg_abi_version() == 7
     assert lib.hg_launch_count() == 0            # nothing launched on a CPU box
 
 
@@ -47,14 +47,14 @@ def test_struct_layouts_match_header_sizes():
     src = '#include "hgb200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(HgGemmProblem),sizeof(HgHeadNet),sizeof(HgLossArgs),sizeof(HgBf16Shadow),sizeof(HgAdamArgs),' \
           'sizeof(HgEnvConfig),sizeof(HgEnvBuffers));printf("%zu %zu %zu\\n",sizeof(HgFusedHead),sizeof(HgCommandArgs),' \
-          'sizeof(HgActionArgs));return 0;}\n'
+          'sizeof(HgActionArgs));printf("%zu\\n",sizeof(HgHistoryRing));return 0;}\n'
     tmp = os.path.join(_lib.BUILD_DIR, "abi_probe")
     os.makedirs(_lib.BUILD_DIR, exist_ok=True)
     open(tmp + ".c", "w").write(src)
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), tmp + ".c", "-o", tmp], check=True)
     sizes = [int(x) for x in subprocess.run([tmp], capture_output=True, text=True, check=True).stdout.split()]
     mirrors = [_lib.HgGemmProblem, _lib.HgHeadNet, _lib.HgLossArgs, _lib.HgBf16Shadow, _lib.HgAdamArgs, _lib.HgEnvConfig,
-               _lib.HgEnvBuffers, _lib.HgFusedHead, _lib.HgCommandArgs, _lib.HgActionArgs]
+               _lib.HgEnvBuffers, _lib.HgFusedHead, _lib.HgCommandArgs, _lib.HgActionArgs, _lib.HgHistoryRing]
     assert sizes == [C.sizeof(m) for m in mirrors]
 
 

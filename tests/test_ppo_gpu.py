@@ -293,8 +293,8 @@ def test_runner_style_loop_and_api_surface():
 
 @pytest.mark.parametrize("callbacks", [False, True])
 def test_bound_env_writes_storage_slots_identically(callbacks):
-    """`SyntheticXBotEnv.bind_storage`: the env kernel writes obs (fp32 + bf16 shadow) straight into the next storage
-    slot.  Must be bit-identical to the generic path (env buffer -> ingest kernel) for a whole rollout, including the
+    """`SyntheticXBotEnv.bind_storage(ring=False)`: the env kernel writes obs (fp32 + bf16 shadow) straight into the next
+    storage slot (stacked format; the ring format has its own tests in test_ring_gpu.py).  Must be bit-identical to the generic path (env buffer -> ingest kernel) for a whole rollout, including the
     carry-over of the last observation into the next iteration (slot T -> slot 0).  (After an update the two runs may
     differ in the last bits: gradient sums use fp32 atomics.)  callbacks=True: the same through the two-phase env step
     with command resampling, pushes and reset extras."""
@@ -309,7 +309,7 @@ def test_bound_env_writes_storage_slots_identically(callbacks):
             env.math.common_step_counter = 396          # a push within the first rollout
         alg, cfg = make_alg(N, T)
         if bound:
-            env.bind_storage(alg.storage, gamma=cfg.gamma if bound == 2 else None)
+            env.bind_storage(alg.storage, gamma=cfg.gamma if bound == 2 else None, ring=False)
         torch.manual_seed(11)
         l0 = _lib.load().hg_launch_count()
         obs, critic_obs = env.get_observations(), env.get_privileged_observations()
