@@ -171,7 +171,7 @@ class HgEnvConfig(C.Structure):
 
 
 class HgHistoryRing(C.Structure):
-    _fields_ = [("live32", C.c_void_p), ("live16", C.c_void_p), ("arch32", C.c_void_p), ("width", C.c_int32),
+    _fields_ = [("live32", C.c_void_p), ("live16", C.c_void_p), ("arch32", C.c_void_p), ("arch16", C.c_void_p), ("width", C.c_int32),
                 ("pitch16", C.c_int32), ("frames", C.c_int32), ("slots", C.c_int32)]
 
 
@@ -226,6 +226,7 @@ _SIGNATURES = {
     "hg_gemm_plan_destroy": (None, [C.c_void_p]),
     "hg_gemm_plan_create_heads": (C.c_int, [C.POINTER(HgGemmProblem), C.POINTER(HgFusedHead), C.c_int, C.POINTER(C.c_void_p)]),
     "hg_gemm_plan_run_heads": (C.c_int, [C.c_void_p, _P, C.c_uint64, C.c_uint64, _P]),
+    "hg_rollout_forward": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, _P, C.c_uint64, C.c_uint64, _P]),
     "hg_gemm_plan_create_tail": (C.c_int, [C.POINTER(HgGemmProblem), C.POINTER(HgGemmProblem), C.POINTER(HgFusedHead), C.c_int,
                                            C.POINTER(C.c_void_p)]),
     "hg_gae_returns": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
@@ -268,7 +269,7 @@ def load(auto_build: bool = True) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.hg_abi_version() != 7:
+    if lib.hg_abi_version() != 8:
         raise HgError("libhgb200.so ABI mismatch")
     _lib = lib
     return lib

@@ -128,6 +128,9 @@ class FusedAdam(optim.Adam):
 
 class PPO:
     actor_critic: ActorCritic
+    # (world_size, rank) to use instead of torch.distributed's while this is set: lets one rank of a running process group
+    # build a single-process replica (a PPO that must not join the group's collectives), e.g. the 2-rank parity test
+    dist_override = None
 
     def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
                  value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0,
@@ -192,6 +195,8 @@ class PPO:
         dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.world_size = torch.distributed.get_world_size() if dist_on else 1
         self.rank = torch.distributed.get_rank() if dist_on else 0
+        if PPO.dist_override is not None:
+            self.world_size, self.rank = PPO.dist_override
         self.last_update_log = None  # [epochs*minibatches, 8] per-minibatch statistics of the last update()
         self._perm_bufs = None
         self._lv_targets = None
@@ -294,8 +299,11 @@ class PPO:
             eps = torch.randn(head_out[0], head_out[1], device=st.actions.device) if self.torch_rng else None
         ac._rng_counter += 1
         if isinstance(gemms, tuple):                  # last hidden layer, output layers and sampling in one launch
-            ac._engine.run_plans(gemms[0])
-            ac._engine.run_head_plan(gemms[1], eps, self._seed, ac._rng_counter)
+            chain = views.get("chain")
+            if chain is None:                         # (plan pointers as a C array: the whole forward is one binding call)
+                chain = views["chain"] = ((C.c_void_p * len(gemms[0]))(*gemms[0]), len(gemms[0]), gemms[1])
+            if self._lib.hg_rollout_forward(chain[0], chain[1], chain[2], ptr(eps), self._seed, ac._rng_counter, current_stream()) != 0:
+                check(-1)
         else:
             ac._engine.run_plans(gemms)
             check(self._lib.hg_policy_head_rollout(*head_args, ptr(eps), self._seed, ac._rng_counter, *head_out,

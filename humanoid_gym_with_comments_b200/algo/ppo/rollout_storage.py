@@ -35,7 +35,8 @@ class _Ring:
         self.live32 = z(N, self.slots, width)
         self.arch32 = z(N, self.slots, width)
         self.live16 = z(N, self.slots, self.pitch16, dtype=torch.bfloat16)
-        self.c = HgHistoryRing(live32=ptr(self.live32), live16=ptr(self.live16), arch32=ptr(self.arch32), width=width,
+        self.arch16 = z(N, self.slots, self.pitch16, dtype=torch.bfloat16)
+        self.c = HgHistoryRing(live32=ptr(self.live32), live16=ptr(self.live16), arch32=ptr(self.arch32), arch16=ptr(self.arch16), width=width,
                                pitch16=self.pitch16, frames=frames, slots=self.slots)
         self.K16 = frames * self.pitch16               # bf16 window width = K of the first layer
         self._flat32 = self.live32.view(N, self.slots * width)
@@ -178,6 +179,7 @@ class RolloutStorage:
                 for t in (ring.live32, ring.arch32):
                     t[:, row:row + ring.frames].copy_(fr)
                 ring.live16[:, row:row + ring.frames, :ring.width].copy_(fr)
+                ring.arch16[:, row:row + ring.frames, :ring.width].copy_(fr)
             self.ring_hist_start.fill_(ALL_VALID)
             self.ring_first_valid[row].fill_(ALL_VALID)
         self._ring_version += 1

@@ -78,6 +78,19 @@ __device__ __forceinline__ void pdl_trigger() {
 #endif
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// LATE trigger: the dependent grid is launched once EVERY block of this grid has executed this (or exited), so a kernel
+// that calls it when its blocks are past their main work -- and therefore all resident -- lets the ~2 us launch latency
+// of its successor (measured with tools/trace_rollout.py: 1.8-2.0 us between the last block's exit and the first
+// instruction of the next kernel) overlap its own tail instead of following it.  The successor still orders its global
+// accesses behind this grid's completion with pdl_wait().  One executing thread per block is enough.
+// Measured (tools/phase_times.py, variants with / without): rollout 3.40 vs 3.38 ms, update 5.47 vs 5.36 ms -- the wait of
+// the successor for this grid's completion + flush (~1.3 us) is there either way and what the trigger saves in launch
+// latency it loses elsewhere, so the trigger is OFF unless HG_LATE_TRIGGER is defined.
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifdef HG_LATE_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -171,6 +184,28 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- device-side timeline (development builds only: tools/build_variant.sh NAME -DHG_TRACE, tools/trace_rollout.py)
+// trace(tag, sub) stores %globaltimer into a fixed slot of a table: [kernel = tag >> 8 (1..3)][point = tag & 63][sub 0..3]
+// [block 0..511] -- plain stores, no atomics (a shared record counter serialised the blocks and distorted the very
+// timeline it was measuring), so a table holds ONE launch of each kernel: the tool traces one rollout step at a time.
+// Each translation unit keeps its own table pointer (no relocatable device code); hg_trace_set() sets them all.
+#ifdef HG_TRACE
+static __device__ unsigned long long* g_trace_buf = nullptr;
+constexpr int TRACE_BLOCKS = 512;
+__device__ __forceinline__ void trace(int tag, int sub = 0) {
+  unsigned long long* b = g_trace_buf;
+  if (!b || blockIdx.x >= TRACE_BLOCKS) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  b[((size_t)((((tag >> 8) & 3) * 64 + (tag & 63)) * 4 + (sub & 3))) * TRACE_BLOCKS + blockIdx.x] = t;
+}
+#define HG_TRACE_SETTER(name) \
+  int name(void* p) { return (int)cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
+#else
+__device__ __forceinline__ void trace(int, int = 0) {}
+#define HG_TRACE_SETTER(name)
+#endif
 
 // ---- small math helpers
 __device__ __forceinline__ float elu1(float z) { return z > 0.f ? z : expm1f(z); }

@@ -122,6 +122,14 @@ __device__ __forceinline__ Tile decode_tile(const GroupParams& P, int t) {
   return ti;
 }
 
+// Tile `it` of CTA (pair) `group_id`: waves of num_groups tiles, odd waves dealt in reverse ("snake"), so the CTAs that drew
+// the expensive tiles of one wave draw the cheap ones of the next.  Problems are listed in decreasing K (actor before
+// critic), e.g. the rollout's first layer as 256 x 256 pair tiles: 32 actor tiles (12 k-blocks) + 48 critic tiles (4) on 74
+// pairs -- plain round-robin gives six pairs 12 + 4 k-blocks, the snake gives them 4 + 4 and nobody more than 12.
+__device__ __forceinline__ int snake_tile(int it, int group_id, int num_groups) {
+  return it * num_groups + ((it & 1) ? num_groups - 1 - group_id : group_id);
+}
+
 // N of the MMA instruction for this tile = its valid columns rounded up to 32: a ragged last tile (N=705 -> 193,
 // the 128-wide lin-vel layer in a 256-wide tile) does not pay for columns that are all zero padding.
 template <int BLOCK_N>
@@ -406,7 +414,7 @@ __device__ __forceinline__ void head_epilogue(const GroupParams& P, float* sm, u
   const int et = (warp - 4) * 32 + lane;       // 0..511
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int t = group_id; t < P.total_tiles; t += num_groups) {
+  for (int it = 0, t; (t = snake_tile(it, group_id, num_groups)) < P.total_tiles; ++it) {
     const Tile ti = decode_tile(P, t);
     const DevProblem& q = P.p[ti.g];
     const HgFusedHead& hd = P.heads[ti.g];
@@ -592,6 +600,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
   float* epi_tiles = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
 
   pdl_trigger();
+  if (threadIdx.x == 0) trace(0x200);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
@@ -622,13 +631,14 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
   if constexpr (CG == 2) cluster_sync_all();   // peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace(0x201);
 
   if (warp == 0) {
     // ================================================================ TMA producer (every CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = group_id; t < P.total_tiles; t += num_groups) {
+      for (int it = 0, t; (t = snake_tile(it, group_id, num_groups)) < P.total_tiles; ++it) {
         const Tile ti = decode_tile(P, t);
         const DevProblem& q = P.p[ti.g];
         const void* ta = &P.tma_a[ti.g];
@@ -657,8 +667,12 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
               tma_load_2d_cg<CG>(sb + j * MN_ATOM_BYTES, tb, fb, nb0 + j * 64, kb * BLOCK_K);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (it == 0 && kb == ti.kb_begin) trace(0x202);
         }
       }
+      // every operand load of this CTA is in flight: what remains is its last MMAs and epilogue.  The dependent launch is
+      // triggered once every CTA of the (fully resident, persistent) grid is here -- its launch latency hides behind that tail.
+      pdl_launch_dependents();
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (leader CTA only)
@@ -667,7 +681,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = group_id; t < P.total_tiles; t += num_groups) {
+      for (int it = 0, t; (t = snake_tile(it, group_id, num_groups)) < P.total_tiles; ++it) {
         const Tile ti = decode_tile(P, t);
         const DevProblem& q = P.p[ti.g];
         // instruction descriptor: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), majors, N>>3 at 17, M>>4 at 24
@@ -691,6 +705,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
+          if (it == 0 && kb == ti.kb_begin) trace(0x203);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t a_lo = a_lo0 | ((sa & 0x3FFFFu) >> 4);
           const uint32_t b_lo = b_lo0 | (((sa + A_BYTES) & 0x3FFFFu) >> 4);
@@ -715,6 +730,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_cg<CG>(smem_u32(&tfull_bar[acc]));        // accumulator complete -> epilogues
+        trace(0x204, it);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -741,7 +757,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
       for (int i = et; i < 4 * HG_MAX_COLSUM_COLS; i += K::EPI_WARPS * 32) s_colsum_all[i] = 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(K::EPI_WARPS * 32) : "memory");
     }
-    for (int t = group_id; t < P.total_tiles; t += num_groups) {
+    for (int it = 0, t; (t = snake_tile(it, group_id, num_groups)) < P.total_tiles; ++it) {
       const Tile ti = decode_tile(P, t);
       const DevProblem& q = P.p[ti.g];
       const int row = (ti.m_blk * CG + rank) * BLOCK_M + quad * 32 + lane;
@@ -755,6 +771,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
       }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
+      if (warp == 4 && lane == 0) trace(0x205, it);
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + half * SLICE;
 #pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
@@ -780,6 +797,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
                        ::"r"(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK) : "memory");
         }
       }
+      if (warp == 4 && lane == 0) trace(0x206, it);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if constexpr (DELU) {      // one flush per CTA and launch: (columns / 32) coalesced REDs instead of one per 32 x 32 chunk
@@ -799,6 +817,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace(0x207);
   if constexpr (CG == 2) cluster_sync_all();   // nobody leaves while the peer may still read its shared memory / barriers
   if (warp == 2) {
     tc_fence_after();
@@ -863,6 +882,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
   float* sm = reinterpret_cast<float*>(smem + HEAD_OFF);
 
   pdl_trigger();
+  if (threadIdx.x == 0) trace(0x300);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x / P.tiles_m, m_blk = blockIdx.x - g * P.tiles_m;
   const TailNet& q = P.net[g];
@@ -891,6 +911,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t ring = smem_u32(smem), h2s = smem_u32(smem + H2_OFF);
+  if (threadIdx.x == 0) trace(0x301);
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -909,6 +930,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
       mbar_wait(smem_u32(acc1_full), 0);
       mbar_arrive_expect_tx(smem_u32(w3_full), num_kb2 * KB_BYTES);
       for (int kb = 0; kb < num_kb2; ++kb) tma_load_2d(ring + kb * KB_BYTES, &q.tma_w3, smem_u32(w3_full), kb * BLOCK_K, 0);
+      pdl_launch_dependents();     // all loads issued, every CTA of the one-wave grid is resident: see gemm_kernel
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
@@ -923,6 +945,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
       for (int kb = 0; kb < num_kb1; ++kb) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
+        if (kb == 0) trace(0x302);
         const uint32_t sa = ring + stage * STAGE_BYTES;
         const uint32_t a_lo = (1u << 16) | ((sa & 0x3FFFFu) >> 4), b_lo = (1u << 16) | (((sa + A_BYTES) & 0x3FFFFu) >> 4);
         const int k_left = q.K1 - kb * BLOCK_K;
@@ -936,10 +959,12 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(smem_u32(acc1_full));
+      trace(0x303);
       // layer 3: A = the h2 tile the epilogue warps wrote to shared memory, B = W3 in the ring
       mbar_wait(smem_u32(w3_full), 0);
       mbar_wait(smem_u32(h2_ready), 0);
       tc_fence_after();
+      trace(0x306);
       accumulate = 0;
       for (int kb = 0; kb < num_kb2; ++kb) {
         const uint32_t a_lo = (1u << 16) | (((h2s + kb * KB_BYTES) & 0x3FFFFu) >> 4);
@@ -975,6 +1000,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
     // ---- epilogue 1: h2 = bf16(elu(acc + b2)) -> shared memory, K-major SWIZZLE_128B (16-byte chunk index XOR row % 8)
     mbar_wait(smem_u32(acc1_full), 0);
     tc_fence_after();
+    if (warp == 4 && lane == 0) trace(0x304);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       const int n0 = slice * 64 + c * 32;
@@ -1001,11 +1027,13 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(h2_ready));
+    if (warp == 4 && lane == 0) trace(0x305);
     epi_bar_sync();                                                 // sW / sB staged by every epilogue thread
 
     // ---- epilogue 2: fused head on the layer-3 accumulator (same math as head_epilogue)
     mbar_wait(smem_u32(acc2_full), 0);
     tc_fence_after();
+    if (warp == 4 && lane == 0) trace(0x307, g);
     const int n0 = slice * 32;
     const bool live = n0 < q.N3;                  // N3 % 32 == 0
     if (live) {
@@ -1034,6 +1062,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
       for (int a = 0; a < n_out; ++a) sAcc[(slice * 128 + rt) * 17 + a] = 0.f;
     }
     tc_fence_before();
+    if (warp == 4 && lane == 0) trace(0x309, g);
     epi_bar_sync();
     const int row = m_blk * BLOCK_M + rt;
     auto dot = [&](int a) {
@@ -1067,6 +1096,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
         for (int a = a_lo; a < a_hi; ++a) hd.out[(long long)row * n_out + a] = dot(a) + sB[a];
       }
     }
+    if (warp == 4 && lane == 0) trace(0x30a, g);
     if (hd.kind == HG_HEAD_POLICY) {
       epi_bar_sync();
       sAcc[slice * 128 + rt] = lp;
@@ -1077,11 +1107,14 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace(0x308, g);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<tail::TMEM_COLS>(tmem_base);
   }
 }
+
+HG_TRACE_SETTER(trace_set_gemm)
 
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1361,4 +1394,17 @@ extern "C" int hg_gemm_plan_run_heads(const HgGemmPlan* plan, const float* eps, 
   gp.seed = seed;
   gp.counter = counter;
   return dispatch(gp, HG_EPI_BIAS_ELU_HEAD, 128, 1, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// The rollout forward of one env step in ONE call: `n` plain plans (layer 1, ...) followed by the fused-head plan.
+// Same launches as hg_gemm_plan_run x n + hg_gemm_plan_run_heads; saves the per-call host overhead of the binding.
+extern "C" int hg_rollout_forward(const HgGemmPlan* const* plans, int n, const HgGemmPlan* head_plan, const float* eps,
+                                  uint64_t seed, uint64_t counter, void* stream) {
+  using namespace hg;
+  HG_CHECK((plans != nullptr || n == 0) && n >= 0 && head_plan != nullptr, "hg_rollout_forward: bad arguments");
+  for (int i = 0; i < n; ++i) {
+    int rc = hg_gemm_plan_run(plans[i], stream);
+    if (rc != HG_OK) return rc;
+  }
+  return hg_gemm_plan_run_heads(head_plan, eps, seed, counter, stream);
 }

@@ -823,6 +823,7 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
     }
     __syncthreads();       // the next tile overwrites sh / s_out / s_dO
   }
+  if (tid == 0) pdl_launch_dependents();     // persistent grid, every block resident: the successor's launch overlaps the flush
 
   // ---- once per block: flush everything that was accumulated in registers
 #pragma unroll

@@ -54,6 +54,7 @@ __device__ void opt_scalars(const HgAdamArgs& a, double sumsq) {
 __global__ void grad_sumsq_kernel(HgAdamArgs a) {
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();   // 592 x 256 threads: the whole grid is resident (see hg_common.cuh)
   const float* __restrict__ g = a.grads;
   double acc = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -82,6 +83,7 @@ __global__ void grad_sumsq_kernel(HgAdamArgs a) {
 __global__ void __launch_bounds__(256) adam_kernel(HgAdamArgs a, const __grid_constant__ ShadowTable tab) {
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
   const float coef = (float)a.opt_state[3];
   const float step_size = (float)a.opt_state[4];
   const float bc2_sqrt = (float)a.opt_state[5];

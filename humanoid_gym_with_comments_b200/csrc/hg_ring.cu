@@ -10,8 +10,9 @@
 
 namespace hg {
 
-// One warp per output row.  The window is `frames * width` contiguous floats: coalesced 128-byte reads; the bf16 output
-// is written as packed pairs at the frame pitch `pitch16` (pad columns zero), the fp32 output packed.
+// One warp per output row.  fp32 output (the reference's layout, packed): the window is `frames * width` contiguous floats of
+// the fp32 archive.  bf16 output (the minibatch operand, frame pitch `pitch16`): the window is `frames * pitch16 / 8`
+// contiguous 16-byte chunks of the bf16 archive, copied chunk for chunk (a whole frame is valid or zero).
 template <bool BF16>
 __global__ void __launch_bounds__(256) ring_gather_kernel(const HgHistoryRing R, int num_envs, const int* __restrict__ first_valid,
                                                           const long long* __restrict__ idx, long long rows_out, void* __restrict__ dst,
@@ -29,16 +30,24 @@ __global__ void __launch_bounds__(256) ring_gather_kernel(const HgHistoryRing R,
     if (dst == nullptr) {
       // only the lin-vel targets are wanted
     } else if constexpr (BF16) {
-      uint32_t* out = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(dst) + i * ld_dst);
-      const int pairs = R.pitch16 >> 1;
-      for (int p = lane; p < R.frames * pairs; p += 32) {
-        const int f = p / pairs, c = 2 * (p - f * pairs);
-        float lo = 0.f, hi = 0.f;
-        if (f >= f0) {
-          if (c < R.width) lo = __ldg(src + f * R.width + c);
-          if (c + 1 < R.width) hi = __ldg(src + f * R.width + c + 1);
+      const int cpf = R.pitch16 >> 3;                          // 16-byte chunks per frame
+      const uint4* s16 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(R.arch16) + ((size_t)n * R.slots + r) * R.pitch16);
+      uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + i * ld_dst);
+      const int chunks = R.frames * cpf;
+      constexpr int U = 4;                                     // loads in flight per lane (a 15 x 48 window is 90 chunks: one pass)
+      for (int c0 = 0; c0 < chunks; c0 += 32 * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int c = c0 + lane + 32 * u;
+          v[u] = make_uint4(0, 0, 0, 0);
+          if (c < chunks && c / cpf >= f0) v[u] = __ldg(s16 + c);
         }
-        out[p] = pack_bf16x2(lo, hi);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int c = c0 + lane + 32 * u;
+          if (c < chunks) out[c] = v[u];
+        }
       }
     } else {
       float* out = reinterpret_cast<float*>(dst) + i * ld_dst;
@@ -81,14 +90,16 @@ __global__ void __launch_bounds__(128) ring_rollover_kernel(const HgHistoryRing 
       R.arch32[base * R.width + j] = arch[u];
     }
   }
-  // bf16 copy of the live window, re-derived from the fp32 values just moved (same rounding as the env kernel)
+  // bf16 copies of the two windows, re-derived from the fp32 values just moved (same rounding as the env kernel)
   __nv_bfloat16* l16 = reinterpret_cast<__nv_bfloat16*>(R.live16) + base * R.pitch16;
+  __nv_bfloat16* a16 = reinterpret_cast<__nv_bfloat16*>(R.arch16) + base * R.pitch16;
 #pragma unroll
   for (int u = 0; u < ROLL_MAX; ++u) {
     const int j = lane + 32 * u;
     if (j < count) {
       const int f = j / R.width, c = j - f * R.width;
       l16[f * R.pitch16 + c] = __float2bfloat16_rn(live[u]);
+      a16[f * R.pitch16 + c] = __float2bfloat16_rn(arch[u]);
     }
   }
   if (ring == 0 && lane == 0) {
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(128) ring_rollover_kernel(const HgHistoryRing 
 }
 
 static int check_ring(const HgHistoryRing* R, const char* who) {
-  HG_CHECK(R && R->live32 && R->live16 && R->arch32, "%s: null ring buffer", who);
+  HG_CHECK(R && R->live32 && R->live16 && R->arch32 && R->arch16, "%s: null ring buffer", who);
   HG_CHECK(R->width >= 1 && R->frames >= 1 && R->pitch16 >= R->width && R->pitch16 % 8 == 0 && R->slots >= R->frames,
            "%s: bad ring geometry (width %d, pitch16 %d, frames %d, slots %d)", who, R->width, R->pitch16, R->frames, R->slots);
   return HG_OK;
@@ -113,8 +124,10 @@ extern "C" int hg_ring_gather(const HgHistoryRing* ring, int num_envs, const int
   int rc = check_ring(ring, "hg_ring_gather");
   if (rc != HG_OK) return rc;
   HG_CHECK(num_envs > 0 && first_valid && (dst || lv_out) && rows_out > 0, "hg_ring_gather: bad arguments");
-  HG_CHECK(!dst || (ld_dst >= (int64_t)ring->frames * (dst_bf16 ? ring->pitch16 : ring->width) && (!dst_bf16 || ld_dst % 2 == 0)),
-           "hg_ring_gather: ld_dst %lld too small for %d frames", (long long)ld_dst, ring->frames);
+  HG_CHECK(!dst || (ld_dst >= (int64_t)ring->frames * (dst_bf16 ? ring->pitch16 : ring->width) && (!dst_bf16 || ld_dst % 8 == 0)),
+           "hg_ring_gather: ld_dst %lld too small for %d frames (bf16 rows: a multiple of 8)", (long long)ld_dst, ring->frames);
+  HG_CHECK(!dst || !dst_bf16 || ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(ring->arch16)) & 15) == 0,
+           "hg_ring_gather: bf16 rows and the bf16 archive must be 16-byte aligned");
   HG_CHECK(!lv_out || (lv_col >= 0 && lv_col + 3 <= ring->frames * ring->width), "hg_ring_gather: lv_col outside the row");
   long long blocks = (rows_out + 7) / 8;
   if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;

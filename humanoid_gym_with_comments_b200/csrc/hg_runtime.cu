@@ -41,6 +41,15 @@ int num_sms() {
 
 }  // namespace hg
 
+#ifdef HG_TRACE
+namespace hg {
+int trace_set_gemm(void* p);
+int trace_set_env(void* p);
+}  // namespace hg
+// trace builds only (not part of the ABI): device timeline table, u64 [4 * 64 * 4 * 512] (hg_common.cuh); null switches off
+extern "C" int hg_trace_set(void* buf) { return hg::trace_set_gemm(buf) | hg::trace_set_env(buf); }
+#endif
+
 extern "C" const char* hg_last_error(void) { return hg::g_err; }
 extern "C" int hg_abi_version(void) { return HG_ABI_VERSION; }
 extern "C" int64_t hg_launch_count(void) { return hg::g_launches.load(std::memory_order_relaxed); }

@@ -21,7 +21,7 @@ extern "C" {
 #define HG_ERR_INVALID (-1)
 #define HG_ERR_CUDA (-2)
 
-#define HG_ABI_VERSION 7
+#define HG_ABI_VERSION 8
 
 const char* hg_last_error(void);
 int hg_abi_version(void);
@@ -107,6 +107,10 @@ typedef struct HgFusedHead {
 int hg_gemm_plan_create_heads(const HgGemmProblem* problems_host, const HgFusedHead* heads_host, int num_problems,
                               HgGemmPlan** out);
 int hg_gemm_plan_run_heads(const HgGemmPlan* plan, const float* eps, uint64_t seed, uint64_t counter, void* stream);
+/* The whole `PPO.act` forward of one env step (ppo.py:116-126) in one call: hg_gemm_plan_run(plans[i]) for i < n, then
+ * hg_gemm_plan_run_heads(head_plan, ...).  Identical launches; one binding call instead of n + 1. */
+int hg_rollout_forward(const HgGemmPlan* const* plans, int n, const HgGemmPlan* head_plan, const float* eps,
+                       uint64_t seed, uint64_t counter, void* stream);
 
 /* Rollout, nets with three hidden layers: layer 2, layer 3 and the output layer of up to two nets (actor, critic) in ONE
  * launch -- what hg_gemm_plan_create (layer 2) + hg_gemm_plan_create_heads (layer 3 + head) do in two.  A CTA keeps its
@@ -305,11 +309,13 @@ typedef struct HgEnvConfig {
  *   live16  the same in bf16 at a 16-byte-aligned frame pitch (pad columns zero): the TMA source of the first layer during
  *           the rollout (tensor map base = live16 + r*pitch16, row stride = slots*pitch16, extent = frames*pitch16);
  *   arch32  never zeroed: together with first_valid[r, n] (frames older than that time read as zero) it reproduces
- *           every row of the iteration for the update's minibatch gather (hg_ring_gather), after later resets too. */
+ *           every row of the iteration (hg_ring_gather), after later resets too: the source of the API-visible fp32 rows;
+ *   arch16  the same archive in bf16 at the frame pitch: the source of the update's minibatch gather (half the bytes). */
 typedef struct HgHistoryRing {
   float* live32;    /* [N, slots, width] */
   void* live16;     /* [N, slots, pitch16] bf16 */
   float* arch32;    /* [N, slots, width] */
+  void* arch16;     /* [N, slots, pitch16] bf16 */
   int32_t width;    /* So / Sp */
   int32_t pitch16;  /* width rounded up to 8 */
   int32_t frames;   /* F / Fc */

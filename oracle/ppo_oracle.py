@@ -295,8 +295,11 @@ def minibatch_losses(p: Params, mb: Dict[str, torch.Tensor], cfg: PPOConfig) -> 
     lin_vel_loss = torch.nn.functional.mse_loss(lv, mb["lin_vel_target"])
     loss = (surrogate_loss + cfg.value_loss_coef * value_loss - cfg.entropy_coef * ent.mean() + cfg.sym_coef * sym_loss
             + cfg.base_lin_vel_coef * lin_vel_loss)
+    # mean |term| of the surrogate: the scale its forward error is measured on (the loss itself is a near-cancelling mean
+    # of signed terms, advantages being normalised to mean 0) -- used by the parity tests only
+    surrogate_abs = torch.max(surrogate, surrogate_clipped).detach().abs().mean()
     return dict(loss=loss, surrogate=surrogate_loss, value=value_loss, lin_vel=lin_vel_loss, sym=sym_loss,
-                entropy=ent.mean(), kl=kl_mean, mu=mu, v=v, lv=lv)
+                entropy=ent.mean(), kl=kl_mean, mu=mu, v=v, lv=lv, surrogate_abs=surrogate_abs)
 
 
 def clip_grad_norm(grads: List[torch.Tensor], max_norm: float) -> float:
@@ -357,7 +360,8 @@ def ppo_update(p: Params, st: AdamState, ro: Rollout, perm: torch.Tensor, cfg: P
         if record is not None:
             record.append(dict(value=float(out["value"]), surrogate=float(out["surrogate"]),
                                lin_vel=float(out["lin_vel"]), entropy=float(out["entropy"]),
-                               kl=float(out["kl"]), lr=lr, grad_norm=gnorm, sym=float(out["sym"])))
+                               kl=float(out["kl"]), lr=lr, grad_norm=gnorm, sym=float(out["sym"]),
+                               surrogate_abs=float(out["surrogate_abs"])))
     return sums["value"] / n, sums["surrogate"] / n, sums["lin_vel"] / n, lr
 
 

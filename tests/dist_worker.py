@@ -41,10 +41,14 @@ def make(n_envs, seed, ws=None):
     torch.manual_seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):
         ac = ActorCritic(705, 219, A, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[768, 256, 128])
-    alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0.994, lam=0.9, value_loss_coef=1.0,
-              entropy_coef=0.001, learning_rate=1e-5, max_grad_norm=1.0, schedule="adaptive", desired_kl=0.01, device=dev)
-    if ws is not None:
-        alg.world_size = ws
+    # ws = 1: a single-process replica built by ONE rank -- it must not join the group's collectives (the constructor's
+    # broadcast would pair up with whatever the other rank does next and deadlock)
+    PPO.dist_override = (ws, 0) if ws is not None else None
+    try:
+        alg = PPO(ac, num_learning_epochs=2, num_mini_batches=4, clip_param=0.2, gamma=0.994, lam=0.9, value_loss_coef=1.0,
+                  entropy_coef=0.001, learning_rate=1e-5, max_grad_norm=1.0, schedule="adaptive", desired_kl=0.01, device=dev)
+    finally:
+        PPO.dist_override = None
     alg.init_storage(n_envs, T, [705], [219], [A])
     return alg
 

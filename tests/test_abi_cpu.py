@@ -30,7 +30,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hgb200.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes prototypes and header disagree"
-    assert lib.hg_abi_version() == 7
+    assert lib.hg_abi_version() == 8
     assert lib.hg_launch_count() == 0            # nothing launched on a CPU box
 
 

@@ -10,7 +10,7 @@ mkdir -p $B
 C=humanoid_gym_with_comments_b200/csrc
 F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 if [ -n "$ALL" ]; then
-  for f in hg_runtime hg_gemm hg_gae hg_misc hg_heads hg_optim hg_sym; do nvcc $F $@ -c $C/$f.cu -o $B/$f.o & done
+  for f in hg_runtime hg_gemm hg_gae hg_misc hg_heads hg_optim hg_sym hg_ring; do nvcc $F $@ -c $C/$f.cu -o $B/$f.o & done
   nvcc $F -fmad=false $@ -c $C/hg_env.cu -o $B/hg_env.o &
   nvcc $F -fmad=false $@ -c $C/hg_env_aux.cu -o $B/hg_env_aux.o &
   wait
