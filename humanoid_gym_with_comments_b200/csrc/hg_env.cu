@@ -150,7 +150,7 @@ struct EnvStage {
   int width[SEG_COUNT];          // floats per env
   int dst[SEG_COUNT];            // float offset in shared memory (multiple of 4)
   // produced in shared memory by the kernel itself
-  int fobs, fpriv, terms, s2, reset, ep, tout, rg, lc, nsv, ddp, total;
+  int fobs, fpriv, terms, s2, reset, ep, tout, rg, lc, nsv, ddp, noise, total;
 };
 
 // Per-env quantities every role needs (cheap, recomputed by each role's warp instead of being exchanged).
@@ -313,6 +313,30 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
   auto ep_stored = [&](int el) { return reinterpret_cast<const long long*>(s_env + L.dst[SEG_EPL])[el]; };
   float* T = s_terms + lane;                          // T[k * E]
 #define HG_TERM(k, val) T[(k) * E] = (val) * C.reward_scale_dt[k]
+
+  // N(0,1) draws of the newest actor frame, [E][So rounded up to 4]: they depend on nothing but (seed, step, env, column
+  // group), so in the ring kernel the three warps without a role produce them WHILE the role warps do the per-env math
+  // (the stacked kernel's spare warps stream the history instead: there all threads draw them after the barrier)
+  float* s_noise = s_env + L.noise;
+  const int ngroups = (So + 3) >> 2, So4 = ngroups * 4;
+  auto draw_noise = [&](int first, int stride) {
+    if (C.noise_level == 0.f) return;
+#pragma unroll 1
+    for (int i = first; i < envs_here * ngroups; i += stride) {
+      const int el = i / ngroups, g = i - el * ngroups;
+      const int ne = n0 + el, j0 = 4 * g, cols = min(4, So - j0);
+      float e4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (B.noise) {
+        for (int k = 0; k < cols; ++k) e4[k] = __ldg(B.noise + (size_t)ne * So + j0 + k);
+      } else {
+        bool any = false;
+        for (int k = 0; k < cols; ++k) any = any || s_nsv[j0 + k] != 0.f;
+        if (any) env_philox_normal4(B.seed, B.counter, ne, g, e4);     // one Philox4x32-10 call: four normals
+      }
+      *reinterpret_cast<float4*>(s_noise + el * So4 + j0) = make_float4(e4[0], e4[1], e4[2], e4[3]);
+    }
+  };
+  if (RING && warp > FRAME_B_WARP) draw_noise(tid - 32 * (FRAME_B_WARP + 1), ENV_THREADS - 32 * (FRAME_B_WARP + 1));
 
   if (!RING && warp >= ENV_ROLE_WARPS) {
     // ---------------------------------------------------------------- history shift (:883-887): needs only the reset flag,
@@ -553,9 +577,9 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
   // ---------------------------------------------------------------- episode sums (all threads, coalesced over [term, env])
   if (doA) {
 #pragma unroll 1
-    for (int i = tid; i < HG_NUM_REWARDS * envs_here; i += ENV_THREADS) {
-      const int k = i / envs_here, el = i - k * envs_here;
-      if (C.reward_scale_dt[k] != 0.f) {
+    for (int i = tid; i < HG_NUM_REWARDS * E; i += ENV_THREADS) {
+      const int k = i / E, el = i % E;                    // (E is a compile-time power of two: no division)
+      if (el < envs_here && C.reward_scale_dt[k] != 0.f) {
         const float term_k = s_terms[k * E + el];
         const size_t idx = (size_t)k * C.num_envs + n0 + el;
         B.episode_sums[idx] = (s_reset[el] && doB) ? 0.f : s_sums[k * E + el] + term_k;   // zeroed by reset_idx (:1144)
@@ -584,9 +608,12 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
   }
 
   // ---------------------------------------------------------------- hand-over :802-806 + reset zeroing :1132-1139, coalesced over [env, dof]
+  // (the flat phases below walk [env = warp, warp + 8, ..][column = lane, lane + 32, ..]: no runtime integer division, which
+  // costs ~100 dependent cycles apiece and used to head every iteration of these short loops)
 #pragma unroll 1
-  for (int i = tid; i < envs_here * D; i += ENV_THREADS) {
-    const int el = i / D, d = i - el * D;
+  for (int el = warp; el < envs_here; el += ENV_THREADS / 32)
+  for (int d = lane; d < D; d += 32) {
+    const int i = el * D + d;
     const size_t k = (size_t)(n0 + el) * D + d;
     const bool reset = s_reset[el] != 0;
     const float araw = s_env[L.dst[SEG_ACT] + i];
@@ -609,50 +636,39 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
     B.ref_dof_pos[k] = ref;
   }
   for (int i = tid; i < envs_here * 6; i += ENV_THREADS) {
-    const int el = i / 6, d = i - el * 6;
+    const int el = i / 6, d = i - el * 6;                   // (constant divisor)
     B.last_root_vel[(size_t)n0 * 6 + i] = s_env[L.dst[SEG_ROOT] + el * 13 + 7 + d];
   }
   if (threadIdx.x == 0) trace(0x104);
 
   // ---------------------------------------------------------------- newest frame: + noise (:877), clip (:654-657), flat over [env, column]
-  {
-    const int groups = (So + 3) >> 2;        // four columns per work item: ONE Philox4x32-10 call gives their four normals
-#pragma unroll 1
-    for (int i = tid; i < envs_here * groups; i += ENV_THREADS) {
-      const int el = i / groups, g = i - el * groups;
-      const int ne = n0 + el, j0 = 4 * g, cols = min(4, So - j0);
-      float e4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (C.noise_level != 0.f) {
-        if (B.noise) {
-          for (int k = 0; k < cols; ++k) e4[k] = __ldg(B.noise + (size_t)ne * So + j0 + k);
-        } else {
-          bool any = false;
-          for (int k = 0; k < cols; ++k) any = any || s_nsv[j0 + k] != 0.f;
-          if (any) env_philox_normal4(B.seed, B.counter, ne, g, e4);
-        }
-      }
-      for (int k = 0; k < cols; ++k) {
-        float v = s_fobs[el * So + j0 + k];
-        if (C.noise_level != 0.f) v = v + e4[k] * s_nsv[j0 + k] * C.noise_level;
-        s_fobs[el * So + j0 + k] = clampf(v, -C.clip_obs, C.clip_obs);
-      }
-    }
+  if (!RING) {
+    draw_noise(tid, ENV_THREADS);
+    __syncthreads();
   }
-  for (int i = tid; i < envs_here * Sp; i += ENV_THREADS) s_fpriv[i] = clampf(s_fpriv[i], -C.clip_obs, C.clip_obs);
-  __syncthreads();
+#pragma unroll 1
+  for (int el = warp; el < envs_here; el += ENV_THREADS / 32) {
+    for (int j = lane; j < So; j += 32) {
+      float v = s_fobs[el * So + j];
+      if (C.noise_level != 0.f) v = v + s_noise[el * So4 + j] * s_nsv[j] * C.noise_level;
+      s_fobs[el * So + j] = clampf(v, -C.clip_obs, C.clip_obs);
+    }
+    for (int j = lane; j < Sp; j += 32) s_fpriv[el * Sp + j] = clampf(s_fpriv[el * Sp + j], -C.clip_obs, C.clip_obs);
+  }
+  __syncwarp();          // the stores below walk the same [env = warp][column = lane] map: a warp reads only what it wrote
   if constexpr (!RING) {
-    for (int i = tid; i < envs_here * So; i += ENV_THREADS) {
-      const int el = i / So, j = i - el * So;
+    for (int el = warp; el < envs_here; el += ENV_THREADS / 32)
+    for (int j = lane; j < So; j += 32) {
       const int ne = n0 + el;
-      const float v = s_fobs[i];
+      const float v = s_fobs[el * So + j];
       B.obs_next[(size_t)ne * B.obs_next_ld + (C.frame_stack - 1) * So + j] = v;
       if (B.obs16_next)
         reinterpret_cast<__nv_bfloat16*>(B.obs16_next)[(size_t)ne * B.obs16_next_ld + (C.frame_stack - 1) * So + j] = __float2bfloat16_rn(v);
     }
-    for (int i = tid; i < envs_here * Sp; i += ENV_THREADS) {
-      const int el = i / Sp, j = i - el * Sp;
+    for (int el = warp; el < envs_here; el += ENV_THREADS / 32)
+    for (int j = lane; j < Sp; j += 32) {
       const int ne = n0 + el;
-      const float v = s_fpriv[i];
+      const float v = s_fpriv[el * Sp + j];
       B.priv_next[(size_t)ne * B.priv_next_ld + (C.c_frame_stack - 1) * Sp + j] = v;
       if (B.priv16_next)
         reinterpret_cast<__nv_bfloat16*>(B.priv16_next)[(size_t)ne * B.priv16_next_ld + (C.c_frame_stack - 1) * Sp + j] = __float2bfloat16_rn(v);
@@ -663,32 +679,32 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
     // archives keep them for the rows of the iteration that still need them (first_valid marks where a row's history starts)
     auto put = [&](const HgHistoryRing& R, const float* frames_s) {
       const int slot = B.ring_row + R.frames - 1;
-#pragma unroll 1
-      for (int i = tid; i < envs_here * R.width; i += ENV_THREADS) {
-        const int el = i / R.width, j = i - el * R.width;
-        const size_t at = ((size_t)(n0 + el) * R.slots + slot) * R.width + j;
-        const float v = frames_s[i];
-        R.live32[at] = v;
-        R.arch32[at] = v;
-      }
       const int pairs = R.pitch16 >> 1;
 #pragma unroll 1
-      for (int i = tid; i < envs_here * pairs; i += ENV_THREADS) {
-        const int el = i / pairs, j = i - el * pairs;
-        const float* fr = frames_s + el * R.width;
-        const float lo = 2 * j < R.width ? fr[2 * j] : 0.f, hi = 2 * j + 1 < R.width ? fr[2 * j + 1] : 0.f;
-        const uint32_t w = pack_bf16x2(lo, hi);
-        const size_t at = ((size_t)(n0 + el) * R.slots + slot) * pairs + j;
-        reinterpret_cast<uint32_t*>(R.live16)[at] = w;
-        reinterpret_cast<uint32_t*>(R.arch16)[at] = w;
-      }
-      for (int el = warp; el < envs_here; el += ENV_THREADS / 32) {      // (rare) reset envs: zero the live history, one warp per env
-        if (!s_reset[el]) continue;
+      for (int el = warp; el < envs_here; el += ENV_THREADS / 32) {      // one warp per env, lanes over the frame's columns
         const size_t env_base = (size_t)(n0 + el) * R.slots;
-        float* z32 = R.live32 + (env_base + B.ring_row) * R.width;
-        for (int j = lane; j < (R.frames - 1) * R.width; j += 32) z32[j] = 0.f;
-        uint32_t* z16 = reinterpret_cast<uint32_t*>(R.live16) + (env_base + B.ring_row) * pairs;
-        for (int j = lane; j < (R.frames - 1) * pairs; j += 32) z16[j] = 0u;
+        const float* fr = frames_s + el * R.width;
+        float* l32 = R.live32 + (env_base + slot) * R.width;
+        float* a32 = R.arch32 + (env_base + slot) * R.width;
+        for (int j = lane; j < R.width; j += 32) {
+          const float v = fr[j];
+          l32[j] = v;
+          a32[j] = v;
+        }
+        uint32_t* l16 = reinterpret_cast<uint32_t*>(R.live16) + (env_base + slot) * pairs;
+        uint32_t* a16 = reinterpret_cast<uint32_t*>(R.arch16) + (env_base + slot) * pairs;
+        for (int j = lane; j < pairs; j += 32) {
+          const float lo = 2 * j < R.width ? fr[2 * j] : 0.f, hi = 2 * j + 1 < R.width ? fr[2 * j + 1] : 0.f;
+          const uint32_t w = pack_bf16x2(lo, hi);
+          l16[j] = w;
+          a16[j] = w;
+        }
+        if (s_reset[el]) {       // (rare) a reset env: zero its live history
+          float* z32 = R.live32 + (env_base + B.ring_row) * R.width;
+          for (int j = lane; j < (R.frames - 1) * R.width; j += 32) z32[j] = 0.f;
+          uint32_t* z16 = reinterpret_cast<uint32_t*>(R.live16) + (env_base + B.ring_row) * pairs;
+          for (int j = lane; j < (R.frames - 1) * pairs; j += 32) z16[j] = 0u;
+        }
       }
     };
     put(B.ring_obs, s_fobs);
@@ -794,6 +810,7 @@ extern "C" int hg_env_step(const HgEnvConfig* cfg, const HgEnvBuffers* buf, void
     };
     L.fobs = take(E * So_); L.fpriv = take(E * Sp_); L.terms = take(HG_NUM_REWARDS * E); L.s2 = take(E);
     L.reset = take(E); L.ep = take(E); L.tout = take(E); L.rg = take(E * 52); L.lc = take(E); L.nsv = take(So_); L.ddp = take(D);
+    L.noise = take(E * ((So_ + 3) & ~3));
     seg(SEG_ROOT, buf->root_states, 13); seg(SEG_DOF, buf->dof_state, 2 * D); seg(SEG_CF, buf->contact_forces, NB * 3);
     seg(SEG_CMD, buf->commands, 4); seg(SEG_TQ, buf->torques, D);
     seg(SEG_ACT, buf->actions_in ? buf->actions_in : buf->actions, D);      // raw policy output (clipped at use) or applied actions

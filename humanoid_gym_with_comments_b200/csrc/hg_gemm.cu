@@ -625,6 +625,15 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_cg<CG, TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == 3 && lane < HG_MAX_GROUP) {
+    // (idle warp) pull the problem table through the constant cache while the predecessor still runs: the device timeline
+    // showed 1.1 us between the end of the set-up and the first TMA issue -- the producer's tile decode missing on
+    // every dependent parameter read
+    const DevProblem& w = P.p[lane];
+    const int touch = w.M + w.tile_end + w.out_fd + (int)(reinterpret_cast<uintptr_t>(w.out) ^ reinterpret_cast<uintptr_t>(w.colsum)) +
+                      P.num_problems + P.total_tiles + P.tiles_per_m + (int)P.counter + P.heads[lane].n_out;
+    asm volatile("" ::"r"(touch));
+  }
   tc_fence_before();
   pdl_wait();          // everything above is on-chip set-up; operands, bias, act and outputs are touched only below
   __syncthreads();
@@ -830,8 +839,11 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
 // Layer 2, layer 3 and the output layer of a net in ONE launch (rollout, three hidden layers): a CTA owns a 128-row
 // tile of one net, computes h2 = elu(h1 W2^T + b2) (128 x N2 <= 256, accumulator in TMEM columns 0..255), parks it as
 // bf16 in shared memory in the canonical K-major SWIZZLE_128B layout (exactly what a TMA load of an activation tile would
-// have produced), multiplies it by W3 (accumulator in TMEM columns 256..383) and finishes with the fused head of
-// HG_EPI_BIAS_ELU_HEAD.  h2 never travels through L2 and the step has one launch (ramp-up, prologue, drain) less.
+// have produced), multiplies it by W3 (accumulator in TMEM columns 256..383), parks h3 = elu(. + b3) the same way and
+// runs the OUTPUT layer on the tensor core as well (W_out split into three bf16 terms, 128 x 16 accumulator in TMEM
+// columns 384..399): the device timeline (tools/trace_rollout.py) showed the 12 x 128 fp32 dot products per row on the
+// CUDA cores taking 5 us of the actor tile's 9 us head -- the critical path of the launch.  Each thread then finishes
+// four outputs of its row (sampling, log-prob).  h2 / h3 never travel through L2 and the step has one launch less.
 //   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-19: the two epilogues
 namespace tail {
 #ifndef HG_TAIL_STAGES
@@ -843,14 +855,23 @@ constexpr int B_BYTES = 256 * BLOCK_K * 2;                // 32 KB: W2 tile 256 
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int KB_BYTES = BLOCK_M * BLOCK_K * 2;           // 16 KB: one 64-wide k-block of h2 (128 rows) / of W3 (<= 128 rows)
 constexpr int H2_OFF = STAGES * STAGE_BYTES;              // 144 KB
-constexpr int BAR_OFF = H2_OFF + 4 * KB_BYTES;            // h2: 64 KB; the head's partial sums reuse it once layer 3 has read it
+// h2: 64 KB.  Once layer 3 has read it the region is reused: its first 32 KB hold the h3 tile (bf16, the A operand of the
+// output layer), the log-prob partial sums [4 slices][128 rows] sit behind that.
+constexpr int LP_OFF = H2_OFF + 2 * KB_BYTES;
+// output-layer weights as the B operand of the tensor core: W = hi + mid + lo, three bf16 terms (24 mantissa bits: exact),
+// each [16 rows x 128 k] K-major SWIZZLE_128B = 2 k-blocks x 2 KB
+constexpr int WOUT_OFF = H2_OFF + 4 * KB_BYTES;
+constexpr int WOUT_KB_BYTES = 16 * BLOCK_K * 2;           // 2 KB
+constexpr int WOUT_TERM_BYTES = 2 * WOUT_KB_BYTES;        // 4 KB
+constexpr int BAR_OFF = WOUT_OFF + 3 * WOUT_TERM_BYTES;
 constexpr int HEAD_OFF = BAR_OFF + 256;
-constexpr int HEAD_BYTES = (16 * 128 + 64) * 4;           // output weights [16][128] + bias / std
+constexpr int HEAD_BYTES = (128 + 64) * 4;                // layer-3 bias [128] + output bias [16] / std [16] / log std [16] / 2 std^2 [16]
 constexpr int SMEM_TOTAL = HEAD_OFF + HEAD_BYTES + 1024;
-static_assert(4 * 128 * 17 * 4 <= 4 * KB_BYTES, "partial sums fit in the h2 tile");
+constexpr int TMEM_OUT_COL = 384;                         // output-layer accumulator: 16 columns behind layer 2 (0-255) and layer 3 (256-383)
 constexpr int THREADS = 128 + 32 * 16;
 constexpr int TMEM_COLS = 512;
 static_assert(SMEM_TOTAL <= 227 * 1024, "rollout tail: shared memory");
+static_assert(LP_OFF + (512 + 3 * 2048) * 4 <= WOUT_OFF, "log-prob sums + staged outputs fit behind the h3 tile");
 }  // namespace tail
 
 struct TailNet {
@@ -878,7 +899,9 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
   uint64_t* h2_ready = bars + 2 * STAGES + 1;    // h2 tile written to shared memory (16 epilogue warps -> MMA)
   uint64_t* w3_full = bars + 2 * STAGES + 2;     // W3 landed in the (idle) operand ring
   uint64_t* acc2_full = bars + 2 * STAGES + 3;   // layer-3 accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* h3_ready = bars + 2 * STAGES + 4;    // h3 tile written to shared memory (16 epilogue warps -> MMA)
+  uint64_t* acc3_full = bars + 2 * STAGES + 5;   // output-layer accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
   float* sm = reinterpret_cast<float*>(smem + HEAD_OFF);
 
   pdl_trigger();
@@ -902,9 +925,16 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
     mbar_init(smem_u32(h2_ready), 16);
     mbar_init(smem_u32(w3_full), 1);
     mbar_init(smem_u32(acc2_full), 1);
+    mbar_init(smem_u32(h3_ready), 16);
+    mbar_init(smem_u32(acc3_full), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(smem_u32(tmem_slot));
+  if (warp == 3 && lane == 0) {      // (idle warp) parameters through the constant cache before they are needed, see gemm_kernel
+    const int touch = q.M + q.K1 + q.N2 + q.N3 + q.head.n_out + q.head.kind + (int)P.counter +
+                      (int)(reinterpret_cast<uintptr_t>(q.b2) ^ reinterpret_cast<uintptr_t>(q.b3) ^ reinterpret_cast<uintptr_t>(q.head.log_prob));
+    asm volatile("" ::"r"(touch));
+  }
   tc_fence_before();
   pdl_wait();
   __syncthreads();
@@ -977,6 +1007,26 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
         }
       }
       umma_commit(smem_u32(acc2_full));
+      // output layer: A = the h3 tile (bf16, shared memory), B = W_out as hi + mid + lo; 128 x 16 accumulator.  The three
+      // terms' products are exact (bf16 x bf16), so the fp32 accumulator holds W h to fp32 round-off.
+      mbar_wait(smem_u32(h3_ready), 0);
+      tc_fence_after();
+      const uint32_t idesc4 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(16 >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+      const uint32_t wout = smem_u32(smem + WOUT_OFF);
+      accumulate = 0;
+      for (int term = 0; term < 3; ++term) {
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint32_t a_lo = (1u << 16) | (((h2s + kb * KB_BYTES) & 0x3FFFFu) >> 4);
+          const uint32_t b_lo = (1u << 16) | (((wout + term * WOUT_TERM_BYTES + kb * WOUT_KB_BYTES) & 0x3FFFFu) >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_bf16(tmem_base + TMEM_OUT_COL, (uint64_t(desc_hi) << 32) | (a_lo + k * step), (uint64_t(desc_hi) << 32) | (b_lo + k * step),
+                      idesc4, accumulate);
+            accumulate = 1;
+          }
+        }
+      }
+      umma_commit(smem_u32(acc3_full));
     }
   } else if (warp >= 4) {
     // ================================================================ epilogues: warps 4..19
@@ -985,17 +1035,47 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
     const int rt = quad * 32 + lane;               // row inside the tile
     const HgFusedHead& hd = q.head;
     const int n_out = hd.n_out;
-    float* sW = sm;                    // [16][128]
-    float* sB = sm + 16 * 128;         // [16] output bias, [16] std
-    float* sAcc = reinterpret_cast<float*>(smem + H2_OFF);   // [4][128][17], over the h2 tile (dead once acc2_full fires)
-    // output-layer weights -> shared memory while the main loops run
-    for (int i = et; i < n_out * q.N3; i += 512) {
-      const int a = i / q.N3, k = i - a * q.N3;
-      sW[a * 128 + k] = __ldg(hd.W + i);
+    float* sB3 = sm;                   // [128] layer-3 bias
+    float* sB = sm + 128;              // [16] output bias, [16] std, [16] log std, [16] 2 std^2
+    float* sLp = reinterpret_cast<float*>(smem + LP_OFF);    // [4][128] log-prob partial sums (h2 region, dead by then)
+    float* sOut = sLp + 512;                                 // [3][128 x 16] actions / mu / sigma of the tile
+    // output-layer weights -> bf16 hi / mid / lo in the canonical K-major SWIZZLE_128B layout (rows >= n_out, k >= N3: zero),
+    // biases and per-action constants -> shared memory, all while the main loops run
+    {
+      uint8_t* wb = smem + WOUT_OFF;
+      for (int i = et; i < 16 * 128; i += 512) {
+        const int a = i >> 7, k = i & 127;
+        const float w = (a < n_out && k < q.N3) ? __ldg(hd.W + a * q.N3 + k) : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const float r1 = w - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+        const int kb = k >> 6, kk = k & 63;
+        const int off = kb * WOUT_KB_BYTES + (a >> 3) * 1024 + (a & 7) * 128 + (((kk >> 3) ^ (a & 7)) << 4) + (kk & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(wb + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(wb + WOUT_TERM_BYTES + off) = mid;
+        *reinterpret_cast<__nv_bfloat16*>(wb + 2 * WOUT_TERM_BYTES + off) = lo;
+      }
+      if (et < 128) sB3[et] = (q.b3 && et < q.N3) ? __ldg(q.b3 + et) : 0.f;
+      if (et < 16) {
+        const float sd = (hd.kind == HG_HEAD_POLICY && et < n_out) ? __ldg(hd.std + et) : 1.f;
+        sB[et] = et < n_out ? __ldg(hd.b + et) : 0.f;
+        sB[16 + et] = sd;
+        sB[32 + et] = logf(sd);
+        sB[48 + et] = 2.f * sd * sd;
+      }
     }
-    if (et < n_out) {
-      sB[et] = __ldg(hd.b + et);
-      sB[16 + et] = hd.kind == HG_HEAD_POLICY ? __ldg(hd.std + et) : 0.f;
+    // The four normals of this thread's outputs (row, 4 * slice ..): they depend on (seed, counter, row, slice) only, so
+    // they are drawn NOW, behind the layer-2 main loop, instead of on the critical path after the output layer (where the
+    // Philox rounds + Box-Muller took ~2 us of the actor tile's head)
+    const int row = m_blk * BLOCK_M + rt;
+    const int a_lo = slice * 4;
+    float e[4] = {0.f, 0.f, 0.f, 0.f};
+    if (hd.kind == HG_HEAD_POLICY && P.eps == nullptr && a_lo < n_out) {
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)slice, (uint32_t)P.counter, (uint32_t)(P.counter >> 32)),
+                                    make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
+      const float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
+      e[0] = n01.x; e[1] = n01.y; e[2] = n23.x; e[3] = n23.y;
     }
     // ---- epilogue 1: h2 = bf16(elu(acc + b2)) -> shared memory, K-major SWIZZLE_128B (16-byte chunk index XOR row % 8)
     mbar_wait(smem_u32(acc1_full), 0);
@@ -1028,80 +1108,96 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(h2_ready));
     if (warp == 4 && lane == 0) trace(0x305);
-    epi_bar_sync();                                                 // sW / sB staged by every epilogue thread
+    epi_bar_sync();                                                 // sB3 / sB staged by every epilogue thread
 
-    // ---- epilogue 2: fused head on the layer-3 accumulator (same math as head_epilogue)
+    // ---- epilogue 2: h3 = bf16(elu(acc + b3)) -> shared memory (over the h2 tile: layer 3 has read it), the A operand of the
+    // output layer; dead 32-column chunks (N3 < 128) are zero-filled, their weights are zero too
     mbar_wait(smem_u32(acc2_full), 0);
     tc_fence_after();
     if (warp == 4 && lane == 0) trace(0x307, g);
-    const int n0 = slice * 32;
-    const bool live = n0 < q.N3;                  // N3 % 32 == 0
-    if (live) {
+    {
+      const int n0 = slice * 32;
       uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + 256 + n0, v);
-      tmem_ld_wait();
-      float z[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(v[j]) + (q.b3 ? __ldg(q.b3 + n0 + j) : 0.f);
-        const float e = x > 0.f ? x : exp2f_fast(x * 1.4426950408889634f) - 1.f;
-        z[j] = __bfloat162float(__float2bfloat16_rn(e));     // what the stored activation would hold
+      const bool live = n0 < q.N3;                  // N3 % 32 == 0
+      if (live) {
+        tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + 256 + n0, v);
+        tmem_ld_wait();
       }
-      for (int a = 0; a < n_out; ++a) {
-        const float4* w4 = reinterpret_cast<const float4*>(sW + a * 128 + n0);
-        float s0 = 0.f, s1 = 0.f;
+      const uint32_t row_addr = h2s + (n0 >> 6) * KB_BYTES + (rt >> 3) * 1024 + (rt & 7) * 128;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const float4 wa = w4[j >> 2], wb = w4[(j >> 2) + 1];
-          s0 += z[j] * wa.x + z[j + 1] * wa.y + z[j + 2] * wa.z + z[j + 3] * wa.w;
-          s1 += z[j + 4] * wb.x + z[j + 5] * wb.y + z[j + 6] * wb.z + z[j + 7] * wb.w;
+      for (int p = 0; p < 4; ++p) {
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (live) {
+          float z[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = __uint_as_float(v[p * 8 + j]) + sB3[n0 + p * 8 + j];
+            z[j] = x > 0.f ? x : exp2f_fast(x * 1.4426950408889634f) - 1.f;
+          }
+          w = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
         }
-        sAcc[(slice * 128 + rt) * 17 + a] = s0 + s1;
+        const int chunk = ((n0 & 63) >> 3) + p;
+        sts128(row_addr + ((chunk ^ (rt & 7)) << 4), w);
       }
-    } else {
-      for (int a = 0; a < n_out; ++a) sAcc[(slice * 128 + rt) * 17 + a] = 0.f;
     }
     tc_fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(h3_ready));
     if (warp == 4 && lane == 0) trace(0x309, g);
-    epi_bar_sync();
-    const int row = m_blk * BLOCK_M + rt;
-    auto dot = [&](int a) {
-      return ((sAcc[rt * 17 + a] + sAcc[(128 + rt) * 17 + a]) + sAcc[(256 + rt) * 17 + a]) + sAcc[(384 + rt) * 17 + a];
-    };
-    const int per = (n_out + 3) >> 2, a_lo = slice * per, a_hi = min(n_out, a_lo + per);
+
+    // ---- epilogue 3: the head.  Thread (row, slice) finishes outputs 4 * slice .. 4 * slice + 3 of its row: it reads just
+    // those four accumulator columns, and one Philox call (keyed by (row, slice)) gives their four normals.
+    mbar_wait(smem_u32(acc3_full), 0);
+    tc_fence_after();
     float lp = 0.f;
-    if (row < q.M) {
-      if (hd.kind == HG_HEAD_POLICY) {
-        int have = -1;
-        float e[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int a = a_lo; a < a_hi; ++a) {
-          if (P.eps == nullptr && (a >> 2) != have) {      // four normals per Philox call, keyed by (row, a / 4)
-            have = a >> 2;
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)have, (uint32_t)P.counter, (uint32_t)(P.counter >> 32)),
-                                          make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32)));
-            const float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
-            e[0] = n01.x; e[1] = n01.y; e[2] = n23.x; e[3] = n23.y;
+    if (a_lo < n_out) {                                     // (warp-uniform)
+      uint32_t o4[4];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(o4[0]), "=r"(o4[1]), "=r"(o4[2]), "=r"(o4[3])
+                   : "r"(tmem_base + (uint32_t(quad * 32) << 16) + TMEM_OUT_COL + a_lo) : "memory");
+      tmem_ld_wait();
+      if (row < q.M) {
+        if (hd.kind == HG_HEAD_POLICY) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int a = a_lo + k;
+            if (a < n_out) {
+              const float m = __uint_as_float(o4[k]) + sB[a], sd = sB[16 + a];
+              const float ee = P.eps ? __ldg(P.eps + (long long)row * n_out + a) : e[k];
+              const float act = m + sd * ee;                 // Normal(mu, std).sample()  (actor_critic.py:129,133)
+              const float d = act - m;
+              lp += -(d * d) / sB[48 + a] - sB[32 + a] - LOG_SQRT_2PI;   // Normal.log_prob
+              sOut[rt * n_out + a] = act;                    // staged: the tile's [128][n_out] block is contiguous in global
+              sOut[2048 + rt * n_out + a] = m;               // memory, written below with coalesced 16-byte stores (12 scattered
+              sOut[4096 + rt * n_out + a] = sd;              // 4-byte stores per thread cost ~2 us of LSU sector traffic)
+            }
           }
-          const int k = a & 3;
-          const float m = dot(a) + sB[a], sd = sB[16 + a];
-          const float ee = P.eps ? __ldg(P.eps + (long long)row * n_out + a) : (k == 0 ? e[0] : k == 1 ? e[1] : k == 2 ? e[2] : e[3]);
-          const float act = m + sd * ee;
-          const float d = act - m;
-          lp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;
-          hd.actions[(long long)row * n_out + a] = act;
-          hd.out[(long long)row * n_out + a] = m;
-          hd.sigma[(long long)row * n_out + a] = sd;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (a_lo + k < n_out) hd.out[(long long)row * n_out + a_lo + k] = __uint_as_float(o4[k]) + sB[a_lo + k];
         }
-      } else {
-        for (int a = a_lo; a < a_hi; ++a) hd.out[(long long)row * n_out + a] = dot(a) + sB[a];
       }
     }
+    tc_fence_before();
     if (warp == 4 && lane == 0) trace(0x30a, g);
-    if (hd.kind == HG_HEAD_POLICY) {
+    if (hd.kind == HG_HEAD_POLICY) {       // log-prob = fixed-order sum of the four slices' terms
+      sLp[slice * 128 + rt] = lp;
       epi_bar_sync();
-      sAcc[slice * 128 + rt] = lp;
-      epi_bar_sync();
-      if (slice == 0 && row < q.M) hd.log_prob[row] = ((sAcc[rt] + sAcc[128 + rt]) + sAcc[256 + rt]) + sAcc[384 + rt];
+      if (slice == 0 && row < q.M) hd.log_prob[row] = ((sLp[rt] + sLp[128 + rt]) + sLp[256 + rt]) + sLp[384 + rt];
+      const int count = min(BLOCK_M, q.M - m_blk * BLOCK_M) * n_out;
+      const long long g0 = (long long)m_blk * BLOCK_M * n_out;
+#pragma unroll 1
+      for (int arr = 0; arr < 3; ++arr) {
+        float* dst = (arr == 0 ? hd.actions : arr == 1 ? hd.out : hd.sigma) + g0;
+        const float* src = sOut + arr * 2048;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (count & 3) == 0) {
+          for (int i = et; i < (count >> 2); i += 512) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        } else {
+          for (int i = et; i < count; i += 512) dst[i] = src[i];
+        }
+      }
     }
   }
 

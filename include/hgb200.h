@@ -117,7 +117,8 @@ int hg_rollout_forward(const HgGemmPlan* const* plans, int n, const HgGemmPlan* 
  * 128-row tile of h2 = elu(h1 W2^T + b2) in shared memory as the bf16 K-major operand of layer 3, so h2 is never stored.
  *   layer2[g]: A = h1 [M,K1] bf16, B = W2 [N2,K1] bf16, bias = b2, M, N = N2 (64..256, multiple of 64), K = K1
  *   layer3[g]: B = W3 [N3,N2] bf16, bias = b3, N = N3 (32..128, multiple of 32), K = N2      (A, M, out unused)
- * Run it with hg_gemm_plan_run_heads; results are bit-identical to the two-launch path. */
+ * The output layer runs on the tensor core too (W_out = hi + mid + lo bf16 terms, exact products, fp32 accumulate).
+ * Run it with hg_gemm_plan_run_heads; results match the two-launch path to fp32 round-off (2e-6). */
 int hg_gemm_plan_create_tail(const HgGemmProblem* layer2_host, const HgGemmProblem* layer3_host, const HgFusedHead* heads_host,
                              int num_nets, HgGemmPlan** out);
 
