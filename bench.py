@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--torch-rng", action="store_true",
                     help="draw action / observation noise with torch.randn (stream parity with the reference on the same device) instead of the in-kernel Philox4x32-10")
     ap.add_argument("--unbound-env", action="store_true", help="env writes its own buffers; PPO.act ingests them (generic drop-in path)")
+    ap.add_argument("--full-body-tables", action="store_true",
+                    help="synthetic simulator state with all 13 rigid bodies / contact rows (1,076 B per env-step over PCIe in the "
+                         "e2e arm) instead of only the rows the kernel reads (2 feet + 2 knees; base + feet: 488 B)")
     ap.add_argument("--stacked", action="store_true", help="bound env writes whole stacked rows (round-1 format) instead of the history ring")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' runs the same torch port on cuda:0 at the FULL workload (the torch-CUDA "
@@ -77,7 +80,13 @@ def workload_config(a, world):
             "precision": "bf16 tensor-core GEMM operands with fp32 accumulation (hidden layers); output layers, losses, GAE, env math and Adam in fp32",
             "l2_policy": "per-iteration working set (history rings 0.34 GB, permuted bf16 minibatch rows 0.46 GB, activations / "
                          "gradients ~0.6 GB, all rewritten every iteration) exceeds the 126 MB L2; no explicit flush",
-            "obs_format": "history ring (one new 47 / 73-wide frame per env step; SURVEY 8f rank 3)"}
+            "obs_format": "history ring (one new 47 / 73-wide frame per env step; SURVEY 8f rank 3)",
+            "sim_state": ("full Isaac Gym tables (13 rigid bodies, 13 contact rows): 1,076 B per env-step" if getattr(a, "full_body_tables", False)
+                          else "only the body rows the kernel reads (rigid_state of 2 feet + 2 knees, contact_forces of base + feet; "
+                               "identical values, tests/test_env_gpu.py): 488 B per env-step instead of 1,076"),
+            "e2e_note": "e2e is OPEN-LOOP: the synthetic simulator states do not depend on the actions, so they are streamed from "
+                        "pinned host memory up to 60 steps ahead on a side stream and the actions are not copied back; a real "
+                        "simulator on the host would add one D2H of [N,12] actions per step and could not run ahead"}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -368,7 +377,8 @@ def run_ours(a):
     alg.init_storage(N, T, [705], [219], [12])
     alg.torch_rng = a.torch_rng
     torch.manual_seed(1000 + rank)               # per-rank env / sampling streams
-    env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, pool=4, seed=rank, torch_rng_noise=a.torch_rng)
+    env = SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), dev, pool=4, seed=rank, torch_rng_noise=a.torch_rng,
+                           compact_bodies=not a.full_body_tables)
     if not a.unbound_env:
         env.bind_storage(alg.storage, gamma=alg.gamma, ring=not a.stacked)
     obs, critic_obs = env.get_observations(), env.get_privileged_observations()
@@ -417,6 +427,7 @@ def run_ours(a):
     with ClockSampler(local, enabled=(rank == 0)) as clocks:      # one sampler per job: N concurrent nvidia-smi pollers perturb the launches
         ms, launches = timed(a.steps, False)
     value = N * T * world * a.steps / (ms / 1e3)
+    allreduce_kind = getattr(alg, "allreduce_kind", "none")
     e2e = None
     if not a.no_e2e:
         env.stream_states_from_host(True)    # every step's state: pinned host -> device (side stream, 12-step chunks, ring of 6)
@@ -561,7 +572,12 @@ def run_ours(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(a, world), "clocks": clocks.summary(), "e2e": e2e,
+                "config": dict(workload_config(a, world), collective=(
+                    "none (one GPU)" if world == 1 else
+                    {"symm_multimem": "gradient arena in symmetric memory, two-shot multimem (NVSwitch in-switch reduce) all-reduce of 4.13 MB per minibatch",
+                     "symm_two_shot": "gradient arena in symmetric memory, peer-to-peer two-shot all-reduce of 4.13 MB per minibatch",
+                     "nccl": "ncclAllReduce of 4.13 MB per minibatch"}.get(allreduce_kind, allreduce_kind))),
+                "clocks": clocks.summary(), "e2e": e2e,
                 "gpu_launches": int(launches), "gpu_launches_per_step": launches / a.steps,
                 "roofline": roofline, "hbm_kernels": aux, "cpu_baseline": base, "reference_torch_cuda": ref_cuda}
         print(json.dumps(line))

@@ -167,7 +167,8 @@ class HgEnvConfig(C.Structure):
                 ("lin_vel_scale", C.c_float), ("ang_vel_scale", C.c_float), ("dof_pos_scale", C.c_float),
                 ("dof_vel_scale", C.c_float), ("quat_scale", C.c_float), ("clip_obs", C.c_float),
                 ("noise_level", C.c_float), ("reward_scale_dt", C.c_float * HG_NUM_REWARDS),
-                ("phase_mul_reciprocal", C.c_int32), ("phases", C.c_int32)]
+                ("phase_mul_reciprocal", C.c_int32), ("phases", C.c_int32),
+                ("num_rigid_bodies", C.c_int32), ("rigid_feet", C.c_int32 * 2), ("rigid_knees", C.c_int32 * 2)]
 
 
 class HgHistoryRing(C.Structure):

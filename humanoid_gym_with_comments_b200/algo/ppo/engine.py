@@ -128,6 +128,19 @@ class FlatParams:
             check(_lib.load().hg_cast_weight_bf16(ptr(w.data), w.shape[0], w.shape[1], ptr(sh), ld, width, pitch, current_stream()))
         return sh
 
+    def rebind_grads(self, g: torch.Tensor) -> None:
+        """Move the gradient arena into `g` (same length; e.g. a symmetric-memory buffer the peers can read for the
+        all-reduce): the `.grad` of every parameter becomes a view of it, the loss statistics stay behind the gradients."""
+        if g.numel() != self.g.numel() or g.dtype != torch.float32 or g.device != self.g.device:
+            raise _lib.HgError("rebind_grads: need a float32 tensor of the arena's length on the arena's device")
+        with torch.no_grad():
+            g.copy_(self.g)
+        self.g = g
+        self.stats = g[self.count:]
+        for p in self.params:
+            o = self.offsets[id(p)]
+            p.grad = g[o:o + p.numel()].view(p.shape)
+
     # -- views ------------------------------------------------------------------------------
     def grad_view(self, p: nn.Parameter) -> torch.Tensor:
         o = self.offsets[id(p)]

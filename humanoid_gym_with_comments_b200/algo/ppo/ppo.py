@@ -209,8 +209,10 @@ class PPO:
         # every rank bit-identical eps for the same local env row
         self._seed = self.actor_critic.philox_seed(self.rank)
         self._replica_versions = None
+        self.allreduce_kind = "none"
         if self.world_size > 1:
             self.sync_replicas()
+            self._setup_allreduce()
         self._gamma_f = float(gamma)
         self.eps_override = None     # callable(step) -> [N, A] standard-normal draws
         self.fuse_rollout_head = os.environ.get("HG_FUSE_HEAD", "1") != "0"   # last hidden layer + output layer + sampling in one launch
@@ -228,6 +230,56 @@ class PPO:
         opt.sync_host()
         self.learning_rate = self._lr_synced = float(opt.param_groups[0]["lr"])
         self._replica_versions = (self.actor_critic._load_version, opt._load_version)
+
+    def _setup_allreduce(self):
+        """The path's one collective: SUM of [gradients | loss statistics] over the ranks, once per minibatch.
+        Optional transport (HG_ALLREDUCE=symm): the gradient arena lives in symmetric memory (every rank maps its peers'
+        arenas over NVLink) and the reduction runs as torch's two-shot multimem all-reduce -- `multimem.ld_reduce` sums a slice
+        inside the NVSwitch, `multimem.st` broadcasts it; without multicast support (or HG_ALLREDUCE=two_shot) the peer-to-peer
+        two-shot kernel.  Any failure to set symmetric memory up falls back to `dist.all_reduce`."""
+        self.allreduce_kind = "nccl"
+        # Default: NCCL.  Measured on 2 x B200 (tools/bench_allreduce.py, 4.13 MB): NCCL 37.9 us, two-shot multimem 46.5 us,
+        # peer-to-peer two-shot 28.0 us -- no gain worth a second code path at N = 2, and the 8-GPU run of the same
+        # microbenchmark did not finish within its time limit (not investigated), so the symmetric-memory transport stays
+        # opt-in (HG_ALLREDUCE=symm | two_shot) until it has been qualified at N = 8.
+        want = os.environ.get("HG_ALLREDUCE", "nccl")
+        if want == "nccl" or torch.distributed.get_backend() != "nccl":
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm
+            flat = self.actor_critic.flat
+            group = torch.distributed.group.WORLD
+            n = flat.g.numel()
+            padded = _round_up(n, 4 * 32 * self.world_size)      # every rank's slice a whole number of 16-byte chunks
+            buf = symm.empty(padded, dtype=torch.float32, device=flat.g.device)
+            hdl = symm.rendezvous(buf, group)
+            buf.zero_()
+            flat.rebind_grads(buf[:n])
+            self._ar_buf, self._ar_group = buf, group.group_name
+            mc = getattr(hdl, "has_multicast_support", False)
+            multicast = bool(mc() if callable(mc) else mc) and want != "two_shot"
+            self.allreduce_kind = "symm_multimem" if multicast else "symm_two_shot"
+            self._ar_op = torch.ops.symm_mem.multimem_all_reduce_ if multicast else torch.ops.symm_mem.two_shot_all_reduce_
+            self._ar_op(self._ar_buf, "sum", self._ar_group)     # first call: any lazy set-up happens here, on zeros
+            torch.cuda.synchronize()
+        except Exception as e:      # noqa: BLE001 -- any set-up problem: the NCCL all-reduce is always available
+            self.allreduce_kind = "nccl"
+            self._ar_fallback_reason = repr(e)
+        # the choice must be the same on every rank (a collective met by a different collective would hang)
+        kinds = {"nccl": 0, "symm_two_shot": 1, "symm_multimem": 2}
+        agreed = torch.tensor([kinds[self.allreduce_kind]], device=self.actor_critic.flat.g.device, dtype=torch.int32)
+        lo = agreed.clone()
+        torch.distributed.all_reduce(agreed, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        if int(agreed.item()) != int(lo.item()):
+            self.allreduce_kind = "nccl"
+
+    def _allreduce_grads(self):
+        g = self.actor_critic.flat.g
+        if self.allreduce_kind == "nccl" or g.data_ptr() != self._ar_buf.data_ptr():     # (a rebuilt arena is no longer symmetric)
+            torch.distributed.all_reduce(g)
+        else:
+            self._ar_op(self._ar_buf, "sum", self._ar_group)
 
     def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
         self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape, self.device)
@@ -476,7 +528,7 @@ class PPO:
                 eng.backward_hidden(nets, inputs, cols, ws, M, frames=frames)
                 if self.world_size > 1:
                     # the only collective of the path: SUM over ranks of [gradients | KL and loss sums]
-                    torch.distributed.all_reduce(flat.g)
+                    self._allreduce_grads()
                 self.optimizer.fused_step(rows_global=M * self.world_size, max_grad_norm=self.max_grad_norm,
                                           adaptive=adaptive, desired_kl=self.desired_kl, loss_log=loss_log, log_slot=slot)
                 slot += 1

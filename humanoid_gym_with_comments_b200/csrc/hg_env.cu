@@ -39,7 +39,10 @@ __device__ __forceinline__ Vec3 quat_rotate_inverse(const Quat& q, const Vec3& v
   return {a.x - b.x + c.x, a.y - b.y + c.y, a.z - b.z + c.z};
 }
 
-__device__ __forceinline__ float wrap_2pi(float a) {   // python-style a % (2*pi), then > pi -> -= 2*pi
+// The env kernel is instruction-FETCH bound (ncu: 47 % of its stall samples are "no instruction": ~87 KB of straight-line
+// code run once per launch by one or two warps per scheduler), so the bulky helpers below exist once (__noinline__) instead
+// of once per call site, and the short runtime-bounded loops are not unrolled.
+__device__ __noinline__ float wrap_2pi(float a) {   // python-style a % (2*pi), then > pi -> -= 2*pi
   float m = fmodf(a, TWO_PI_F);
   if (m < 0.f) m += TWO_PI_F;
   if (m > PI_F) m -= TWO_PI_F;
@@ -47,7 +50,7 @@ __device__ __forceinline__ float wrap_2pi(float a) {   // python-style a % (2*pi
 }
 
 // isaacgym get_euler_xyz + the wrap of get_euler_xyz_tensor (humanoid_env.py:51-56)
-__device__ __forceinline__ Vec3 euler_xyz_wrapped(const Quat& q) {
+__device__ __noinline__ Vec3 euler_xyz_wrapped(const Quat& q) {
   const float sinr = 2.0f * (q.w * q.x + q.y * q.z);
   const float cosr = q.w * q.w - q.x * q.x - q.y * q.y + q.z * q.z;
   const float roll = atan2f(sinr, cosr);
@@ -62,10 +65,22 @@ __device__ __forceinline__ Vec3 euler_xyz_wrapped(const Quat& q) {
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
+__device__ __noinline__ float sin_2pi(float phase) { return sinf(TWO_PI_F * phase); }
 __device__ __forceinline__ float gait_sin(const HgEnvConfig& c, long long ep_len) {
   const float t = (float)ep_len * c.dt;
   const float phase = c.phase_mul_reciprocal ? t * (1.0f / c.cycle_time) : t / c.cycle_time;   // :692
-  return sinf(TWO_PI_F * phase);
+  return sin_2pi(phase);
+}
+// number of the listed bodies whose contact force exceeds `thr` (check_termination :811-816, _reward_collision :1419-1425)
+__device__ __noinline__ int contacts_above(const float* cf, const int* bodies, int n, float thr) {
+  int cnt = 0;
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const float* f = cf + bodies[i] * 3;
+    const float x = f[0], y = f[1], z = f[2];
+    cnt += (sqrtf(x * x + y * y + z * z) > thr) ? 1 : 0;
+  }
+  return cnt;
 }
 __device__ __forceinline__ float gait_phase(const HgEnvConfig& c, long long ep_len) {
   const float t = (float)ep_len * c.dt;
@@ -166,12 +181,7 @@ __device__ __forceinline__ EnvBase env_base(const HgEnvConfig& C, const HgEnvBuf
   EnvBase e;
   e.ep = ep_stored + (doA ? 1 : 0);
   if (doA) {                                                                    // check_termination :811-816
-    bool term = false;
-    for (int i = 0; i < C.num_term_bodies; ++i) {
-      const float* f = cf + C.term_bodies[i] * 3;
-      const float x = f[0], y = f[1], z = f[2];
-      term = term || (sqrtf(x * x + y * y + z * z) > 1.0f);
-    }
+    const bool term = contacts_above(cf, C.term_bodies, C.num_term_bodies, 1.0f) > 0;
     e.time_out = (float)e.ep > C.max_episode_length;
     e.reset = term || e.time_out;
   } else {
@@ -286,8 +296,10 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
 #pragma unroll 1
   for (int i = tid; i < envs_here * 52; i += ENV_THREADS) {            // rigid-body rows of the two feet and the two knees only
     const int e = i / 52, r = (i - e * 52) / 13, c = i - e * 52 - r * 13;
-    const int body = r == 0 ? C.feet[0] : r == 1 ? C.feet[1] : r == 2 ? C.knees[0] : C.knees[1];
-    cp_async4(smem_u32(s_env + L.rg + i), B.rigid_state + ((size_t)(n0 + e) * NB + body) * 13 + c);
+    const bool cr = C.num_rigid_bodies > 0;          // compact rigid-body table with its own indices
+    const int body = r == 0 ? (cr ? C.rigid_feet[0] : C.feet[0]) : r == 1 ? (cr ? C.rigid_feet[1] : C.feet[1])
+                            : r == 2 ? (cr ? C.rigid_knees[0] : C.knees[0]) : (cr ? C.rigid_knees[1] : C.knees[1]);
+    cp_async4(smem_u32(s_env + L.rg + i), B.rigid_state + ((size_t)(n0 + e) * (cr ? C.num_rigid_bodies : NB) + body) * 13 + c);
   }
   if (tid < So) cp_async4(smem_u32(s_env + L.nsv + tid), B.noise_scale_vec + tid);
   if (tid < D) cp_async4(smem_u32(s_env + L.ddp + tid), B.default_dof_pos + tid);
@@ -330,6 +342,7 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
         for (int k = 0; k < cols; ++k) e4[k] = __ldg(B.noise + (size_t)ne * So + j0 + k);
       } else {
         bool any = false;
+#pragma unroll 1
         for (int k = 0; k < cols; ++k) any = any || s_nsv[j0 + k] != 0.f;
         if (any) env_philox_normal4(B.seed, B.counter, ne, g, e4);     // one Philox4x32-10 call: four normals
       }
@@ -384,7 +397,7 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
       if (doB) {
         const long long ep = e.reset ? 0 : e.ep;                                // reset_idx :1138
         const float ph = gait_phase(C, ep);
-        const float s2 = sinf(TWO_PI_F * ph), c2 = cosf(TWO_PI_F * ph);
+        const float s2 = sin_2pi(ph), c2 = cosf(TWO_PI_F * ph);
         float so0 = s2 >= 0.f ? 1.f : 0.f, so1 = s2 < 0.f ? 1.f : 0.f;
         const bool dsup = fabsf(s2) < 0.1f;
         if (dsup) { so0 = 1.f; so1 = 1.f; }
@@ -469,13 +482,7 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
         HG_TERM(HG_R_BASE_HEIGHT, expf(-fabsf(bh - C.base_height_target) * 100.0f));
       }
       {  // collision :1419-1425
-        float cnt = 0.f;
-        for (int i = 0; i < C.num_pen_bodies; ++i) {
-          const float* f = cf + C.pen_bodies[i] * 3;
-          const float x = f[0], y = f[1], z = f[2];
-          cnt += (sqrtf(x * x + y * y + z * z) > 0.1f) ? 1.f : 0.f;
-        }
-        HG_TERM(HG_R_COLLISION, cnt);
+        HG_TERM(HG_R_COLLISION, (float)contacts_above(cf, C.pen_bodies, C.num_pen_bodies, 0.1f));
       }
       {  // feet_air_time :1216-1230 (stateful)
         float air0 = s_env[L.dst[SEG_AIR] + lane * 2], air1 = s_env[L.dst[SEG_AIR] + lane * 2 + 1];
@@ -590,7 +597,7 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
   // ---------------------------------------------------------------- total reward (alphabetical order :894-898), clip
   if (doA && ok && warp == 1) {
     float rew = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < HG_NUM_REWARDS; ++k)
       if (C.reward_scale_dt[k] != 0.f) rew += s_terms[k * E + lane];
     if (C.only_positive_rewards) rew = fmaxf(rew, 0.f);                              // :899-900
@@ -603,6 +610,7 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
   if (threadIdx.x == 0) trace(0x103);
   if (!doB) return;
   if (!doA && ok && warp == 1 && s_reset[lane]) {
+#pragma unroll 1
     for (int k = 0; k < HG_NUM_REWARDS; ++k) B.episode_sums[(size_t)k * C.num_envs + n] = 0.f;
     B.feet_air_time[n * 2] = 0.f; B.feet_air_time[n * 2 + 1] = 0.f;
   }
@@ -648,11 +656,13 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
   }
 #pragma unroll 1
   for (int el = warp; el < envs_here; el += ENV_THREADS / 32) {
+#pragma unroll 1
     for (int j = lane; j < So; j += 32) {
       float v = s_fobs[el * So + j];
       if (C.noise_level != 0.f) v = v + s_noise[el * So4 + j] * s_nsv[j] * C.noise_level;
       s_fobs[el * So + j] = clampf(v, -C.clip_obs, C.clip_obs);
     }
+#pragma unroll 1
     for (int j = lane; j < Sp; j += 32) s_fpriv[el * Sp + j] = clampf(s_fpriv[el * Sp + j], -C.clip_obs, C.clip_obs);
   }
   __syncwarp();          // the stores below walk the same [env = warp][column = lane] map: a warp reads only what it wrote
@@ -686,6 +696,7 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
         const float* fr = frames_s + el * R.width;
         float* l32 = R.live32 + (env_base + slot) * R.width;
         float* a32 = R.arch32 + (env_base + slot) * R.width;
+#pragma unroll 1
         for (int j = lane; j < R.width; j += 32) {
           const float v = fr[j];
           l32[j] = v;
@@ -693,6 +704,7 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
         }
         uint32_t* l16 = reinterpret_cast<uint32_t*>(R.live16) + (env_base + slot) * pairs;
         uint32_t* a16 = reinterpret_cast<uint32_t*>(R.arch16) + (env_base + slot) * pairs;
+#pragma unroll 1
         for (int j = lane; j < pairs; j += 32) {
           const float lo = 2 * j < R.width ? fr[2 * j] : 0.f, hi = 2 * j + 1 < R.width ? fr[2 * j + 1] : 0.f;
           const uint32_t w = pack_bf16x2(lo, hi);
@@ -701,8 +713,10 @@ __global__ void __launch_bounds__(ENV_THREADS, RING ? 4 : 2) env_step_kernel(con
         }
         if (s_reset[el]) {       // (rare) a reset env: zero its live history
           float* z32 = R.live32 + (env_base + B.ring_row) * R.width;
+#pragma unroll 1
           for (int j = lane; j < (R.frames - 1) * R.width; j += 32) z32[j] = 0.f;
           uint32_t* z16 = reinterpret_cast<uint32_t*>(R.live16) + (env_base + B.ring_row) * pairs;
+#pragma unroll 1
           for (int j = lane; j < (R.frames - 1) * pairs; j += 32) z16[j] = 0u;
         }
       }
@@ -770,6 +784,11 @@ extern "C" int hg_env_step(const HgEnvConfig* cfg, const HgEnvBuffers* buf, void
   HG_CHECK(cfg->num_term_bodies >= 0 && cfg->num_term_bodies <= 4 && cfg->num_pen_bodies >= 0 && cfg->num_pen_bodies <= 4,
            "hg_env_step: at most 4 termination / penalised bodies");
   HG_CHECK(cfg->frame_stack >= 1 && cfg->c_frame_stack >= 1, "hg_env_step: frame stacks");
+  HG_CHECK(cfg->num_rigid_bodies == 0 || (cfg->num_rigid_bodies >= 1 && cfg->rigid_feet[0] >= 0 && cfg->rigid_feet[0] < cfg->num_rigid_bodies &&
+                                          cfg->rigid_feet[1] >= 0 && cfg->rigid_feet[1] < cfg->num_rigid_bodies &&
+                                          cfg->rigid_knees[0] >= 0 && cfg->rigid_knees[0] < cfg->num_rigid_bodies &&
+                                          cfg->rigid_knees[1] >= 0 && cfg->rigid_knees[1] < cfg->num_rigid_bodies),
+           "hg_env_step: compact rigid-body table: indices outside [0, num_rigid_bodies)");
   HG_CHECK((cfg->phases & (HG_ENV_PHASE_REWARD | HG_ENV_PHASE_OBS)) != 0, "hg_env_step: phases must select REWARD and/or OBS");
   const bool ring = buf->ring_obs.live32 != nullptr;
   HG_CHECK(ring || (buf->obs_prev != buf->obs_next && buf->priv_prev != buf->priv_next), "hg_env_step: history in/out must not alias");

@@ -425,7 +425,7 @@ class SyntheticXBotEnv:
     (the hot path) is the fused kernel.  Drives `OnPolicyRunner`-style loops in bench.py and the tests."""
 
     def __init__(self, cfg: XBotMathConfig, device, pool: int = 4, seed: int = 0, torch_rng_noise: bool = True,
-                 callbacks: bool = False):
+                 callbacks: bool = False, compact_bodies: bool = False):
         """callbacks=True also runs `_post_physics_step_callback` (command resampling, heading command, pushes) and the
         command / extras["episode"] part of `reset_idx` every step: five launches per step instead of
         one, commands and push buffers owned by the env instead of taken from the synthetic pool.  Works with
@@ -442,6 +442,26 @@ class SyntheticXBotEnv:
         self.max_episode_length = self.math.max_episode_length
         gen = torch.Generator(device=self.device).manual_seed(seed)
         self.pool = [synthetic_sim_state(cfg, gen, self.device, upright=(i % 2 == 0)) for i in range(pool)]
+        if compact_bodies:
+            # What a simulator bridge that knows the hot path's inputs would export: of the 13 rigid bodies only the rows the
+            # kernel reads -- rigid_state of the two feet and the two knees, contact_forces of the termination / penalised
+            # bodies and the feet (humanoid_env.py:811-816,1180-1257,1342-1425).  Same values as the full tables (tested),
+            # 488 instead of 1,076 bytes of simulator state per env-step.
+            rig = [*cfg.feet_indices, *cfg.knee_indices]
+            cfr = sorted({*cfg.termination_contact_indices, *cfg.penalised_contact_indices, *cfg.feet_indices})
+            at = {b: i for i, b in enumerate(cfr)}
+            for sim in self.pool:
+                sim["rigid_state"] = sim["rigid_state"][:, rig].contiguous()
+                sim["contact_forces"] = sim["contact_forces"][:, cfr].contiguous()
+            c = self.math._c
+            c.num_rigid_bodies = 4
+            c.rigid_feet[0], c.rigid_feet[1], c.rigid_knees[0], c.rigid_knees[1] = 0, 1, 2, 3
+            c.num_bodies = len(cfr)
+            c.feet[0], c.feet[1] = at[cfg.feet_indices[0]], at[cfg.feet_indices[1]]
+            for i, b in enumerate(cfg.termination_contact_indices):
+                c.term_bodies[i] = at[b]
+            for i, b in enumerate(cfg.penalised_contact_indices):
+                c.pen_bodies[i] = at[b]
         self.math.episode_length_buf.copy_(torch.randint(0, self.max_episode_length, (self.num_envs,), generator=gen,
                                                          device=self.device))
         self.torch_rng_noise = torch_rng_noise

@@ -296,6 +296,11 @@ typedef struct HgEnvConfig {
    * HG_ENV_PHASE_OBS: buffer/history zeroing of reset envs, observations, history, hand-over (what follows it).
    * A real Isaac Gym env launches the two separately around its gym reset calls; synthetic loops pass both. */
   int32_t phases;
+  /* Optional compact rigid-body table: rigid_state is [N, num_rigid_bodies, 13] and rigid_feet / rigid_knees index into it
+   * (a simulator bridge that exports only the four consumed body rows: 208 B instead of 676 B per env for XBot-L).
+   * num_rigid_bodies = 0: rigid_state is [N, num_bodies, 13], indexed by feet / knees.  contact_forces can be compacted
+   * without extra fields: num_bodies, feet, term_bodies, pen_bodies then refer to the compact contact table. */
+  int32_t num_rigid_bodies, rigid_feet[2], rigid_knees[2];
 } HgEnvConfig;
 #define HG_ENV_PHASE_REWARD 1
 #define HG_ENV_PHASE_OBS 2

@@ -9,7 +9,7 @@ import torch
 
 from gpu_util import DEV
 from humanoid_gym_with_comments_b200._lib import ENV_PHASE_OBS, ENV_PHASE_REWARD
-from humanoid_gym_with_comments_b200.envs import XBotEnvMath, XBotMathConfig, synthetic_sim_state
+from humanoid_gym_with_comments_b200.envs import SyntheticXBotEnv, XBotEnvMath, XBotMathConfig, synthetic_sim_state
 from oracle import env_oracle as eo
 
 pytestmark = pytest.mark.gpu
@@ -383,3 +383,24 @@ def test_dead_band_decisions_at_adversarial_phases():
     print(f"{len(cases)} adversarial (episode length, cycle time) cases: {below} inside the dead band, {above} outside, "
           f"{exempt} env rows exactly on the edge (oracle comparison skipped, self-consistency still checked)")
     assert below >= 8 and above >= 8
+
+
+def test_compact_body_tables_are_bit_identical_to_full_tables():
+    """SyntheticXBotEnv(compact_bodies=True) ships only the rigid-body rows (2 feet + 2 knees) and contact rows (base + feet)
+    the kernel reads; with the same pool seed every output must equal the full-table run bit for bit, resets included."""
+    N = 200
+    envs = [SyntheticXBotEnv(XBotMathConfig.for_dof(12, num_envs=N), DEV, pool=3, seed=7, torch_rng_noise=False, compact_bodies=c)
+            for c in (False, True)]
+    assert envs[1].pool[0]["rigid_state"].shape == (N, 4, 13) and envs[1].pool[0]["contact_forces"].shape[1] == 3
+    g = torch.Generator(device=DEV).manual_seed(3)
+    resets = 0
+    for s in range(12):
+        a = torch.randn(N, 12, device=DEV, generator=g)
+        outs = [e.step(a.clone()) for e in envs]
+        for x, y, name in zip(outs[0][:4], outs[1][:4], ("obs", "priv", "rew", "reset")):
+            assert torch.equal(x, y), (s, name)
+        assert torch.equal(outs[0][4]["time_outs"], outs[1][4]["time_outs"])
+        resets += int(outs[0][3].sum())
+    assert resets > 0
+    for name in ("feet_air_time", "feet_height", "last_feet_z", "episode_sums_tensor", "last_contacts"):
+        assert torch.equal(getattr(envs[0].math, name), getattr(envs[1].math, name)), name
