@@ -545,7 +545,7 @@ def run_ours(a):
             st.env_stored = None
         us = time_calls(env_once, min(T - 1, 40))
         if st.ring_enabled:      # history ring: newest frame only -- fp32 live + fp32 archive + bf16 live, actor and critic, + ~0.9 KB state
-            env_bytes = (2 * 4.0 * (47 + 73) + 2.0 * (48 + 80) + 900.0) * N
+            env_bytes = (2 * 4.0 * (47 + 73) + 2 * 2.0 * (48 + 80) + 900.0) * N     # fp32 live + archive, bf16 live + archive, state
         else:                    # SURVEY 8d K-a: history shift + state, D = 12
             env_bytes = (4.0 * (47 * 29 + 73 * 5) + 900.0) * N
         st.step = 0

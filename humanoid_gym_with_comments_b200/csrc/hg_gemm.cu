@@ -40,7 +40,8 @@ struct Cfg {
   static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;          // 8 / 16 / 32 KB (per CTA)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // per-warp staging tile: 32 x 33 floats for the transposing split-K epilogue, 32 rows x 80 B for the bf16 ones
-  static constexpr int EPI_TILE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 32 * 33 * 4 : 32 * 80;
+  // (+ 256 B behind the bf16 tiles: the warp's slice of the bias vector, fetched before the accumulator is waited for)
+  static constexpr int EPI_TILE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 32 * 33 * 4 : 32 * 80 + 256;
   static constexpr bool F32_OUT = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32);
   // epilogue warps: 4 per scheduler for the bf16 epilogues (they bound the short-K launches: 16 beat 8 by ~20 %);
   // the fp32 ones sit behind K = rows main loops and keep 8 so that their 4 KB staging tiles leave a deeper TMA ring
@@ -269,7 +270,7 @@ __device__ __forceinline__ void prefetch_act(const DevProblem& q, int row_base, 
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int n0, uint32_t (&v)[32], int lane, float* tile,
-                                               const uint4 (&pre)[4], float* s_colsum) {
+                                               const uint4 (&pre)[4], float* s_colsum, const float* bias_s) {
   const bool row_ok = row < q.M;
   const bool full = (n0 + 32 <= q.N);
   if constexpr (EPI == HG_EPI_STORE_F32) {
@@ -302,15 +303,10 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
   } else if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(q.out) + (long long)row * q.ldo + n0;
     float z[32], bv[32];
-    if (q.bias && full && ((reinterpret_cast<uintptr_t>(q.bias) & 15) == 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(q.bias + n0 + j));
-        bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) bv[j] = (q.bias && n0 + j < q.N) ? __ldg(q.bias + n0 + j) : 0.f;
+    for (int j = 0; j < 32; j += 4) {        // the chunk's biases out of the warp's shared-memory copy (zero past N / without bias)
+      const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j);
+      bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -778,6 +774,13 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) prefetch_act(q, row - lane, col0 + c * 32, lane, pre[c]);   // (bounds-checked inside)
       }
+      if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16) {
+        // the slice's biases -> shared memory BEFORE the accumulator is waited for: a global load per chunk sat on the
+        // epilogue's critical path (~0.5-1 us per tile; it matters for the rollout launches, whose last epilogue is exposed)
+        float* bs = tile + 640;
+        for (int j = lane; j < SLICE; j += 32) bs[j] = (q.bias && col0 + j < q.N) ? __ldg(q.bias + col0 + j) : 0.f;
+        __syncwarp();
+      }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       if (warp == 4 && lane == 0) trace(0x205, it);
@@ -792,7 +795,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
 #pragma unroll
           for (int j = 0; j < 32; ++j) asm volatile("" ::"r"(v[j]));
 #else
-          epilogue_chunk<EPI>(q, row, col0 + c * 32, v, lane, tile, pre[DELU ? c : 0], s_colsum);
+          epilogue_chunk<EPI>(q, row, col0 + c * 32, v, lane, tile, pre[DELU ? c : 0], s_colsum, tile + 640 + c * 32);
 #endif
         }
       }
@@ -865,7 +868,7 @@ constexpr int WOUT_KB_BYTES = 16 * BLOCK_K * 2;           // 2 KB
 constexpr int WOUT_TERM_BYTES = 2 * WOUT_KB_BYTES;        // 4 KB
 constexpr int BAR_OFF = WOUT_OFF + 3 * WOUT_TERM_BYTES;
 constexpr int HEAD_OFF = BAR_OFF + 256;
-constexpr int HEAD_BYTES = (128 + 64) * 4;                // layer-3 bias [128] + output bias [16] / std [16] / log std [16] / 2 std^2 [16]
+constexpr int HEAD_BYTES = (128 + 64 + 256) * 4;          // layer-3 bias [128] + output bias [16] / std [16] / log std [16] / 2 std^2 [16] + layer-2 bias [256]
 constexpr int SMEM_TOTAL = HEAD_OFF + HEAD_BYTES + 1024;
 constexpr int TMEM_OUT_COL = 384;                         // output-layer accumulator: 16 columns behind layer 2 (0-255) and layer 3 (256-383)
 constexpr int THREADS = 128 + 32 * 16;
@@ -1037,6 +1040,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
     const int n_out = hd.n_out;
     float* sB3 = sm;                   // [128] layer-3 bias
     float* sB = sm + 128;              // [16] output bias, [16] std, [16] log std, [16] 2 std^2
+    float* sB2 = sm + 192;             // [256] layer-2 bias (a global load per use sat on the critical path of epilogue 1)
     float* sLp = reinterpret_cast<float*>(smem + LP_OFF);    // [4][128] log-prob partial sums (h2 region, dead by then)
     float* sOut = sLp + 512;                                 // [3][128 x 16] actions / mu / sigma of the tile
     // output-layer weights -> bf16 hi / mid / lo in the canonical K-major SWIZZLE_128B layout (rows >= n_out, k >= N3: zero),
@@ -1057,6 +1061,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
         *reinterpret_cast<__nv_bfloat16*>(wb + 2 * WOUT_TERM_BYTES + off) = lo;
       }
       if (et < 128) sB3[et] = (q.b3 && et < q.N3) ? __ldg(q.b3 + et) : 0.f;
+      if (et >= 256) sB2[et - 256] = (et - 256 < q.N2) ? __ldg(q.b2 + et - 256) : 0.f;
       if (et < 16) {
         const float sd = (hd.kind == HG_HEAD_POLICY && et < n_out) ? __ldg(hd.std + et) : 1.f;
         sB[et] = et < n_out ? __ldg(hd.b + et) : 0.f;
@@ -1077,6 +1082,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
       const float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
       e[0] = n01.x; e[1] = n01.y; e[2] = n23.x; e[3] = n23.y;
     }
+    epi_bar_sync();                                                 // sB2 / sB3 / sB staged by every epilogue thread
     // ---- epilogue 1: h2 = bf16(elu(acc + b2)) -> shared memory, K-major SWIZZLE_128B (16-byte chunk index XOR row % 8)
     mbar_wait(smem_u32(acc1_full), 0);
     tc_fence_after();
@@ -1094,7 +1100,7 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
           float z[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float t = __uint_as_float(v[p * 8 + j]) + __ldg(q.b2 + n0 + p * 8 + j);
+            const float t = __uint_as_float(v[p * 8 + j]) + sB2[n0 + p * 8 + j];
             z[j] = t > 0.f ? t : exp2f_fast(t * 1.4426950408889634f) - 1.f;
           }
           const uint4 w = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
@@ -1108,7 +1114,6 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(h2_ready));
     if (warp == 4 && lane == 0) trace(0x305);
-    epi_bar_sync();                                                 // sB3 / sB staged by every epilogue thread
 
     // ---- epilogue 2: h3 = bf16(elu(acc + b3)) -> shared memory (over the h2 tile: layer 3 has read it), the A operand of the
     // output layer; dead 32-column chunks (N3 < 128) are zero-filled, their weights are zero too

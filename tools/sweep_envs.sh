@@ -8,7 +8,7 @@ sizes="$@"
 : > gpurun_out/env_sweep.jsonl
 for e in $sizes; do
   steps=10; [ $e -ge 16384 ] && steps=4
-  timeout 600 python bench.py --envs $e --steps $steps --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/sweep_$e.log 2>&1
+  timeout 600 python bench.py --envs $e --steps $steps --warmup 3 --no-cpu-baseline --no-ref-cuda --no-e2e > gpurun_out/sweep_$e.log 2>&1
   rc=$?
   tail -1 gpurun_out/sweep_$e.log | grep '^{' >> gpurun_out/env_sweep.jsonl || echo "{\"envs_per_gpu\": $e, \"failed\": $rc}" >> gpurun_out/env_sweep.jsonl
   echo "envs $e exit $rc"
