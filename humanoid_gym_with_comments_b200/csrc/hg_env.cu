@@ -845,6 +845,13 @@ extern "C" int hg_env_step(const HgEnvConfig* cfg, const HgEnvBuffers* buf, void
     return L;
   };
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool configured = false;
+  if (!configured) {       // 32 envs per block stage ~60 KB: above the 48 KB a kernel gets without asking
+    HG_CUDA(cudaFuncSetAttribute(env_step_kernel<16, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    HG_CUDA(cudaFuncSetAttribute(env_step_kernel<16, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    HG_CUDA(cudaFuncSetAttribute(env_step_kernel<32, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
   if (!ring) {
     const EnvStage L = make_stage(16);
     HG_CUDA(launch_kernel(env_step_kernel<16, 512, false>, dim3((cfg->num_envs + 15) / 16), dim3(512), (size_t)L.total * 4, st, 1, *cfg, *buf, L));

@@ -65,6 +65,7 @@ struct DevProblem {
   int a_mn, b_mn;
   int k_splits, kb_per_split, num_kb;
   int tiles_m, tiles_n;
+  unsigned inv_tiles_m, inv_tiles_n;   // ceil(2^32 / d): x / d == __umulhi(x, inv) for the tile counts that occur (x * d < 2^32)
   int tile_begin, tile_end;
   void* out;
   long long ldo;
@@ -111,13 +112,16 @@ __device__ __forceinline__ Tile decode_tile(const GroupParams& P, int t) {
   int g = 0;
   while (g + 1 < P.num_problems && t >= P.p[g].tile_end) ++g;
   const DevProblem& q = P.p[g];
-  int local = t - q.tile_begin;
+  // (every warp of the CTA decodes every tile: the four runtime divisions this replaces were ~250 instructions and
+  // 10 % of the epilogue samples of the rollout launches)
+  const unsigned local = (unsigned)(t - q.tile_begin);
   Tile ti;
   ti.g = g;
-  ti.n_blk = local % q.tiles_n;
-  local /= q.tiles_n;
-  ti.m_blk = local % q.tiles_m;
-  int ks = local / q.tiles_m;
+  const unsigned l1 = q.tiles_n == 1 ? local : __umulhi(local, q.inv_tiles_n);
+  ti.n_blk = (int)(local - l1 * (unsigned)q.tiles_n);
+  const unsigned ks_u = q.tiles_m == 1 ? l1 : __umulhi(l1, q.inv_tiles_m);
+  ti.m_blk = (int)(l1 - ks_u * (unsigned)q.tiles_m);
+  const int ks = (int)ks_u;
   ti.kb_begin = ks * q.kb_per_split;
   ti.kb_end = min(q.num_kb, ti.kb_begin + q.kb_per_split);
   return ti;
@@ -189,8 +193,12 @@ __device__ __forceinline__ void tile_colsum_mma(uint32_t tile_addr, int lane, fl
 // Write the warp's 32 rows x 32 columns (one row per lane, fp32 in registers) as bf16 with COALESCED global stores:
 // each lane parks its 64-byte row in the warp's shared tile, then 4 lanes cooperate on each row segment, so one
 // store instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.
-__device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* tile, int lane, __nv_bfloat16* out_col0,
-                                                long long ldo, int row_base, int M, float* colsum = nullptr) {
+// `out_p` is THIS lane's first 16-byte piece (row lane/4 of the warp's 32 rows, piece lane%4 of the chunk), `ld_u4` the
+// distance of 8 rows in 16-byte units (= the row pitch in elements), `rows_left` the number of valid rows of the warp's 32: the
+// epilogues are issue-bound (ncu: 1,086 warp instructions per 32 x 32 chunk of the dX launches, of which 89 in these four
+// stores and 175 in the four activation loads when every access recomputed row * ld in 64 bits from the problem table).
+__device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* tile, int lane, uint4* out_p, long long ld_u4,
+                                                int rows_left, float* colsum = nullptr) {
   const uint32_t tb = smem_u32(tile);
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
@@ -216,16 +224,17 @@ __device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* til
     }
     colsum[lane] += mine;                 // this warp's own shared-memory accumulator (flushed once at the end of the launch)
   }
+  const int r0 = lane >> 2;
+  const uint32_t src = tb + r0 * EPI_ROW_PITCH + (lane & 3) * 16;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = i * 8 + (lane >> 2), piece = lane & 3;
-    const uint4 w = lds128(tb + r * EPI_ROW_PITCH + piece * 16);
+    const uint4 w = lds128(src + i * 8 * EPI_ROW_PITCH);
 #ifdef HG_DBG_NOSTORE
-    if (row_base + r < M && w.x == 0x12345678u)
+    if (r0 + 8 * i < rows_left && w.x == 0x12345678u)
 #else
-    if (row_base + r < M)
+    if (r0 + 8 * i < rows_left)
 #endif
-      *(reinterpret_cast<uint4*>(out_col0 + (long long)(row_base + r) * ldo) + piece) = w;
+      out_p[i * ld_u4] = w;
   }
   __syncwarp();
 }
@@ -254,23 +263,27 @@ __device__ __forceinline__ void tile_colsum_mma(uint32_t tile_addr, int lane, fl
 
 // Activation rows of the layer below for one 32x32 chunk, in the coalesced pattern of store_rows_bf16 (4 lanes per
 // 64-byte row segment).  Issued BEFORE the accumulator barrier so the HBM latency hides behind the tile's main loop.
-__device__ __forceinline__ void prefetch_act(const DevProblem& q, int row_base, int n0, int lane, uint4 (&pre)[4]) {
+// `act_p`: this lane's first 16-byte piece of the chunk (see store_rows_bf16); `live`: the chunk is a full chunk of the problem.
+__device__ __forceinline__ void prefetch_act(const uint4* act_p, long long ld_u4, int rows_left, bool live, int lane, uint4 (&pre)[4]) {
+  const int r0 = lane >> 2;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-#ifdef HG_DX_DIRECT_ACT      // A/B variant: every lane fetches its OWN row (no shared-memory staging, 4x the L1 wavefronts)
-    const int r = lane, piece = i;
-#else
-    const int r = i * 8 + (lane >> 2), piece = lane & 3;
-#endif
     pre[i] = make_uint4(0, 0, 0, 0);
-    if (n0 + 32 <= q.N && row_base + r < q.M)
-      pre[i] = __ldg(reinterpret_cast<const uint4*>(q.act + (long long)(row_base + r) * q.ldact + n0) + piece);
+    if (live && r0 + 8 * i < rows_left) pre[i] = __ldg(act_p + i * ld_u4);
   }
 }
 
+// Per-(warp, tile) addressing shared by the chunks of a tile, computed once after the tile decode.
+struct EpiCtx {
+  uint4* out_p;          // bf16 outputs: this lane's piece of chunk 0 (chunk c: + 4 c)
+  const uint4* act_p;    // DELU: the activation tile, same addressing
+  long long ldo_u4, ldact_u4;   // 8 rows further, in 16-byte units
+  int rows_left;         // valid rows of the warp's 32 (<= 0: none)
+};
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int n0, uint32_t (&v)[32], int lane, float* tile,
-                                               const uint4 (&pre)[4], float* s_colsum, const float* bias_s) {
+                                               const uint4 (&pre)[4], float* s_colsum, const float* bias_s, const EpiCtx& X, int c) {
   const bool row_ok = row < q.M;
   const bool full = (n0 + 32 <= q.N);
   if constexpr (EPI == HG_EPI_STORE_F32) {
@@ -319,7 +332,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
 #endif
     }
     if (full) {
-      store_rows_bf16(z, tile, lane, reinterpret_cast<__nv_bfloat16*>(q.out) + n0, q.ldo, row - lane, q.M);
+      store_rows_bf16(z, tile, lane, X.out_p + 4 * c, X.ldo_u4, X.rows_left);
     } else if (row_ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -333,7 +346,6 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
       // activation rows of the layer below: coalesced global -> shared (4 lanes per 64-byte row segment), then each
       // lane reads back its own row
       const uint32_t tb = smem_u32(tile);
-      const int row_base = row - lane;
 #ifndef HG_DX_DIRECT_ACT
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -363,11 +375,10 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
       }
       __syncwarp();
 #ifndef HG_COLSUM_BUTTERFLY
-      store_rows_bf16(d, tile, lane, reinterpret_cast<__nv_bfloat16*>(q.out) + n0, q.ldo, row_base, q.M,
-                      q.colsum ? s_colsum + q.colsum_off + n0 : nullptr);
+      store_rows_bf16(d, tile, lane, X.out_p + 4 * c, X.ldo_u4, X.rows_left, q.colsum ? s_colsum + q.colsum_off + n0 : nullptr);
       return;
 #else     // A/B switch (tools/build_variant.sh): fp32 shuffle butterfly below
-      store_rows_bf16(d, tile, lane, reinterpret_cast<__nv_bfloat16*>(q.out) + n0, q.ldo, row_base, q.M);
+      store_rows_bf16(d, tile, lane, X.out_p + 4 * c, X.ldo_u4, X.rows_left);
 #endif
     } else {
 #pragma unroll
@@ -735,7 +746,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_cg<CG>(smem_u32(&tfull_bar[acc]));        // accumulator complete -> epilogues
-        trace(0x204, it);
+        if (it < 4) trace(0x204, it);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -768,11 +779,26 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
       const int row = (ti.m_blk * CG + rank) * BLOCK_M + quad * 32 + lane;
       const int col0 = ti.n_blk * BLOCK_N + half * SLICE;
       const int nchunks = q.N > col0 ? min(CHUNKS, (q.N - col0 + 31) >> 5) : 0;
+      // addressing of this warp's 32 rows x SLICE columns, once per tile (bf16 epilogues; rows are 16-byte aligned: checked
+      // by the host)
+      EpiCtx X;
+      {
+        const int row_w = row - lane, r0 = lane >> 2, piece = lane & 3;
+        X.rows_left = q.M - row_w;
+        X.ldo_u4 = q.ldo;              // 8 rows further, in 16-byte units: 8 * ld elements * 2 B / 16 B = ld
+        X.ldact_u4 = q.ldact;
+        X.out_p = nullptr;
+        X.act_p = nullptr;
+        if constexpr (!K::F32_OUT)
+          X.out_p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(q.out) + (long long)(row_w + r0) * q.ldo + col0) + piece;
+        if constexpr (DELU)
+          X.act_p = reinterpret_cast<const uint4*>(q.act + (long long)(row_w + r0) * q.ldact + col0) + piece;
+      }
       // DELU: the activation rows are requested BEFORE the accumulator barrier, their latency hides behind the main loop
       uint4 pre[DELU ? CHUNKS : 1][4];
       if constexpr (DELU) {
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c) prefetch_act(q, row - lane, col0 + c * 32, lane, pre[c]);   // (bounds-checked inside)
+        for (int c = 0; c < CHUNKS; ++c) prefetch_act(X.act_p + 4 * c, X.ldact_u4, X.rows_left, col0 + c * 32 + 32 <= q.N, lane, pre[c]);
       }
       if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16) {
         // the slice's biases -> shared memory BEFORE the accumulator is waited for: a global load per chunk sat on the
@@ -783,7 +809,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
       }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
-      if (warp == 4 && lane == 0) trace(0x205, it);
+      if (warp == 4 && lane == 0 && it < 4) trace(0x205, it);
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + half * SLICE;
 #pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
@@ -791,12 +817,14 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
+          if (warp == 4 && lane == 0 && it < 2 && c < 2) trace(0x208, it * 2 + c);
 #if defined(HG_DBG_EPI_NONE)
 #pragma unroll
           for (int j = 0; j < 32; ++j) asm volatile("" ::"r"(v[j]));
 #else
-          epilogue_chunk<EPI>(q, row, col0 + c * 32, v, lane, tile, pre[DELU ? c : 0], s_colsum, tile + 640 + c * 32);
+          epilogue_chunk<EPI>(q, row, col0 + c * 32, v, lane, tile, pre[DELU ? c : 0], s_colsum, tile + 640 + c * 32, X, c);
 #endif
+          if (warp == 4 && lane == 0 && it < 2 && c < 2) trace(0x209, it * 2 + c);
         }
       }
       tc_fence_before();
@@ -809,7 +837,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
                        ::"r"(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK) : "memory");
         }
       }
-      if (warp == 4 && lane == 0) trace(0x206, it);
+      if (warp == 4 && lane == 0 && it < 4) trace(0x206, it);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if constexpr (DELU) {      // one flush per CTA and launch: (columns / 32) coalesced REDs instead of one per 32 x 32 chunk
@@ -1319,6 +1347,10 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
     q.k_splits = (q.num_kb + q.kb_per_split - 1) / q.kb_per_split;   // no empty split
     q.tiles_m = (h.M + BLOCK_M * cg - 1) / (BLOCK_M * cg);
     q.tiles_n = (h.N + block_n - 1) / block_n;
+    q.inv_tiles_m = (unsigned)((0x100000000ull + (unsigned)q.tiles_m - 1) / (unsigned)q.tiles_m);
+    q.inv_tiles_n = (unsigned)((0x100000000ull + (unsigned)q.tiles_n - 1) / (unsigned)q.tiles_n);
+    HG_CHECK((unsigned long long)q.tiles_m * q.tiles_n * q.k_splits * (unsigned long long)(q.tiles_m > q.tiles_n ? q.tiles_m : q.tiles_n) < 0x100000000ull,
+             "problem %d: too many tiles for the reciprocal tile decode", g);
     q.tile_begin = tiles;
     tiles += q.tiles_m * q.tiles_n * q.k_splits;
     q.tile_end = tiles;

@@ -193,28 +193,32 @@ class XBotEnvMath:
     # ------------------------------------------------------------------ callback, pushes, extras
     def _callback_state(self):
         if not hasattr(self, "commands"):
-            N, z = self.num_envs, lambda *s, **k: torch.zeros(*s, device=self.device, **k)
-            self.commands = z(N, 4)                      # x vel, y vel, yaw vel, heading (:271)
-            self.rand_push_force, self.rand_push_torque = z(N, 3), z(N, 3)
-            self.root_vel_prepush = z(N, 6)
-            self.common_step_counter = 0
-            self.episode_means_tensor = z(HG_NUM_REWARDS)
-            self.episode_reset_count = z(1, dtype=torch.int32)
-            cfg = self.cfg
-            self.resampling_steps = int(cfg.resampling_time / cfg.dt)                  # :1005
-            self.push_interval = math.ceil(cfg.push_interval_s / cfg.dt)               # :191
-            a = HgCommandArgs()
-            a.num_envs, a.resampling_steps, a.heading_command = N, self.resampling_steps, 1 if cfg.heading_command else 0
-            for i, k in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw", "heading")):
-                lo, hi = cfg.command_ranges[k]
-                a.cmd_scale[i], a.cmd_lo[i] = hi - lo, lo                              # python double difference, cast once
-            a.push_vel_scale, a.push_vel_lo = cfg.max_push_vel_xy - (-cfg.max_push_vel_xy), -cfg.max_push_vel_xy
-            a.push_ang_scale, a.push_ang_lo = cfg.max_push_ang_vel - (-cfg.max_push_ang_vel), -cfg.max_push_ang_vel
-            a.commands, a.rand_push_force, a.rand_push_torque = ptr(self.commands), ptr(self.rand_push_force), ptr(self.rand_push_torque)
-            a.root_vel_prepush = ptr(self.root_vel_prepush)
-            a.episode_length_buf, a.reset_buf = ptr(self.episode_length_buf), ptr(self.reset_buf)
-            a.seed = self.seed
-            self._cmd_args = a
+            with torch.inference_mode(False):          # persistent buffers: never inference tensors, whoever triggers this first
+                self._make_callback_state()
+
+    def _make_callback_state(self):
+        N, z = self.num_envs, lambda *s, **k: torch.zeros(*s, device=self.device, **k)
+        self.commands = z(N, 4)                      # x vel, y vel, yaw vel, heading (:271)
+        self.rand_push_force, self.rand_push_torque = z(N, 3), z(N, 3)
+        self.root_vel_prepush = z(N, 6)
+        self.common_step_counter = 0
+        self.episode_means_tensor = z(HG_NUM_REWARDS)
+        self.episode_reset_count = z(1, dtype=torch.int32)
+        cfg = self.cfg
+        self.resampling_steps = int(cfg.resampling_time / cfg.dt)                  # :1005
+        self.push_interval = math.ceil(cfg.push_interval_s / cfg.dt)               # :191
+        a = HgCommandArgs()
+        a.num_envs, a.resampling_steps, a.heading_command = N, self.resampling_steps, 1 if cfg.heading_command else 0
+        for i, k in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw", "heading")):
+            lo, hi = cfg.command_ranges[k]
+            a.cmd_scale[i], a.cmd_lo[i] = hi - lo, lo                              # python double difference, cast once
+        a.push_vel_scale, a.push_vel_lo = cfg.max_push_vel_xy - (-cfg.max_push_vel_xy), -cfg.max_push_vel_xy
+        a.push_ang_scale, a.push_ang_lo = cfg.max_push_ang_vel - (-cfg.max_push_ang_vel), -cfg.max_push_ang_vel
+        a.commands, a.rand_push_force, a.rand_push_torque = ptr(self.commands), ptr(self.rand_push_force), ptr(self.rand_push_torque)
+        a.root_vel_prepush = ptr(self.root_vel_prepush)
+        a.episode_length_buf, a.reset_buf = ptr(self.episode_length_buf), ptr(self.reset_buf)
+        a.seed = self.seed
+        self._cmd_args = a
 
     def post_physics_callback(self, root_states: torch.Tensor, u_cmd: Optional[torch.Tensor] = None,
                               u_push: Optional[torch.Tensor] = None, ep_increment: int = 1) -> bool:
@@ -637,7 +641,8 @@ class SyntheticXBotEnv:
                 st.env_stored = (t, self.math.rew_buf.data_ptr(), self.math.reset_buf.data_ptr(), float(self._store_gamma))
         if self.callbacks:
             if not hasattr(self, "_root_scratch"):
-                self._root_scratch = torch.empty_like(sim["root_states"])
+                with torch.inference_mode(False):      # (a buffer first made under inference_mode could not be written outside it)
+                    self._root_scratch = torch.empty(sim["root_states"].shape, device=self.device)
             self._root_scratch.copy_(sim["root_states"])           # a push overwrites root velocities in place
             sim = dict(sim, root_states=self._root_scratch)
             ur = (lambda *sh: torch.rand(*sh, device=self.device)) if self.torch_rng_noise else (lambda *sh: None)

@@ -74,11 +74,12 @@ def test_ring_golden_replay(D, golden_dir):
             live = {0: last}
 
 
-def test_ring_equals_stacked_4096():
-    """4096 envs, 3 iterations x 12 steps with ~3 % resets per step: the ring's live views and the rows re-stacked from its
-    archive are BIT-IDENTICAL to the stacked format (same kernel math, different history plumbing), as are rewards, flags and
-    every piece of persistent env state."""
-    N, T, ITERS = 4096, 12, 3
+@pytest.mark.parametrize("N,T,ITERS,min_resets", [(4096, 12, 3, 500), (5003, 6, 2, 200)])
+def test_ring_equals_stacked(N, T, ITERS, min_resets):
+    """3 iterations x 12 steps with ~3 % resets per step: the ring's live views and the rows re-stacked from its archive are
+    BIT-IDENTICAL to the stacked format (same kernel math, different history plumbing), as are rewards, flags and every
+    piece of persistent env state.  4096 envs run the 16-envs-per-block ring kernel, 5003 the 32-envs-per-block one (more
+    than two blocks per SM; ~60 KB of staged inputs per block, a ragged last block)."""
     cfg = XBotMathConfig.for_dof(12, num_envs=N)
     g = torch.Generator(device=DEV).manual_seed(21)
     a, b = XBotEnvMath(cfg, DEV), XBotEnvMath(cfg, DEV)
@@ -107,7 +108,7 @@ def test_ring_equals_stacked_4096():
     for name in ("actions", "last_actions", "last_last_actions", "last_dof_vel", "last_root_vel", "feet_air_time", "feet_height",
                  "last_feet_z", "ref_dof_pos", "episode_length_buf", "episode_sums_tensor"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
-    assert resets > 500
+    assert resets > min_resets
 
 
 def make_alg(N, T, seed=0):
