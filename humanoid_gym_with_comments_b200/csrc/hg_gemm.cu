@@ -39,9 +39,11 @@ struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KB
   static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;          // 8 / 16 / 32 KB (per CTA)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // per-warp staging tile: 32 x 33 floats for the transposing split-K epilogue, 32 rows x 80 B for the bf16 ones
-  // (+ 256 B behind the bf16 tiles: the warp's slice of the bias vector, fetched before the accumulator is waited for)
-  static constexpr int EPI_TILE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 32 * 33 * 4 : 32 * 80 + 256;
+  // per-warp staging tile: 32 x 33 floats for the transposing split-K epilogue; for the bf16 ones 32 rows x 64 B, dense, in
+  // the SWIZZLE_64B layout (16-byte chunk index XOR (row / 2) % 4: conflict-free 16-byte accesses) -- the source of the
+  // TMA store of the chunk.  Behind ALL tiles: 256 B per warp for its slice of the bias vector.
+  static constexpr int EPI_TILE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 32 * 33 * 4 : 32 * 64;
+  static constexpr int BIAS_SLICE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 0 : 256;
   static constexpr bool F32_OUT = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32);
   // epilogue warps: 4 per scheduler for the bf16 epilogues (they bound the short-K launches: 16 beat 8 by ~20 %);
   // the fp32 ones sit behind K = rows main loops and keep 8 so that their 4 KB staging tiles leave a deeper TMA ring
@@ -54,9 +56,10 @@ struct Cfg {
   // (one array per TMEM lane quarter: slot (quarter, column) has exactly one owner warp, so no shared atomics -- fp32
   // shared atomics are CAS loops)
   static constexpr int COLSUM_BYTES = (EPI == HG_EPI_DELU_BF16) ? 4 * HG_MAX_COLSUM_COLS * 4 : 0;
-  static constexpr int EPI_BYTES = (EPI == HG_EPI_BIAS_ELU_HEAD) ? HEAD_BYTES : EPI_WARPS * EPI_TILE_BYTES + COLSUM_BYTES;
-  static constexpr int STAGES = (SMEM_BUDGET - EPI_BYTES) / STAGE_BYTES;  // 3..7 deep TMA ring
-  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
+  static constexpr int EPI_BYTES = (EPI == HG_EPI_BIAS_ELU_HEAD) ? HEAD_BYTES : EPI_WARPS * (EPI_TILE_BYTES + BIAS_SLICE_BYTES) + COLSUM_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET - 768 - EPI_BYTES) / STAGE_BYTES;  // 3..7 deep TMA ring
+  // ring | barriers (256 B, padded to 1 KB so that the staging tiles stay 1024-byte aligned) | tiles | bias slices | column sums
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 1024 + EPI_BYTES;
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
@@ -80,6 +83,7 @@ struct DevProblem {
 struct alignas(64) GroupParams {
   CUtensorMap tma_a[HG_MAX_GROUP];
   CUtensorMap tma_b[HG_MAX_GROUP];
+  CUtensorMap tma_out[HG_MAX_GROUP];   // bf16 epilogues: output [M, N], box {32 columns, 32 rows}, SWIZZLE_64B (the chunk of one warp)
   DevProblem p[HG_MAX_GROUP];
   int num_problems;
   int total_tiles;
@@ -186,27 +190,42 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   return w;
 }
 
-constexpr int EPI_ROW_PITCH = 80;   // bytes per staged row: 64 B of bf16 + 16 B pad (conflict-free 16-byte accesses)
+// Byte offset of 16-byte chunk `c16` (0..3) of row `row` (0..31) in a warp's staged 32 x 32 bf16 tile: dense 64-byte rows
+// in the TMA SWIZZLE_64B pattern (chunk index XOR bits 7-8 of the address = (row / 2) % 4).  Eight lanes of a 16-byte
+// access phase hit eight different 16-byte bank groups whether they walk rows (one row per lane) or a row's chunks.
+__device__ __forceinline__ uint32_t epi_off(int row, int c16) { return (uint32_t)(row * 64 + ((c16 ^ ((row >> 1) & 3)) << 4)); }
+
+// TMA store of a staged tile: [32 rows x 32 columns] bf16 at (col, row) of the output tensor; rows / columns outside the
+// tensor are clipped by the hardware.  One lane issues it after every lane has fenced its shared-memory writes.
+__device__ __forceinline__ void tma_store_tile(const void* tmap, uint32_t src, int col, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(col), "r"(row) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the staged tile may be overwritten once the bulk store has READ it
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tile_colsum_mma(uint32_t tile_addr, int lane, float (&c)[4][2]);
 
-// Write the warp's 32 rows x 32 columns (one row per lane, fp32 in registers) as bf16 with COALESCED global stores:
-// each lane parks its 64-byte row in the warp's shared tile, then 4 lanes cooperate on each row segment, so one
-// store instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.
-// `out_p` is THIS lane's first 16-byte piece (row lane/4 of the warp's 32 rows, piece lane%4 of the chunk), `ld_u4` the
-// distance of 8 rows in 16-byte units (= the row pitch in elements), `rows_left` the number of valid rows of the warp's 32: the
-// epilogues are issue-bound (ncu: 1,086 warp instructions per 32 x 32 chunk of the dX launches, of which 89 in these four
-// stores and 175 in the four activation loads when every access recomputed row * ld in 64 bits from the problem table).
-__device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* tile, int lane, uint4* out_p, long long ld_u4,
-                                                int rows_left, float* colsum = nullptr) {
+// Write the warp's 32 rows x 32 columns (one row per lane, fp32 in registers) as bf16: every lane parks its 64-byte row
+// in the warp's staged tile (SWIZZLE_64B layout), one lane hands the tile to the TMA unit (`cp.async.bulk.tensor` store:
+// UTMASTG).  The four-lanes-per-row LDS + STG.128 pass this replaces cost ~90 issue slots per chunk in an issue-bound
+// epilogue and eight half-line requests per store instruction in the LSU; the bulk store writes whole rows and clips
+// rows >= M / columns >= N itself.  The caller has made sure the previous bulk store has read the tile (tma_store_wait_read).
+__device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* tile, int lane, const void* tmap_out, int col, int row_w,
+                                                float* colsum = nullptr) {
   const uint32_t tb = smem_u32(tile);
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const uint4 w = make_uint4(pack_bf16x2(z[j], z[j + 1]), pack_bf16x2(z[j + 2], z[j + 3]),
                                pack_bf16x2(z[j + 4], z[j + 5]), pack_bf16x2(z[j + 6], z[j + 7]));
-    sts128(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16, w);
+    sts128(tb + epi_off(lane, j >> 3), w);
   }
+  fence_proxy_async_smem();            // this lane's generic-proxy writes -> visible to the bulk (async-proxy) store
   __syncwarp();
+  if (lane == 0) tma_store_tile(tmap_out, tb, col, row_w);
   if (colsum) {     // (warp-uniform) bias gradient of the layer below: column sums of the staged tile, 32 REDs per chunk
     float c[4][2];
     tile_colsum_mma(tb, lane, c);
@@ -224,22 +243,9 @@ __device__ __forceinline__ void store_rows_bf16(const float (&z)[32], float* til
     }
     colsum[lane] += mine;                 // this warp's own shared-memory accumulator (flushed once at the end of the launch)
   }
-  const int r0 = lane >> 2;
-  const uint32_t src = tb + r0 * EPI_ROW_PITCH + (lane & 3) * 16;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 w = lds128(src + i * 8 * EPI_ROW_PITCH);
-#ifdef HG_DBG_NOSTORE
-    if (r0 + 8 * i < rows_left && w.x == 0x12345678u)
-#else
-    if (r0 + 8 * i < rows_left)
-#endif
-      out_p[i * ld_u4] = w;
-  }
-  __syncwarp();
 }
 
-// Column sums of the warp's staged 32 x 32 bf16 tile (rows EPI_ROW_PITCH bytes apart) on the tensor core: ones[16x16] x
+// Column sums of the warp's staged 32 x 32 bf16 tile (SWIZZLE_64B layout, see epi_off) on the tensor core: ones[16x16] x
 // tile[16 x 8] per mma.sync.m16n8k16, the tile read as B fragments with ldmatrix.trans.  Every row of the product holds
 // the column sums, so lane t ends up with the sums of columns nb*8 + 2*(t%4) + {0,1}, nb = 0..3, in c[nb][0..1].
 // Replaces a 31-shuffle butterfly (~190 instructions per chunk) with 4 ldmatrix + 8 mma + 8 shuffles; the summands are
@@ -250,7 +256,7 @@ __device__ __forceinline__ void tile_colsum_mma(uint32_t tile_addr, int lane, fl
   for (int nb = 0; nb < 4; ++nb) {
     uint32_t b0, b1, b2, b3;              // k rows 0-7, 8-15, 16-23, 24-31 of column block nb
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(tile_addr + lane * EPI_ROW_PITCH + nb * 16) : "memory");
+                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(tile_addr + epi_off(lane, nb)) : "memory");
     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
                  : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(ones), "r"(b0), "r"(b1));
@@ -275,9 +281,10 @@ __device__ __forceinline__ void prefetch_act(const uint4* act_p, long long ld_u4
 
 // Per-(warp, tile) addressing shared by the chunks of a tile, computed once after the tile decode.
 struct EpiCtx {
-  uint4* out_p;          // bf16 outputs: this lane's piece of chunk 0 (chunk c: + 4 c)
-  const uint4* act_p;    // DELU: the activation tile, same addressing
-  long long ldo_u4, ldact_u4;   // 8 rows further, in 16-byte units
+  const void* tmap_out;  // bf16 outputs: the problem's output tensor map (TMA store of the warp's chunks)
+  int row_w;             // first of the warp's 32 rows
+  const uint4* act_p;    // DELU: this lane's first 16-byte piece of the activation tile (chunk c: + 4 c)
+  long long ldact_u4;    // 8 rows further, in 16-byte units
   int rows_left;         // valid rows of the warp's 32 (<= 0: none)
 };
 
@@ -286,6 +293,10 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
                                                const uint4 (&pre)[4], float* s_colsum, const float* bias_s, const EpiCtx& X, int c) {
   const bool row_ok = row < q.M;
   const bool full = (n0 + 32 <= q.N);
+  if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16 || EPI == HG_EPI_DELU_BF16) {
+    if (lane == 0) tma_store_wait_read();      // the previous chunk's bulk store has read the staged tile (long done by now)
+    __syncwarp();
+  }
   if constexpr (EPI == HG_EPI_STORE_F32) {
     float* o = reinterpret_cast<float*>(q.out) + (long long)row * q.ldo + n0;
     if (row_ok) {
@@ -332,7 +343,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
 #endif
     }
     if (full) {
-      store_rows_bf16(z, tile, lane, X.out_p + 4 * c, X.ldo_u4, X.rows_left);
+      store_rows_bf16(z, tile, lane, X.tmap_out, n0, X.row_w);
     } else if (row_ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -350,7 +361,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + (lane >> 2), piece = lane & 3;
-        sts128(tb + r * EPI_ROW_PITCH + piece * 16, pre[i]);
+        sts128(tb + epi_off(r, piece), pre[i]);
       }
       __syncwarp();
 #endif
@@ -361,7 +372,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
 #ifdef HG_DX_DIRECT_ACT
         const uint4 hw = pre[j >> 3];
 #else
-        const uint4 hw = lds128(tb + lane * EPI_ROW_PITCH + (j >> 3) * 16);
+        const uint4 hw = lds128(tb + epi_off(lane, j >> 3));
 #endif
         const uint32_t hv[4] = {hw.x, hw.y, hw.z, hw.w};
 #pragma unroll
@@ -375,10 +386,10 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
       }
       __syncwarp();
 #ifndef HG_COLSUM_BUTTERFLY
-      store_rows_bf16(d, tile, lane, X.out_p + 4 * c, X.ldo_u4, X.rows_left, q.colsum ? s_colsum + q.colsum_off + n0 : nullptr);
+      store_rows_bf16(d, tile, lane, X.tmap_out, n0, X.row_w, q.colsum ? s_colsum + q.colsum_off + n0 : nullptr);
       return;
 #else     // A/B switch (tools/build_variant.sh): fp32 shuffle butterfly below
-      store_rows_bf16(d, tile, lane, X.out_p + 4 * c, X.ldo_u4, X.rows_left);
+      store_rows_bf16(d, tile, lane, X.tmap_out, n0, X.row_w);
 #endif
     } else {
 #pragma unroll
@@ -604,7 +615,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]  (CG=2: only the leader's are used)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* epi_tiles = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+  float* epi_tiles = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 1024);     // 1024-byte aligned (TMA store source)
 
   pdl_trigger();
   if (threadIdx.x == 0) trace(0x200);
@@ -618,6 +629,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
     for (int g = 0; g < P.num_problems; ++g) {
       tma_prefetch_desc(&P.tma_a[g]);
       tma_prefetch_desc(&P.tma_b[g]);
+      if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16 || EPI == HG_EPI_DELU_BF16) tma_prefetch_desc(&P.tma_out[g]);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -766,7 +778,8 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
     // below beat eight by ~20 %; double-buffering the TMEM loads or fetching the DELU activations a tile ahead costs
     // more in registers (640 threads -> 102 per thread) than it hides in latency, so neither is done.
     constexpr bool DELU = (EPI == HG_EPI_DELU_BF16);
-    float* s_colsum_all = epi_tiles + K::EPI_WARPS * (K::EPI_TILE_BYTES / 4);     // [4 quarters][HG_MAX_COLSUM_COLS]
+    float* bias_s = epi_tiles + K::EPI_WARPS * (K::EPI_TILE_BYTES / 4) + (warp - 4) * (K::BIAS_SLICE_BYTES / 4);   // this warp's bias slice
+    float* s_colsum_all = epi_tiles + K::EPI_WARPS * ((K::EPI_TILE_BYTES + K::BIAS_SLICE_BYTES) / 4);   // [4 quarters][HG_MAX_COLSUM_COLS]
     float* s_colsum = s_colsum_all + quad * HG_MAX_COLSUM_COLS;   // column c of a problem is always handled by the same
     const int et = (warp - 4) * 32 + lane;                        // (quarter, column slice) warp: plain read-modify-write
     if constexpr (DELU) {
@@ -784,13 +797,11 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
       EpiCtx X;
       {
         const int row_w = row - lane, r0 = lane >> 2, piece = lane & 3;
+        X.row_w = row_w;
         X.rows_left = q.M - row_w;
-        X.ldo_u4 = q.ldo;              // 8 rows further, in 16-byte units: 8 * ld elements * 2 B / 16 B = ld
-        X.ldact_u4 = q.ldact;
-        X.out_p = nullptr;
+        X.tmap_out = &P.tma_out[ti.g];
+        X.ldact_u4 = q.ldact;          // 8 rows further, in 16-byte units: 8 * ld elements * 2 B / 16 B = ld
         X.act_p = nullptr;
-        if constexpr (!K::F32_OUT)
-          X.out_p = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(q.out) + (long long)(row_w + r0) * q.ldo + col0) + piece;
         if constexpr (DELU)
           X.act_p = reinterpret_cast<const uint4*>(q.act + (long long)(row_w + r0) * q.ldact + col0) + piece;
       }
@@ -803,8 +814,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
       if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16) {
         // the slice's biases -> shared memory BEFORE the accumulator is waited for: a global load per chunk sat on the
         // epilogue's critical path (~0.5-1 us per tile; it matters for the rollout launches, whose last epilogue is exposed)
-        float* bs = tile + 640;
-        for (int j = lane; j < SLICE; j += 32) bs[j] = (q.bias && col0 + j < q.N) ? __ldg(q.bias + col0 + j) : 0.f;
+        for (int j = lane; j < SLICE; j += 32) bias_s[j] = (q.bias && col0 + j < q.N) ? __ldg(q.bias + col0 + j) : 0.f;
         __syncwarp();
       }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
@@ -822,7 +832,7 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
 #pragma unroll
           for (int j = 0; j < 32; ++j) asm volatile("" ::"r"(v[j]));
 #else
-          epilogue_chunk<EPI>(q, row, col0 + c * 32, v, lane, tile, pre[DELU ? c : 0], s_colsum, tile + 640 + c * 32, X, c);
+          epilogue_chunk<EPI>(q, row, col0 + c * 32, v, lane, tile, pre[DELU ? c : 0], s_colsum, bias_s + c * 32, X, c);
 #endif
           if (warp == 4 && lane == 0 && it < 2 && c < 2) trace(0x209, it * 2 + c);
         }
@@ -839,6 +849,10 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
       }
       if (warp == 4 && lane == 0 && it < 4) trace(0x206, it);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (!K::F32_OUT) {
+      if (lane == 0) tma_store_wait_all();     // this warp's bulk stores are complete before the CTA's shared memory goes away
+      __syncwarp();
     }
     if constexpr (DELU) {      // one flush per CTA and launch: (columns / 32) coalesced REDs instead of one per 32 x 32 chunk
       asm volatile("bar.sync 1, %0;" ::"n"(K::EPI_WARPS * 32) : "memory");
@@ -1263,6 +1277,21 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 tensor map over row-major [outer, inner] with row stride ld elements, box {64, box_outer}, 128 B swizzle.
+// 2-D bf16 tensor map over the row-major output [outer, inner]: box {32 columns, 32 rows} = one warp's chunk, 64 B swizzle.
+static int make_tmap_out(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld) {
+  EncodeTiledFn enc = get_encode_fn();
+  HG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (output) failed with %d (inner %lld outer %lld ld %lld)", (int)r, inner, outer, ld);
+  return HG_OK;
+}
+
 static int make_tmap(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld, int box_outer) {
   EncodeTiledFn enc = get_encode_fn();
   HG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
@@ -1374,6 +1403,10 @@ static int build_params(const HgGemmProblem* pr, int n, int epilogue, int block_
     if (!q.b_mn) rc = make_tmap(&gp.tma_b[g], h.B, h.K, h.N, h.ldb, block_n / cg);
     else rc = make_tmap(&gp.tma_b[g], h.B, h.N, h.K, h.ldb, BLOCK_K);
     if (rc != HG_OK) return rc;
+    if (epilogue == HG_EPI_BIAS_ELU_BF16 || epilogue == HG_EPI_DELU_BF16 || epilogue == HG_EPI_BIAS_BF16) {
+      rc = make_tmap_out(&gp.tma_out[g], h.out, h.N, h.M, h.ldo);
+      if (rc != HG_OK) return rc;
+    }
   }
   gp.total_tiles = tiles;
   gp.m_major = n > 1 ? 1 : 0;
