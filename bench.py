@@ -493,8 +493,9 @@ def run_ours(a):
     achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
     traffic, traffic_src = None, None
     try:      # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture (never measured under ncu here)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_update_gemms.json")))
-        traffic, traffic_src = float(tj["traffic_bytes_per_launch"]), "profiles/r01_ncu_update_gemms.json (dram read + write, mean over one minibatch's 8 launches)"
+        name = next(n for n in ("r02_ncu_update_gemms.json", "r01_ncu_update_gemms.json") if os.path.exists(os.path.join(ROOT, "profiles", n)))
+        tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+        traffic, traffic_src = float(tj["traffic_bytes_per_launch"]), f"profiles/{name} (dram read + write, mean over one minibatch's 8 launches)"
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": "hg::gemm_kernel (grouped tcgen05 GEMM; update-phase launches)",

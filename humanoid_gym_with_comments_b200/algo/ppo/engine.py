@@ -27,7 +27,7 @@ def round_up(x: int, m: int) -> int:
 
 # Row pitch of every bf16 operand, in elements: a multiple of 64 (128 bytes) so that each 128-byte row of a TMA box
 # is exactly one L2 line.  With a merely 16-byte-aligned pitch (712 for 705 columns) the rows straddle lines and the
-# first-layer GEMMs lose ~25 % (tools/bench_gemm_ld.py).
+# first-layer GEMMs lose ~25 % (measured in round 1 with HG_LD_ALIGN=8 in tools/bench_gemm.py).
 LD_ALIGN = 64
 
 

@@ -1,6 +1,6 @@
-"""profiles/r01_ncu_update_gemms.json from the `ncu --set full` capture of one minibatch's 8 grouped-GEMM launches
+"""profiles/r02_ncu_update_gemms.json from the `ncu --set full` capture of one minibatch's 8 grouped-GEMM launches
 (tools/ncu_capture.sh): per-launch duration, DRAM bytes, tensor-pipe activity; bench.py reads `traffic_bytes_per_launch`.
-usage: ncu_gemm_json.py gpurun_out/ncu_update_gemms.ncu-rep > profiles/r01_ncu_update_gemms.json"""
+usage: ncu_gemm_json.py gpurun_out/ncu_update_gemms.ncu-rep > profiles/r02_ncu_update_gemms.json"""
 import csv, io, json, subprocess, sys
 
 NAMES = ["fwd L1 (actor 705->512 | critic 219->768 | lin-vel 705->128)", "fwd L2 (512->256 | 768->256 | 128->128)",
