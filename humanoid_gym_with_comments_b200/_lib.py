@@ -230,6 +230,8 @@ _SIGNATURES = {
     "hg_rollout_forward": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, _P, C.c_uint64, C.c_uint64, _P]),
     "hg_gemm_plan_create_tail": (C.c_int, [C.POINTER(HgGemmProblem), C.POINTER(HgGemmProblem), C.POINTER(HgFusedHead), C.c_int,
                                            C.POINTER(C.c_void_p)]),
+    "hg_gemm_plan_create_step": (C.c_int, [C.POINTER(HgGemmProblem), C.POINTER(HgGemmProblem), C.POINTER(HgGemmProblem),
+                                           C.POINTER(HgFusedHead), C.c_int, C.POINTER(C.c_void_p)]),
     "hg_gae_returns": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
     "hg_ingest_rows": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, C.c_int64, _P, C.c_int64, _P]),
     "hg_gather_rows_bf16": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P]),

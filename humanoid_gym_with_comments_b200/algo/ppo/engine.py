@@ -246,7 +246,9 @@ class MLPEngine:
         return all(n.num_hidden == 3 and 64 <= n.hidden[1] <= 256 and n.hidden[1] % 64 == 0
                    and 32 <= n.hidden[2] <= 128 and n.hidden[2] % 32 == 0 for n in nets)
 
-    def _tail_plan(self, nets: Sequence[NetSpec], ws: "Workspace", rows: int, heads) -> int:
+    def _tail_plan(self, nets: Sequence[NetSpec], ws: "Workspace", rows: int, heads, layer1=None) -> int:
+        """layer1 = the layer-1 problems of the same nets: ONE launch for the whole forward (`hg_gemm_plan_create_step`);
+        raises HgError when the shapes do not qualify (the caller then keeps layer 1 and the tail as two launches)."""
         l2, l3, hs = [], [], []
         for net in nets:
             h1 = ws.h[net.name][0]
@@ -262,7 +264,11 @@ class MLPEngine:
         a2, a3 = (HgGemmProblem * len(l2))(*l2), (HgGemmProblem * len(l3))(*l3)
         harr = (_lib.HgFusedHead * len(hs))(*hs)
         handle = C.c_void_p()
-        check(self.lib.hg_gemm_plan_create_tail(a2, a3, harr, len(l2), C.byref(handle)))
+        if layer1 is not None:
+            a1 = (HgGemmProblem * len(layer1))(*layer1)
+            check(self.lib.hg_gemm_plan_create_step(a1, a2, a3, harr, len(l2), C.byref(handle)))
+        else:
+            check(self.lib.hg_gemm_plan_create_tail(a2, a3, harr, len(l2), C.byref(handle)))
         self._all_plans.append(handle.value)
         return handle.value
 
@@ -315,6 +321,16 @@ class MLPEngine:
                     M=rows, N=lin.out_features, K=k, k_splits=1, out=ptr(out), ldo=out.stride(0),
                     bias=ptr(lin.bias.data), act=0, ldact=0, colsum=0, out_frame_src=0, out_frame_dst=0))
                 ns.append(lin.out_features)
+            if fuse_tail and depth == 3 and l == 0 and os.environ.get("HG_ROLLOUT_STEP", "0") == "1":
+                # layer 1 + tail in ONE launch (rollout_step_kernel); shapes that do not qualify keep the two launches.
+                # OFF by default: bit-identical to the two launches, but measured SLOWER at 4096 envs (rollout 2.90 vs 2.39 ms
+                # per iteration): layer 1 is bound by the L2 -> SM operand fill per SM and takes 20 us on the 84 SMs the 64 tail
+                # CTAs leave it instead of 13.5 us on 148; the overlap it buys the tail is smaller than that (device timeline)
+                try:
+                    plans.append(self._tail_plan(nets, ws, rows, heads, layer1=probs))
+                    break
+                except _lib.HgError:
+                    pass
             if make_plans and heads is not None and l == depth - 1:
                 hs = [heads[net.name] for net in nets if l < net.num_hidden]
                 arr, harr = (HgGemmProblem * len(probs))(*probs), (_lib.HgFusedHead * len(hs))(*hs)

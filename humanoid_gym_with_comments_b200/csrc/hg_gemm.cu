@@ -599,8 +599,12 @@ __device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr) {
 //         [128 r, 128 r + 128) of A and of the accumulator and loads only columns [r BLOCK_N/2, (r+1) BLOCK_N/2) of B;
 //         the leader CTA issues the MMAs for both, each tensor core reads the other half of B from its peer's
 //         shared memory.  Operand fill per SM drops from 16 + 32 KB to 16 + 16 KB per 128x256x64 MMA block.
-template <int BLOCK_N, int EPI, int CG>
-__global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kernel(const __grid_constant__ GroupParams P) {
+// STEP = true: the body runs as the layer-1 part of rollout_step_kernel (below): CTA `group_id` of `num_groups`, and every
+// epilogue warp publishes each finished tile in `step_flags[problem * tiles_m + m_blk]` once its bulk stores have completed.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int BLOCK_N, int EPI, int CG, bool STEP>
+__device__ __forceinline__ void gemm_body(const GroupParams& P, const int group_id, const int num_groups, unsigned* step_flags) {
   using K = Cfg<BLOCK_N, EPI, CG>;
   constexpr int A_BYTES = K::A_BYTES, STAGE_BYTES = K::STAGE_BYTES, STAGES = K::STAGES;
   constexpr int B_ROWS = BLOCK_N / CG;                      // rows (K-major) / columns (MN-major) of B this CTA loads
@@ -622,8 +626,6 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
-  const int group_id = blockIdx.x / CG;
-  const int num_groups = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < P.num_problems; ++g) {
@@ -848,6 +850,17 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
         }
       }
       if (warp == 4 && lane == 0 && it < 4) trace(0x206, it);
+      if constexpr (STEP) {
+        // this warp's part of tile (problem, m block) is in global memory: completed bulk stores -> proxy fence ->
+        // gpu-scope release of the tile's counter (the tail CTA of that row block acquires it before its TMA loads of h1)
+        if (lane == 0) {
+          tma_store_wait_all();
+          fence_proxy_async_all();
+          __threadfence();
+          atomicAdd(step_flags + ti.g * q.tiles_m + ti.m_blk, 1u);
+        }
+        __syncwarp();
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if constexpr (!K::F32_OUT) {
@@ -877,6 +890,11 @@ __global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kern
     tc_fence_after();
     tmem_dealloc_cg<CG, TMEM_COLS>(tmem_base);
   }
+}
+
+template <int BLOCK_N, int EPI, int CG>
+__global__ void __launch_bounds__((Cfg<BLOCK_N, EPI, CG>::THREADS), 1) gemm_kernel(const __grid_constant__ GroupParams P) {
+  gemm_body<BLOCK_N, EPI, CG, false>(P, blockIdx.x / CG, gridDim.x / CG, nullptr);
 }
 
 
@@ -933,7 +951,9 @@ struct alignas(64) TailParams {
   unsigned long long seed, counter;
 };
 
-__global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __grid_constant__ TailParams P) {
+// step_flags != nullptr: the body runs inside rollout_step_kernel and waits for the layer-1 tiles of its row block (counter
+// of (net, m block) reaching `step_target`) before it loads h1.
+__device__ __forceinline__ void tail_body(const TailParams& P, const int g, const int m_blk, const unsigned* step_flags, const unsigned step_target) {
   using namespace tail;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -952,7 +972,6 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
   pdl_trigger();
   if (threadIdx.x == 0) trace(0x300);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x / P.tiles_m, m_blk = blockIdx.x - g * P.tiles_m;
   const TailNet& q = P.net[g];
   const int num_kb1 = (q.K1 + BLOCK_K - 1) / BLOCK_K, num_kb2 = q.N2 / BLOCK_K;
 
@@ -993,6 +1012,21 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (step_flags) {
+        // fused rollout step: h1 of this row block is being produced by the layer-1 CTAs of the SAME launch (they never wait
+        // for anything of ours and have lower block indices, i.e. are resident first).  Acquire the tile counter, then order
+        // the async-proxy loads behind it.  Watchdog as in mbar_wait: a protocol bug traps instead of hanging.
+        const unsigned* f = step_flags + g * P.tiles_m + m_blk;
+        const long long t0 = clock64();
+        for (;;) {
+          unsigned v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+          if ((int)(v - step_target) >= 0) break;
+          if (clock64() - t0 > 4000000000LL) __trap();
+          __nanosleep(64);
+        }
+        fence_proxy_async_all();
+      }
       for (int kb = 0; kb < num_kb1; ++kb) {
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -1257,6 +1291,37 @@ __global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __
   }
 }
 
+__global__ void __launch_bounds__(tail::THREADS, 1) rollout_tail_kernel(const __grid_constant__ TailParams P) {
+  const int g = blockIdx.x / P.tiles_m;
+  tail_body(P, g, blockIdx.x - g * P.tiles_m, nullptr, 0u);
+}
+
+// ------------------------------------------------------------------------------------------ fused rollout step
+// Layer 1 AND the tail (layer 2 + layer 3 + output layers + sampling) of one env step in ONE launch: the first `num_l1`
+// CTAs run the grouped layer-1 GEMM (m-major tile order: the row blocks complete front to back), the remaining CTAs each
+// own one (128-row block, net) of the tail and start as soon as the layer-1 tiles of THEIR row block are published.
+// Removes one kernel boundary per step (~2 us: completion + flush + dependent launch) and overlaps the tail's main loops
+// and epilogues with the rest of layer 1; both parts pull their operands through the same chip-wide L2 -> SM cap, which the
+// layer-1 CTAs alone (fill-bound at ~42 B/clk/SM on 148 SMs) do not need all SMs to saturate.
+struct alignas(64) StepParams {
+  GroupParams gp;
+  TailParams tp;
+  unsigned* flags;       // [nets * tiles_m] tile counters, monotonically increasing over the launches of the plan
+  unsigned target[2];    // per net: counter value at which all layer-1 tiles of a row block are in
+  int num_l1;            // CTAs of the layer-1 part
+};
+static_assert(Cfg<128, HG_EPI_BIAS_ELU_BF16, 1>::THREADS == tail::THREADS, "one block shape for both parts");
+
+__global__ void __launch_bounds__(tail::THREADS, 1) rollout_step_kernel(const __grid_constant__ StepParams S) {
+  if ((int)blockIdx.x < S.num_l1) {
+    gemm_body<128, HG_EPI_BIAS_ELU_BF16, 1, true>(S.gp, (int)blockIdx.x, S.num_l1, S.flags);
+  } else {
+    const int j = (int)blockIdx.x - S.num_l1;
+    const int g = j % S.tp.num_nets;
+    tail_body(S.tp, g, j / S.tp.num_nets, S.flags, S.target[g]);
+  }
+}
+
 HG_TRACE_SETTER(trace_set_gemm)
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1429,6 +1494,13 @@ struct HgGemmPlan {
   int epilogue, block_n, cta_group;
   bool tail = false;          // hg_gemm_plan_create_tail: layer 2 + layer 3 + head in one launch
   hg::TailParams tp;
+  bool step = false;          // hg_gemm_plan_create_step: layer 1 + tail in one launch (gp = layer 1, tp = tail)
+  unsigned* step_flags = nullptr;
+  mutable unsigned step_epoch = 0;
+  int step_num_l1 = 0;
+  ~HgGemmPlan() {
+    if (step_flags) cudaFree(step_flags);
+  }
 };
 
 extern "C" int hg_gemm_grouped(const HgGemmProblem* pr, int n, int epilogue, int block_n, int cta_group, void* stream) {
@@ -1493,6 +1565,36 @@ extern "C" int hg_gemm_plan_create_heads(const HgGemmProblem* pr, const HgFusedH
   return HG_OK;
 }
 
+namespace hg {
+static int fill_tail_params(const HgGemmProblem* l2, const HgGemmProblem* l3, const HgFusedHead* heads, int n, TailParams& tp) {
+  memset(&tp, 0, sizeof(tp));
+  tp.num_nets = n;
+  for (int g = 0; g < n; ++g) {
+    const HgGemmProblem& a = l2[g];
+    const HgGemmProblem& b = l3[g];
+    const HgFusedHead& h = heads[g];
+    const bool ok = a.A && a.B && b.B && a.bias && a.M > 0 && a.K > 0 && !a.a_mn_major && !a.b_mn_major && !b.b_mn_major &&
+                    a.N >= 64 && a.N <= 256 && a.N % 64 == 0 && b.K == a.N && b.N >= 32 && b.N <= 128 && b.N % 32 == 0 &&
+                    a.M == l2[0].M && (h.kind == HG_HEAD_POLICY || h.kind == HG_HEAD_LINEAR) && h.n_out >= 1 && h.n_out <= 16 &&
+                    h.W && h.b && h.out && (h.kind != HG_HEAD_POLICY || (h.std && h.actions && h.sigma && h.log_prob));
+    if (!ok) {
+      set_error("rollout tail: net %d: needs K-major operands, 64 <= N2 <= 256 (multiple of 64), K3 == N2, "
+                "32 <= N3 <= 128 (multiple of 32), equal M, a valid head", g);
+      return HG_ERR_INVALID;
+    }
+    TailNet& q = tp.net[g];
+    q.M = a.M; q.K1 = a.K; q.N2 = a.N; q.N3 = b.N;
+    q.b2 = a.bias; q.b3 = b.bias; q.head = h;
+    int rc = make_tmap(&q.tma_h1, a.A, a.K, a.M, a.lda, BLOCK_M);
+    if (rc == HG_OK) rc = make_tmap(&q.tma_w2, a.B, a.K, a.N, a.ldb, 256);
+    if (rc == HG_OK) rc = make_tmap(&q.tma_w3, b.B, b.K, b.N, b.ldb, 128);
+    if (rc != HG_OK) return rc;
+  }
+  tp.tiles_m = (l2[0].M + BLOCK_M - 1) / BLOCK_M;
+  return HG_OK;
+}
+}  // namespace hg
+
 extern "C" int hg_gemm_plan_create_tail(const HgGemmProblem* l2, const HgGemmProblem* l3, const HgFusedHead* heads, int n,
                                         HgGemmPlan** out) {
   using namespace hg;
@@ -1502,36 +1604,56 @@ extern "C" int hg_gemm_plan_create_tail(const HgGemmProblem* l2, const HgGemmPro
   plan->epilogue = HG_EPI_BIAS_ELU_HEAD;
   plan->block_n = 128;
   plan->cta_group = 1;
-  TailParams& tp = plan->tp;
-  memset(&tp, 0, sizeof(tp));
-  tp.num_nets = n;
-  int rc = HG_OK;
-  for (int g = 0; g < n && rc == HG_OK; ++g) {
-    const HgGemmProblem& a = l2[g];
-    const HgGemmProblem& b = l3[g];
-    const HgFusedHead& h = heads[g];
-    const bool ok = a.A && a.B && b.B && a.bias && a.M > 0 && a.K > 0 && !a.a_mn_major && !a.b_mn_major && !b.b_mn_major &&
-                    a.N >= 64 && a.N <= 256 && a.N % 64 == 0 && b.K == a.N && b.N >= 32 && b.N <= 128 && b.N % 32 == 0 &&
-                    a.M == l2[0].M && (h.kind == HG_HEAD_POLICY || h.kind == HG_HEAD_LINEAR) && h.n_out >= 1 && h.n_out <= 16 &&
-                    h.W && h.b && h.out && (h.kind != HG_HEAD_POLICY || (h.std && h.actions && h.sigma && h.log_prob));
+  const int rc = fill_tail_params(l2, l3, heads, n, plan->tp);
+  if (rc != HG_OK) {
+    delete plan;
+    return rc;
+  }
+  *out = plan;
+  return HG_OK;
+}
+
+extern "C" int hg_gemm_plan_create_step(const HgGemmProblem* l1, const HgGemmProblem* l2, const HgGemmProblem* l3,
+                                        const HgFusedHead* heads, int n, HgGemmPlan** out) {
+  using namespace hg;
+  HG_CHECK(out && l1 && l2 && l3 && heads && n >= 1 && n <= 2, "hg_gemm_plan_create_step: 1 or 2 nets, non-null arguments");
+  HgGemmPlan* plan = new HgGemmPlan();
+  plan->tail = true;
+  plan->step = true;
+  plan->epilogue = HG_EPI_BIAS_ELU_HEAD;
+  plan->block_n = 128;
+  plan->cta_group = 1;
+  int rc = build_params(l1, n, HG_EPI_BIAS_ELU_BF16, 128, 1, plan->gp);
+  if (rc == HG_OK) rc = fill_tail_params(l2, l3, heads, n, plan->tp);
+  for (int g = 0; rc == HG_OK && g < n; ++g) {
+    // layer 1 of net g writes exactly what the tail of net g reads, whole 32-column chunks (every store a bulk store)
+    const bool ok = l1[g].M == l2[g].M && l1[g].out == l2[g].A && l1[g].ldo == l2[g].lda && l1[g].N == l2[g].K && l1[g].N % 32 == 0 &&
+                    l1[g].k_splits == 1 && !l1[g].a_mn_major && !l1[g].b_mn_major;
     if (!ok) {
-      set_error("hg_gemm_plan_create_tail: net %d: needs K-major operands, 64 <= N2 <= 256 (multiple of 64), K3 == N2, "
-                "32 <= N3 <= 128 (multiple of 32), equal M, a valid head", g);
+      set_error("hg_gemm_plan_create_step: net %d: layer 1 must produce the tail's h1 (same M, buffer, pitch; N %% 32 == 0)", g);
       rc = HG_ERR_INVALID;
-      break;
     }
-    TailNet& q = tp.net[g];
-    q.M = a.M; q.K1 = a.K; q.N2 = a.N; q.N3 = b.N;
-    q.b2 = a.bias; q.b3 = b.bias; q.head = h;
-    rc = make_tmap(&q.tma_h1, a.A, a.K, a.M, a.lda, BLOCK_M);
-    if (rc == HG_OK) rc = make_tmap(&q.tma_w2, a.B, a.K, a.N, a.ldb, 256);
-    if (rc == HG_OK) rc = make_tmap(&q.tma_w3, b.B, b.K, b.N, b.ldb, 128);
+  }
+  if (rc == HG_OK) {
+    const int tail_ctas = n * plan->tp.tiles_m;
+    plan->step_num_l1 = num_sms() - tail_ctas;
+    if (plan->step_num_l1 < 32) {
+      set_error("hg_gemm_plan_create_step: %d tail CTAs leave fewer than 32 of %d SMs for layer 1", tail_ctas, num_sms());
+      rc = HG_ERR_INVALID;
+    }
+  }
+  if (rc == HG_OK) {
+    plan->gp.m_major = 1;        // row blocks complete front to back (all problems have tiles_m row blocks, no split-K)
+    const size_t bytes = sizeof(unsigned) * n * plan->tp.tiles_m;
+    if (cudaMalloc(&plan->step_flags, bytes) != cudaSuccess || cudaMemset(plan->step_flags, 0, bytes) != cudaSuccess) {
+      set_error("hg_gemm_plan_create_step: cannot allocate the tile counters");
+      rc = HG_ERR_CUDA;
+    }
   }
   if (rc != HG_OK) {
     delete plan;
     return rc;
   }
-  tp.tiles_m = (l2[0].M + BLOCK_M - 1) / BLOCK_M;
   *out = plan;
   return HG_OK;
 }
@@ -1539,6 +1661,30 @@ extern "C" int hg_gemm_plan_create_tail(const HgGemmProblem* l2, const HgGemmPro
 extern "C" int hg_gemm_plan_run_heads(const HgGemmPlan* plan, const float* eps, uint64_t seed, uint64_t counter, void* stream) {
   using namespace hg;
   HG_CHECK(plan != nullptr && plan->epilogue == HG_EPI_BIAS_ELU_HEAD, "hg_gemm_plan_run_heads: not a fused-head plan");
+  if (plan->step) {
+    constexpr int SMEM = Cfg<128, HG_EPI_BIAS_ELU_BF16, 1>::SMEM_TOTAL > tail::SMEM_TOTAL ? Cfg<128, HG_EPI_BIAS_ELU_BF16, 1>::SMEM_TOTAL
+                                                                                          : tail::SMEM_TOTAL;
+    static bool configured = false;
+    if (!configured) {
+      HG_CUDA(cudaFuncSetAttribute(rollout_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      configured = true;
+    }
+    StepParams sp;
+    sp.gp = plan->gp;
+    sp.tp = plan->tp;
+    sp.tp.eps = eps;
+    sp.tp.seed = seed;
+    sp.tp.counter = counter;
+    sp.flags = plan->step_flags;
+    sp.num_l1 = plan->step_num_l1;
+    const unsigned epoch = ++plan->step_epoch;
+    for (int g = 0; g < sp.tp.num_nets; ++g) sp.target[g] = epoch * (unsigned)(plan->gp.p[g].tiles_n * Cfg<128, HG_EPI_BIAS_ELU_BF16, 1>::EPI_WARPS);
+    HG_CUDA(launch_kernel(rollout_step_kernel, dim3(sp.num_l1 + sp.tp.num_nets * sp.tp.tiles_m), dim3(tail::THREADS), SMEM,
+                          reinterpret_cast<cudaStream_t>(stream), 1, sp));
+    HG_LAUNCH_CHECK();
+    count_launch();
+    return HG_OK;
+  }
   if (plan->tail) {
     static bool configured = false;
     if (!configured) {

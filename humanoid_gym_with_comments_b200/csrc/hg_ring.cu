@@ -60,6 +60,60 @@ __global__ void __launch_bounds__(256) ring_gather_kernel(const HgHistoryRing R,
   }
 }
 
+// Targets only (dst == nullptr): one THREAD per row, three floats each (a warp per row left 29 lanes idle: 41 us for 245,760 rows).
+__global__ void __launch_bounds__(256) ring_targets_kernel(const HgHistoryRing R, int num_envs, const int* __restrict__ first_valid,
+                                                           const long long* __restrict__ idx, long long rows_out,
+                                                           float* __restrict__ lv_out, int lv_col) {
+  pdl_trigger();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows_out; i += stride) {
+    const long long flat = idx ? __ldg(idx + i) : i;
+    const int r = (int)(flat / num_envs), n = (int)(flat - (long long)r * num_envs);
+    const int f0 = max(0, __ldg(first_valid + flat) - (r - R.frames + 1));
+    const float* src = R.arch32 + ((size_t)n * R.slots + r) * R.width;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((lv_col + 0) / R.width >= f0) o.x = __ldg(src + lv_col);
+    if ((lv_col + 1) / R.width >= f0) o.y = __ldg(src + lv_col + 1);
+    if ((lv_col + 2) / R.width >= f0) o.z = __ldg(src + lv_col + 2);
+    *reinterpret_cast<float4*>(lv_out + i * 4) = o;
+  }
+}
+
+// Hand-over without overlap (from_row >= frames, e.g. 60 >= 15): source and destination windows are disjoint, so the copy is
+// a plain grid-stride loop over [ring][env][frames * width] floats -- the register-staged kernel below (one warp per env,
+// 96 values per lane) took 84 us for 33 MB.
+__global__ void __launch_bounds__(256) ring_rollover_disjoint_kernel(const HgHistoryRing R0, const HgHistoryRing R1, int num_rings, int num_envs,
+                                                                     int from_row, int* __restrict__ hist_start, int* __restrict__ first_valid_row0) {
+  pdl_trigger();
+  pdl_wait();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  for (int ring = 0; ring < num_rings; ++ring) {
+    const HgHistoryRing& R = ring == 0 ? R0 : R1;
+    const int count = R.frames * R.width, count16 = R.frames * (R.pitch16 >> 1);     // floats / bf16 pairs per window
+    for (long long i = tid; i < (long long)num_envs * count; i += stride) {
+      const int n = (int)(i / count), j = (int)(i - (long long)n * count);
+      const size_t base = (size_t)n * R.slots * R.width;
+      R.live32[base + j] = R.live32[base + (size_t)from_row * R.width + j];
+      R.arch32[base + j] = R.arch32[base + (size_t)from_row * R.width + j];
+    }
+    const uint32_t* l16 = reinterpret_cast<const uint32_t*>(R.live16);
+    const uint32_t* a16 = reinterpret_cast<const uint32_t*>(R.arch16);
+    const int pairs = R.pitch16 >> 1;
+    for (long long i = tid; i < (long long)num_envs * count16; i += stride) {
+      const int n = (int)(i / count16), j = (int)(i - (long long)n * count16);
+      const size_t base = (size_t)n * R.slots * pairs;
+      reinterpret_cast<uint32_t*>(R.live16)[base + j] = l16[base + (size_t)from_row * pairs + j];
+      reinterpret_cast<uint32_t*>(R.arch16)[base + j] = a16[base + (size_t)from_row * pairs + j];
+    }
+  }
+  for (long long n = tid; n < num_envs; n += stride) {
+    const int hs = max(hist_start[n] - from_row, -(1 << 24));
+    hist_start[n] = hs;
+    first_valid_row0[n] = hs;
+  }
+}
+
 // One warp per (ring, env): the whole window of `from_row` is read into registers before the first store (source and
 // destination slots overlap when from_row < frames - 1).
 constexpr int ROLL_MAX = 48;      // floats per lane: frames * width <= 32 * 48 = 1536 (15 x 97 = 1455 for the 18-DOF layout)
@@ -133,6 +187,16 @@ extern "C" int hg_ring_gather(const HgHistoryRing* ring, int num_envs, const int
   if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long* idx_ll = reinterpret_cast<const long long*>(idx);
+  if (dst == nullptr) {
+    HG_CHECK((reinterpret_cast<uintptr_t>(lv_out) & 15) == 0, "hg_ring_gather: lv_out must be 16-byte aligned");
+    long long tb = (rows_out + 255) / 256;
+    if (tb > (long long)num_sms() * 8) tb = (long long)num_sms() * 8;
+    HG_CUDA(launch_kernel(ring_targets_kernel, dim3((unsigned)tb), dim3(256), 0, st, 1, *ring, num_envs, first_valid, idx_ll,
+                          (long long)rows_out, lv_out, lv_col));
+    HG_LAUNCH_CHECK();
+    count_launch();
+    return HG_OK;
+  }
   if (dst_bf16)
     HG_CUDA(launch_kernel(ring_gather_kernel<true>, dim3((unsigned)blocks), dim3(256), 0, st, 1, *ring, num_envs, first_valid, idx_ll,
                           (long long)rows_out, dst, (long long)ld_dst, lv_out, lv_col));
@@ -155,6 +219,15 @@ extern "C" int hg_ring_rollover(const HgHistoryRing* rings, int num_rings, int n
     HG_CHECK(from_row >= 0 && from_row + rings[i].frames <= rings[i].slots, "hg_ring_rollover: from_row %d outside the ring", from_row);
   }
   if (from_row == 0) return HG_OK;
+  bool disjoint = true;
+  for (int i = 0; i < num_rings; ++i) disjoint = disjoint && from_row >= rings[i].frames;
+  if (disjoint) {
+    HG_CUDA(launch_kernel(ring_rollover_disjoint_kernel, dim3(num_sms() * 8), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 1,
+                          rings[0], rings[num_rings - 1], num_rings, num_envs, from_row, hist_start, first_valid_row0));
+    HG_LAUNCH_CHECK();
+    count_launch();
+    return HG_OK;
+  }
   const int warps = num_rings * num_envs;
   HG_CUDA(launch_kernel(ring_rollover_kernel, dim3((warps + 3) / 4), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 1, rings[0],
                         rings[num_rings - 1], num_rings, num_envs, from_row, hist_start, first_valid_row0));

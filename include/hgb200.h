@@ -122,6 +122,17 @@ int hg_rollout_forward(const HgGemmPlan* const* plans, int n, const HgGemmPlan* 
 int hg_gemm_plan_create_tail(const HgGemmProblem* layer2_host, const HgGemmProblem* layer3_host, const HgFusedHead* heads_host,
                              int num_nets, HgGemmPlan** out);
 
+/* The whole rollout forward of one env step -- layer 1 AND the tail above -- in ONE launch (`rollout_step_kernel`): the first
+ * CTAs run the grouped layer-1 GEMM (layer1[g]: obs / critic-obs window -> h1 of net g, bias + ELU, bf16), the others each own
+ * one (128-row block, net) of the tail and start once the layer-1 tiles of their row block are published (per-tile counters
+ * in device memory owned by the plan; the layer-1 CTAs never wait).  Requirements: those of the tail; layer1[g].out must be
+ * layer2[g].A (same M, pitch), N a multiple of 32, and the tail CTAs must leave >= 32 SMs for layer 1 (otherwise the call
+ * fails and the caller keeps the two launches).  Same results as the two launches, bit for bit.  Run with
+ * hg_gemm_plan_run_heads / hg_rollout_forward.  Measured on B200 at 4096 rows: SLOWER than the two launches (32.5 vs 26 us per
+ * step: layer 1 is per-SM fill-bound and loses the tail's 64 SMs), so the Python mirror uses it only with HG_ROLLOUT_STEP=1. */
+int hg_gemm_plan_create_step(const HgGemmProblem* layer1_host, const HgGemmProblem* layer2_host, const HgGemmProblem* layer3_host,
+                             const HgFusedHead* heads_host, int num_nets, HgGemmPlan** out);
+
 /* ------------------------------------------------------------------------------------------
  * GAE: replaces RolloutStorage.compute_returns (humanoid/algo/ppo/rollout_storage.py:122-143).
  * rewards/values/returns/advantages are [T,N] fp32, dones [T,N] uint8, last_values [N].

@@ -461,35 +461,41 @@ def test_fused_rollout_head_matches_separate_head_kernel(N):
 
 @pytest.mark.parametrize("N", [200, 4096])
 def test_rollout_tail_launch_matches_two_launches(N, monkeypatch):
-    """Layer 2 + layer 3 + heads in ONE launch (`hg_gemm_plan_create_tail`: h2 and h3 stay in shared memory as K-major bf16
-    operands, the output layer runs on the tensor core with W_out = hi + mid + lo bf16 terms) against layer 2 and layer 3 +
-    heads as two launches (output layer as fp32 FMAs): same bf16 hidden activations, so the outputs agree to fp32 round-off
-    of a 128-term dot product (2e-6), for external eps and for the Philox stream (identical keys: same normals)."""
+    """The rollout forward in ONE launch (`hg_gemm_plan_create_step`: layer 1 + tail, the tail CTAs start on per-row-block
+    tile counters), in TWO (layer 1 | `hg_gemm_plan_create_tail`: layer 2 + layer 3 + heads, h2 and h3 stay in shared memory as
+    K-major bf16 operands, the output layer runs on the tensor core with W_out = hi + mid + lo bf16 terms) and in THREE (layer
+    2 and layer 3 + heads separately, output layer as fp32 FMAs).  One launch must equal two launches BIT FOR BIT (same
+    kernels' code, only the scheduling differs); the three-launch path has the same bf16 hidden activations, so it agrees to
+    fp32 round-off of a 128-term dot product (2e-6).  External eps and the Philox stream (identical keys: same normals)."""
     g = torch.Generator(device=DEV).manual_seed(9)
     obs = torch.randn(N, 705, device=DEV, generator=g)
     priv = torch.randn(N, 219, device=DEV, generator=g)
     eps = torch.randn(N, 12, device=DEV, generator=g)
     outs = {}
-    for tail in ("1", "0"):
+    for mode, (step, tail, plain) in {"one": ("1", "1", 0), "two": ("0", "1", 1), "three": ("0", "0", 2)}.items():
+        monkeypatch.setenv("HG_ROLLOUT_STEP", step)
         monkeypatch.setenv("HG_ROLLOUT_TAIL", tail)
-        for mode in ("eps", "philox"):
+        for rng in ("eps", "philox"):
             alg, _ = make_alg(N, 2, seed=3)
             with torch.no_grad():
                 alg.actor_critic.std.fill_(0.7)
             alg.torch_rng = False
-            alg.eps_override = (lambda t: eps) if mode == "eps" else None
+            alg.eps_override = (lambda t: eps) if rng == "eps" else None
             alg._seed = 99
             with torch.inference_mode():
-                a = alg.act(obs, priv).clone()
+                for _ in range(3):                      # (the fused step's tile counters advance per launch: run it repeatedly)
+                    a = alg.act(obs, priv).clone()
             plans = alg._slot_plan(0)[0]
-            assert isinstance(plans, tuple) and len(plans[0]) == (1 if tail == "1" else 2)      # launches in front of the head launch
+            if N <= 128 * 58 or mode != "one":           # the fused step needs >= 32 SMs left for layer 1
+                assert isinstance(plans, tuple) and len(plans[0]) == plain, (mode, len(plans[0]))      # launches in front of the head launch
             st = alg.storage
-            outs[(tail, mode)] = (a, st.mu[0].clone(), st.sigma[0].clone(), st.actions_log_prob[0].clone(), st.values[0].clone())
+            outs[(mode, rng)] = (a, st.mu[0].clone(), st.sigma[0].clone(), st.actions_log_prob[0].clone(), st.values[0].clone())
     torch.cuda.synchronize()
-    for mode in ("eps", "philox"):
-        for name, x, y in zip(("actions", "mu", "sigma", "log_prob", "values"), outs[("1", mode)], outs[("0", mode)]):
-            assert torch.isfinite(x).all(), (mode, name)
-            assert torch.allclose(x, y, rtol=2e-6, atol=4e-6), (mode, name, float((x - y).abs().max()))
+    for rng in ("eps", "philox"):
+        for name, x, y, z in zip(("actions", "mu", "sigma", "log_prob", "values"), outs[("one", rng)], outs[("two", rng)], outs[("three", rng)]):
+            assert torch.isfinite(x).all(), (rng, name)
+            assert torch.equal(x, y), (rng, name, float((x - y).abs().max()))
+            assert torch.allclose(y, z, rtol=2e-6, atol=4e-6), (rng, name, float((y - z).abs().max()))
 
 
 def test_symmetry_loss_update_vs_oracle():
