@@ -237,6 +237,8 @@ _SIGNATURES = {
     "hg_gather_rows_bf16": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P]),
     "hg_policy_head_rollout": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, _P, _P, C.c_int64, C.c_int, _P, _P, _P,
                                          C.c_uint64, C.c_uint64, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "hg_gaussian_sample": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_int, C.c_int, _P, _P, _P]),
+    "hg_gaussian_log_prob": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "hg_value_head": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P]),
     "hg_head_forward": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P]),
     "hg_store_rewards_dones": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P]),

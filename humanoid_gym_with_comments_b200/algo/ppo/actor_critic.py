@@ -181,17 +181,39 @@ class ActorCritic(nn.Module):
     def update_distribution(self, observations):
         self.engine()
         self._mean = self._net_forward(self.net_actor, observations)
-        self.distribution = torch.distributions.Normal(self._mean, self._mean * 0.0 + self.std.data, validate_args=False)
+
+    @property
+    def distribution(self):
+        """The reference's `self.distribution` attribute (a torch Normal over the last means), built on access only: `act`
+        and `get_actions_log_prob` run on the library's kernels."""
+        if self._mean is None:
+            return None
+        return torch.distributions.Normal(self._mean, self._mean * 0.0 + self.std.data, validate_args=False)
+
+    @distribution.setter
+    def distribution(self, value):
+        pass
 
     def act(self, observations, **kwargs):
         self.engine()
         self.update_distribution(observations)
-        action = self.distribution.sample()
+        rows, A = self._mean.shape
+        # the reference draws Normal(mean, std).sample() from torch's generator: the same stream as randn of that shape
+        eps = torch.randn(rows, A, device=self._mean.device)
+        action = torch.empty_like(self._mean)
+        self._rng_counter += 1
+        check(_lib.load().hg_gaussian_sample(ptr(self._mean), ptr(self.std.data), ptr(eps), 0, self._rng_counter, rows, A, ptr(action), None,
+                                             current_stream()))
         base_lin_vel = self.base_get_lin_vel(observations)
         return action, base_lin_vel
 
     def get_actions_log_prob(self, actions):
-        return self.distribution.log_prob(actions).sum(dim=-1)
+        _lib.require_cuda(actions)
+        a = actions if (actions.dtype == torch.float32 and actions.is_contiguous()) else actions.float().contiguous()
+        rows, A = self._mean.shape
+        out = torch.empty(rows, device=self._mean.device)
+        check(_lib.load().hg_gaussian_log_prob(ptr(a), ptr(self._mean), ptr(self.std.data), rows, A, ptr(out), current_stream()))
+        return out
 
     def act_inference(self, observations):
         self.engine()

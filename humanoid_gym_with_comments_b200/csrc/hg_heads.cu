@@ -948,6 +948,66 @@ static int launch_rollout(const void* h_actor, int64_t ld_ha, int H_a, const flo
 
 }  // namespace hg
 
+namespace hg {
+// Generic `ActorCritic.act` / `get_actions_log_prob` (actor_critic.py:127-138) for callers outside the fused rollout path:
+// a = mu + std * eps (eps given, or Philox4x32-10 keyed by (seed, counter, row, action)) and sum_a log N(a | mu, std).
+// One thread per row; the same fp32 expressions as the fused heads.
+__global__ void gaussian_sample_kernel(const float* __restrict__ mu, const float* __restrict__ std, const float* __restrict__ eps,
+                                       uint64_t seed, uint64_t counter, int n, int A, float* __restrict__ actions,
+                                       float* __restrict__ log_prob) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  float lp = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const float m = mu[(long long)row * A + a], sd = __ldg(std + a);
+    const float e = eps ? eps[(long long)row * A + a] : philox_normal(seed, counter, (uint32_t)row, (uint32_t)a);
+    const float act = m + sd * e;
+    const float d = act - m;
+    lp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;
+    actions[(long long)row * A + a] = act;
+  }
+  if (log_prob) log_prob[row] = lp;
+}
+
+__global__ void gaussian_log_prob_kernel(const float* __restrict__ actions, const float* __restrict__ mu, const float* __restrict__ std,
+                                         int n, int A, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  float lp = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const float sd = __ldg(std + a);
+    const float d = actions[(long long)row * A + a] - mu[(long long)row * A + a];
+    lp += -(d * d) / (2.f * sd * sd) - logf(sd) - LOG_SQRT_2PI;
+  }
+  out[row] = lp;
+}
+}  // namespace hg
+
+extern "C" int hg_gaussian_sample(const float* mu, const float* std, const float* eps, uint64_t seed, uint64_t counter, int n, int A,
+                                  float* actions, float* log_prob, void* stream) {
+  using namespace hg;
+  HG_CHECK(mu && std && actions && n > 0 && A >= 1, "hg_gaussian_sample: bad arguments");
+  HG_CUDA(launch_kernel(gaussian_sample_kernel, dim3((n + 127) / 128), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 1, mu, std, eps,
+                        seed, counter, n, A, actions, log_prob));
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
+}
+
+extern "C" int hg_gaussian_log_prob(const float* actions, const float* mu, const float* std, int n, int A, float* out, void* stream) {
+  using namespace hg;
+  HG_CHECK(actions && mu && std && out && n > 0 && A >= 1, "hg_gaussian_log_prob: bad arguments");
+  HG_CUDA(launch_kernel(gaussian_log_prob_kernel, dim3((n + 127) / 128), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 1, actions, mu,
+                        std, n, A, out));
+  HG_LAUNCH_CHECK();
+  count_launch();
+  return HG_OK;
+}
+
 extern "C" int hg_policy_head_rollout(const void* h_actor, int64_t ld_ha, int H_a, const float* W_a, const float* b_a,
                                       const float* std, const void* h_critic, int64_t ld_hc, int H_c, const float* W_c,
                                       const float* b_c, const float* eps, uint64_t seed, uint64_t counter, int n, int A,

@@ -157,6 +157,15 @@ int hg_ingest_rows(const float* src, int64_t src_ld, int rows, int cols, float* 
 /* Minibatch gather (rollout_storage.py:176-181): dst[r,:] = src[idx[r],:] for bf16 rows of `ld` elements. */
 int hg_gather_rows_bf16(const void* src, int64_t ld, const int64_t* idx, int rows, void* dst, void* stream);
 
+/* Generic `ActorCritic.act` / `get_actions_log_prob` (humanoid/algo/ppo/actor_critic.py:127-138) outside the fused rollout path:
+ *   hg_gaussian_sample:   actions = mu + std * eps  (eps [n,A] given, or NULL -> Philox4x32-10 keyed by (seed, counter, row, action)),
+ *                         log_prob (optional) = sum_a log N(actions | mu, std)           (Normal.sample / Normal.log_prob)
+ *   hg_gaussian_log_prob: out[n] = sum_a log N(actions | mu, std)
+ * mu, actions: f32 [n, A]; std: f32 [A]. */
+int hg_gaussian_sample(const float* mu, const float* std, const float* eps, uint64_t seed, uint64_t counter, int n, int A,
+                       float* actions, float* log_prob, void* stream);
+int hg_gaussian_log_prob(const float* actions, const float* mu, const float* std, int n, int A, float* out, void* stream);
+
 /* Output layers of actor and critic + Gaussian sampling + log-prob for one rollout step.
  * Replaces ActorCritic.act / evaluate / get_actions_log_prob as used by PPO.act
  * (actor_critic.py:127-138,144-146; ppo.py:116-126) for the last Linear of each net.

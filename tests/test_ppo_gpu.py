@@ -323,9 +323,18 @@ def test_runner_style_loop_and_api_surface():
         alg.actor_critic.forward()
     # generic API methods
     ac = alg.actor_critic
+    torch.manual_seed(77)
     a, lv = ac.act(obs)
     assert a.shape == (N, 12) and lv.shape == (N, 3)
     assert ac.get_actions_log_prob(a).shape == (N,)
+    # ... which run on the library's kernels (hg_gaussian_sample / hg_gaussian_log_prob) and reproduce the reference's
+    # Normal(mean, std).sample() / .log_prob(a).sum(-1) for the same generator state
+    torch.manual_seed(77)
+    want = torch.distributions.Normal(ac.action_mean, ac.action_std).sample()
+    assert torch.allclose(a, want, atol=1e-6), float((a - want).abs().max())
+    lp_want = torch.distributions.Normal(ac.action_mean, ac.action_std).log_prob(a).sum(-1)
+    assert torch.allclose(ac.get_actions_log_prob(a), lp_want, rtol=1e-5, atol=1e-5)
+    assert isinstance(ac.distribution, torch.distributions.Normal)
     assert ac.action_mean.shape == (N, 12) and ac.action_std.shape == (N, 12) and ac.entropy.shape == (N,)
     assert ac.evaluate(critic_obs).shape == (N, 1) and ac.act_inference(obs).shape == (N, 12)
     # reference-shaped minibatch generator: 12-tuple, bit-exact row gather
