@@ -1,16 +1,19 @@
 // Fused env-step tensor math: one launch replaces the several hundred ATen launches of
 // XBotLFreeEnv.post_physics_step (reference humanoid/envs/custom/humanoid_env.py:780-806 and callees).
 //
-// The scalar math runs one THREAD per env (32x fewer warp instructions than a warp per env), split over four "role"
-// warps of the block (observation frames / joint rewards / feet rewards / base-motion rewards) so each env's
-// dependent-latency chain is short; the new frames are assembled in shared memory.  Two history formats:
+// One block = 16 (or 32) envs.  All per-env inputs and persistent state of the block are first staged into shared memory by
+// one table-driven cp.async loop (a single global round trip); the scalar math then runs one THREAD per env and role out of
+// shared memory (32x fewer warp instructions than a warp per env), split over "role" warps (observation frames: phase /
+// joints and base frame / euler; joint rewards; feet rewards; base-motion rewards) so each env's dependent-latency chain is
+// short; the new frames are assembled in shared memory and leave with coalesced stores.  Two history formats:
 //   * stacked (generic API, `obs_prev` -> `obs_next`): 16 envs per 512-thread block; warps 4-15 stream the history
 //     shift obs_next[n,:] = clip([obs_prev[n,So:], new_frame]) with coalesced 128-byte accesses while warps 0-3 do the
 //     math (15 x So floats written, 14 x So read per env; same for the 3-frame critic stack).
 //     Algorithmic HBM bytes per env-step (D=12): 4*(47*29 + 73*5) = 6,912 B history + ~0.9 KB state.
-//   * history ring (`ring_obs` / `ring_priv`): 16 or 32 envs per 128-thread block; only the NEWEST frame
-//     is written (fp32 live + fp32 archive + bf16 live), nothing is shifted or re-read; a reset zeroes the env's live
-//     frames in place.  Algorithmic bytes per env-step (D=12): 2*4*(47+73) + 2*(48+80) = 1,216 B frames + ~0.9 KB state.
+//   * history ring (`ring_obs` / `ring_priv`): 16 or 32 envs per 256-thread block (warp 4 takes the
+//     base-frame part of the frames, warps 5-7 draw the observation noise while the role warps work); only the NEWEST frame
+//     is written (fp32 live + archive, bf16 live + archive), nothing is shifted or re-read; a reset zeroes the env's live
+//     frames in place.  Algorithmic bytes per env-step (D=12): 2*4*(47+73) + 2*2*(48+80) = 1,472 B frames + ~0.9 KB state.
 //
 // Compiled with -fmad=false: every +,-,*,/ is a separately rounded IEEE op in the reference's order, so all
 // threshold decisions (contacts, resets, dead-bands, feet clearance) are bit-identical to torch-CPU; only
