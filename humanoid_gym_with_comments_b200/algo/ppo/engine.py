@@ -384,7 +384,12 @@ class MLPEngine:
                 bn = self._block_n(dw_n, "dw")
                 cg = self._cta_group(dw, EPI_ATOMIC_F32)
                 tiles = sum(((p.M + 128 * cg - 1) // (128 * cg)) * ((p.N + bn - 1) // bn) for p in dw)
-                splits = max(1, min((rows + 63) // 64, (self.num_sms // cg) // max(tiles, 1)))
+                # split-K so that every CTA (pair) gets `waves` tiles.  One tile per CTA leaves the fp32-atomic epilogue of
+                # the tile exposed (9 us of a 31 us layer-3 launch in the device timeline); two or more would overlap it
+                # with the next tile's main loop, but measured SLOWER (update 4.84 / 4.95 / 5.00 / 5.14 ms for 1 / 2 / 3 / 4
+                # waves: every extra split adds a full fp32 RED pass over the weight gradient), so 1 stays
+                waves = int(os.environ.get("HG_DW_WAVES", "1"))
+                splits = max(1, min((rows + 63) // 64, waves * (self.num_sms // cg) // max(tiles, 1)))
                 for p in dw:
                     p.k_splits = splits
                 self._launch(dw, EPI_ATOMIC_F32, bn)

@@ -24,6 +24,19 @@ if which in ("dx1", "dx2"):
         H = bg.bf(m, KL); out = torch.empty(m, KL, dtype=torch.bfloat16, device=bg.DEV); cs = torch.zeros(KL, device=bg.DEV)
         probs.append(make_problem(dZ, W, out, m, KL, NL, 0, 1, act=H, colsum=cs)); keep.append((dZ, W, H, out, cs))
     run = lambda: bg.gemm_nosync(probs, _lib.EPI_DELU_BF16, 256)
+elif which in ("dw3", "dw2"):
+    # dW = dZ^T [NL, m] @ H [m, KL]: split-K over the rows, fp32 atomic epilogue (layer 3 / layer 2 shapes)
+    specs = [(128, 256), (128, 256), (128, 128)] if which == "dw3" else [(256, 512), (256, 768), (128, 720)]
+    bg.CG = int(os.environ.get("HG_CG", 2))
+    tiles = sum(((NL + 128 * bg.CG - 1) // (128 * bg.CG)) * ((KL + 255) // 256) for NL, KL in specs)
+    splits = max(1, min((m + 63) // 64, (148 // bg.CG) // max(tiles, 1)))
+    probs, keep = [], []
+    for NL, KL in specs:
+        dZ, H = bg.bf(m, NL, 1e-3), bg.bf(m, (KL + 63) // 64 * 64)
+        out = torch.zeros(NL, KL, device=bg.DEV)
+        probs.append(make_problem(dZ, H, out, NL, KL, m, 1, 1, k_splits=splits)); keep.append((dZ, H, out))
+    print("splits", splits, "tiles", tiles, "cg", bg.CG)
+    run = lambda: bg.gemm_nosync(probs, _lib.EPI_ATOMIC_F32, 256)
 else:
     specs = [(512, 720), (768, 240), (128, 720)] if which == "fwd1" else [(128, 256), (128, 256), (128, 128)]
     probs, keep = [], []
