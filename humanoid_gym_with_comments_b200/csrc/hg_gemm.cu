@@ -31,6 +31,9 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barrie
 #ifndef HG_EPI_WARPS
 #define HG_EPI_WARPS 16
 #endif
+#ifndef HG_F32_EPI_WARPS
+#define HG_F32_EPI_WARPS 8
+#endif
 constexpr int MN_ATOM_BYTES = BLOCK_K * 128;  // 8192: one [64 x 64] bf16 atom
 constexpr int HG_MAX_COLSUM_COLS = 2048;      // columns (summed over the problems of a group) a DELU launch can column-sum
 
@@ -39,15 +42,15 @@ struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;                 // 16 KB
   static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;          // 8 / 16 / 32 KB (per CTA)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // per-warp staging tile: 32 x 33 floats for the transposing split-K epilogue; for the bf16 ones 32 rows x 64 B, dense, in
+  // per-warp staging tile: 32 x 36 floats for the transposing split-K epilogue; for the bf16 ones 32 rows x 64 B, dense, in
   // the SWIZZLE_64B layout (16-byte chunk index XOR (row / 2) % 4: conflict-free 16-byte accesses) -- the source of the
   // TMA store of the chunk.  Behind ALL tiles: 256 B per warp for its slice of the bias vector.
-  static constexpr int EPI_TILE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 32 * 33 * 4 : 32 * 64;
+  static constexpr int EPI_TILE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 32 * 36 * 4 : 32 * 64;
   static constexpr int BIAS_SLICE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 0 : 256;
   static constexpr bool F32_OUT = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32);
   // epilogue warps: 4 per scheduler for the bf16 epilogues (they bound the short-K launches: 16 beat 8 by ~20 %);
   // the fp32 ones sit behind K = rows main loops and keep 8 so that their 4 KB staging tiles leave a deeper TMA ring
-  static constexpr int EPI_WARPS = F32_OUT ? 8 : HG_EPI_WARPS;
+  static constexpr int EPI_WARPS = F32_OUT ? HG_F32_EPI_WARPS : HG_EPI_WARPS;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int COL_SPLIT = EPI_WARPS / 4;       // column slices per tile
   // HEAD: [16][128] fp32 output weights + [4 slices][128][17] fp32 partial sums + per-output constants
@@ -305,23 +308,40 @@ __device__ __forceinline__ void epilogue_chunk(const DevProblem& q, int row, int
         if (n0 + j < q.N) o[j] = __uint_as_float(v[j]) + (q.bias ? __ldg(q.bias + n0 + j) : 0.f);
     }
   } else if constexpr (EPI == HG_EPI_ATOMIC_F32) {
-    // Transpose the warp's 32x32 chunk through shared memory so that every RED instruction adds 32 CONSECUTIVE
-    // floats of one output row (1-2 L2 lines per instruction instead of 32).
+    // Transpose the warp's 32x32 chunk through shared memory (rows 36 floats apart: 16-byte aligned and conflict-free
+    // both ways) so that every RED instruction adds CONSECUTIVE floats of an output row.  Whole chunks of a 16-byte
+    // aligned output go out as red.global.add.v4.f32: 8 lanes cover a row's 128 bytes, 8 instructions the chunk
+    // (a quarter of the scalar form's LSU work); ragged chunks and the frame-remapped layer-1 gradients take the
+    // scalar form, 32 consecutive floats per instruction.
+    const uint32_t tile_s = smem_u32(tile);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+    for (int j = 0; j < 8; ++j) sts128(tile_s + lane * 144 + j * 16, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
     __syncwarp();
     const int row_base = row - lane;
-    bool col_ok = n0 + lane < q.N;
-    int ocol = n0 + lane;
-    if (q.out_fs) {      // frame-pitched input columns -> the packed columns of the weight gradient; pad columns are dropped
-      const int f = ocol / q.out_fs, c = ocol - f * q.out_fs;
-      col_ok = col_ok && c < q.out_fd;
-      ocol = f * q.out_fd + c;
-    }
+    float* out = reinterpret_cast<float*>(q.out);
+    if (full && !q.out_fs && ((q.ldo & 3) | (int)(reinterpret_cast<uintptr_t>(out) & 15)) == 0) {
+      const int r0 = lane >> 3, c4 = lane & 7;
+      float* o = out + (long long)(row_base + r0) * q.ldo + n0 + c4 * 4;
+      const long long step = 4ll * q.ldo;
+#pragma unroll
+      for (int i = 0; i < 8; ++i, o += step) {
+        const uint4 w = lds128(tile_s + (i * 4 + r0) * 144 + c4 * 16);
+        if (row_base + i * 4 + r0 < q.M)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(__uint_as_float(w.x)), "f"(__uint_as_float(w.y)),
+                       "f"(__uint_as_float(w.z)), "f"(__uint_as_float(w.w)) : "memory");
+      }
+    } else {
+      bool col_ok = n0 + lane < q.N;
+      int ocol = n0 + lane;
+      if (q.out_fs) {      // frame-pitched input columns -> the packed columns of the weight gradient; pad columns are dropped
+        const int f = ocol / q.out_fs, c = ocol - f * q.out_fs;
+        col_ok = col_ok && c < q.out_fd;
+        ocol = f * q.out_fd + c;
+      }
 #pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-      if (col_ok && row_base + i < q.M)
-        atomicAdd(reinterpret_cast<float*>(q.out) + (long long)(row_base + i) * q.ldo + ocol, tile[i * 33 + lane]);
+      for (int i = 0; i < 32; ++i) {
+        if (col_ok && row_base + i < q.M) atomicAdd(out + (long long)(row_base + i) * q.ldo + ocol, tile[i * 36 + lane]);
+      }
     }
     __syncwarp();
   } else if constexpr (EPI == HG_EPI_BIAS_ELU_BF16 || EPI == HG_EPI_BIAS_BF16) {
