@@ -467,29 +467,36 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
 //   backward: dH = dOut W and gW = dOut^T h with dOut = hi + lo (16 mantissa bits), W = hi + mid.
 // The critic (1 output) and lin-vel (3 outputs) heads share one 16-row weight tile: row 0 = critic, rows 1..3 = lin-vel.
 namespace mh {
-constexpr int ROWS = 64;             // rows per tile
+constexpr int ROWS = 32;             // rows per tile
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int SUB = THREADS / ROWS;  // lanes per row in the loss phase
+static_assert(SUB >= 7, "the SUB lanes of a row fetch its 7 scalars, one each");
 constexpr int NO = 16;               // padded outputs per head (two n8 mma tiles)
 constexpr int DP = NO + 8;           // row pitch of the gradient tiles (48 B: conflict-free ldmatrix)
 constexpr int MAXP = 3;              // (net, 16-column tile) pairs per warp: 3 nets * (128/16) / 8 warps
 constexpr int HMAX = 128;
 constexpr int AJ = NO / SUB;         // actions per lane
-constexpr int MAXCH = ROWS * (HMAX / 8) / THREADS;   // 16-byte chunks of one activation tile per thread
+// A row's old-policy record in shared memory: actions | old means | old sigmas (NO words each) | old log-prob, advantage,
+// return, old value, 3 lin-vel targets.  56 words: 16-byte aligned rows, and the 4 rows a warp reads sit 24 banks apart.
+constexpr int RS = 3 * NO + 8;
+constexpr int RS_SCALARS = 3 * NO;
 
 struct Layout {
-  size_t sh, wm, out, dO, bias, cst, total;
+  size_t sh, wm, out, dO, bias, cst, rec, bar, sh_buf, total;
   __host__ __device__ explicit Layout(int H) {
     const size_t HP = H + 8;
     size_t o = 0;
     auto take = [&](size_t b) { size_t q = o; o += (b + 127) & ~size_t(127); return q; };
-    sh = take(3 * ROWS * HP * 2);
+    sh_buf = (3 * ROWS * HP * 2 + 127) & ~size_t(127);
+    sh = take(2 * sh_buf);                       // two tiles: the next one lands while this one is computed on
+    rec = take(2 * ROWS * RS * 4);
     wm = take(2 * 3 * NO * HP * 2);
     out = take(3 * ROWS * NO * 4);
     dO = take(3 * 2 * ROWS * DP * 2);
     bias = take(3 * NO * 4);
     cst = take(4 * NO * 4);
+    bar = take(2 * 8);                           // one mbarrier per activation buffer
     total = o;
   }
 };
@@ -508,6 +515,16 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g, bool valid) {
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+}
+// One contiguous run of bytes global -> shared through the TMA unit (no L1 miss slots, no per-thread address work);
+// completion is counted on an mbarrier.  dst, src and bytes are multiples of 16.
+__device__ __forceinline__ void bulk_g2s(uint32_t saddr, const void* g, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(saddr), "l"(g), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, bool valid) {
   const int sz = valid ? 16 : 0;      // src-size 0 -> the 16 bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
@@ -518,71 +535,140 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
   using namespace mh;
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x == 0) trace(0x000);
   extern __shared__ __align__(128) uint8_t smem[];
   const int H = L.actor.H, HP = H + 8, A = L.A, NT = H >> 4, P = 3 * NT;
   const Layout lay(H);
-  __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(smem + lay.sh);          // [3][ROWS][HP]
+  __nv_bfloat16* sh0 = reinterpret_cast<__nv_bfloat16*>(smem + lay.sh);         // [2 buffers][3][ROWS][HP]
+  const float* s_rec = reinterpret_cast<const float*>(smem + lay.rec);          // [2][ROWS][RS]
   __nv_bfloat16* wm = reinterpret_cast<__nv_bfloat16*>(smem + lay.wm);          // [2][3][NO][HP]
   float* s_out = reinterpret_cast<float*>(smem + lay.out);                      // [3][ROWS][NO]
   __nv_bfloat16* s_dO = reinterpret_cast<__nv_bfloat16*>(smem + lay.dO);        // [3][2][ROWS][DP]
   float* s_bias = reinterpret_cast<float*>(smem + lay.bias);                    // [3][NO]
   float* s_c = reinterpret_cast<float*>(smem + lay.cst);                        // [std | 1/(2 s^2) | log s | 1/s][NO]
-  const uint32_t sh_u = smem_u32(sh), wm_u = smem_u32(wm), dO_u = smem_u32(s_dO);
+  const uint32_t sh0_u = smem_u32(sh0), wm_u = smem_u32(wm), dO_u = smem_u32(s_dO);
+  const uint32_t rec_u = smem_u32(s_rec), bar_u = smem_u32(smem + lay.bar);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g8 = lane >> 2, t4 = lane & 3;           // mma fragment coordinates
   const int mi = lane >> 3, rr = lane & 7;           // ldmatrix: this lane addresses row rr of 8x8 matrix mi
+  if (tid == 0) {
+    mbar_init(bar_u, 1);
+    mbar_init(bar_u + 8, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
 
-  // ---- once per block: weights as three bf16 terms, biases, per-action constants, zeroed gradient tiles
-  for (int i = tid; i < 2 * NO * H; i += THREADS) {
-    const int mat = i / (NO * H), rem = i - mat * NO * H, n = rem / H, k = rem - n * H;
-    float w = 0.f;
-    if (mat == 0) {
-      if (n < A) w = __ldg(L.actor.W + n * H + k);
-    } else if (n == 0) {
-      w = __ldg(L.critic.W + k);
-    } else if (n < 4) {
-      w = __ldg(L.linvel.W + (n - 1) * H + k);
-    }
-    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-    const float r1 = w - __bfloat162float(hi);
-    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-    __nv_bfloat16* d = wm + (size_t)(mat * 3) * NO * HP + n * HP + k;
-    d[0] = hi;
-    d[(size_t)NO * HP] = mid;
-    d[(size_t)2 * NO * HP] = lo;
-  }
-  for (int i = tid; i < 3 * 2 * ROWS * DP / 2; i += THREADS) reinterpret_cast<uint32_t*>(s_dO)[i] = 0u;
-  if (tid < 3 * NO) {
-    const int net = tid / NO, n = tid - net * NO;
-    float b = 0.f;
-    if (net == 0) { if (n < A) b = __ldg(L.actor.b + n); }
-    else if (net == 1) { if (n == 0) b = __ldg(L.critic.b); }
-    else if (n >= 1 && n < 4) b = __ldg(L.linvel.b + n - 1);
-    s_bias[tid] = b;
-  }
-  if (tid < NO) {
-    const float sd = tid < A ? __ldg(L.std + tid) : 1.f;
-    s_c[tid] = sd;
-    s_c[NO + tid] = 1.f / (2.f * sd * sd);
-    s_c[2 * NO + tid] = logf(sd);
-    s_c[3 * NO + tid] = 1.f / sd;
-  }
-  // activation staging map of this thread (tile independent): chunk u -> (row, 16-byte column chunk)
-  const int chunks = H >> 3;
-  int st_row[MAXCH], st_col[MAXCH];
-#pragma unroll
-  for (int u = 0; u < MAXCH; ++u) {
-    const int i = tid + u * THREADS;
-    st_row[u] = i / chunks;                      // >= ROWS when this thread has no chunk u
-    st_col[u] = (i - st_row[u] * chunks) * 8;
-  }
   // per-net kernel parameters picked with selects (a runtime-indexed array would live in local memory)
   auto net_h = [&](int net) { return reinterpret_cast<const __nv_bfloat16*>(net == 0 ? L.actor.h : net == 1 ? L.critic.h : L.linvel.h); };
   auto net_ldh = [&](int net) { return net == 0 ? L.actor.ld_h : net == 1 ? L.critic.ld_h : L.linvel.ld_h; };
   auto net_dz = [&](int net) { return reinterpret_cast<__nv_bfloat16*>(net == 0 ? L.actor.dZ : net == 1 ? L.critic.dZ : L.linvel.dZ); };
   auto net_lddz = [&](int net) { return net == 0 ? L.actor.ld_dz : net == 1 ? L.critic.ld_dz : L.linvel.ld_dz; };
+  // Four consecutive weights per step, all of a thread's loads issued before the first is used (the element-wise loop
+  // paid one L2 / DRAM round trip per iteration, 16 in a row: ~15 us of an 86 us launch).
+  constexpr int STEPS = 2 * NO * HMAX / 4 / THREADS;
+  const int h4 = H >> 2;
+  float4 w4[STEPS];
+  int dst[STEPS];
+#pragma unroll
+  for (int u = 0; u < STEPS; ++u) {
+    const int i = tid + u * THREADS;                 // float4 index over [2 matrices][NO rows][H / 4]
+    const int row = i / h4, k = (i - row * h4) * 4, mat = row / NO, n = row - mat * NO;
+    const float* src = nullptr;
+    if (mat == 0) { if (n < A) src = L.actor.W + n * H + k; }
+    else if (mat == 1) { if (n == 0) src = L.critic.W + k; else if (n < 4) src = L.linvel.W + (n - 1) * H + k; }
+    w4[u] = src ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dst[u] = mat < 2 ? (mat * 3 * NO + n) * HP + k : -1;
+  }
+  float b_early = 0.f, sd_early = 1.f;               // biases and std: loaded here, stored behind the first tile's issue
+  if (tid < 3 * NO) {
+    const int net = tid / NO, n = tid - net * NO;
+    if (net == 0) { if (n < A) b_early = __ldg(L.actor.b + n); }
+    else if (net == 1) { if (n == 0) b_early = __ldg(L.critic.b); }
+    else if (n >= 1 && n < 4) b_early = __ldg(L.linvel.b + n - 1);
+  }
+  if (tid < A) sd_early = __ldg(L.std + tid);
+  const int r = tid / SUB, sub = tid % SUB;
+  const float inv_rows = L.inv_world / (float)L.rows;      // 1 / (rows over all ranks)
+  const int ntiles = (L.rows + ROWS - 1) / ROWS;
+  // Row of the old-policy record that thread (r, sub) reads for tile t (minibatch permutation), 0 past the end.
+  auto record_row = [&](int t) -> long long {
+    const int row = t * ROWS + r;
+    if (t >= ntiles || row >= L.rows) return 0;
+    if (!L.idx) return (long long)row;
+    long long v;      // volatile: the load is issued HERE, a tile ahead of its use (left to the compiler it sinks to the use)
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(L.idx + row));
+    return v;
+  };
+  // Everything tile t needs, global -> shared buffer b with cp.async: the three activation tiles (rows past the end
+  // zero-filled) and the old-policy record -- each thread fetches the action-wise words it will consume itself, the SUB
+  // lanes of a row one per-row scalar each.
+  auto issue_loads = [&](int t, int b, long long src) {
+    const int row0 = t * ROWS;
+    const int valid = min(ROWS, L.rows - row0);
+    const uint32_t sh_b = sh0_u + (uint32_t)(b * lay.sh_buf);
+    if (tid == 0) mbar_arrive_expect_tx(bar_u + b * 8, (uint32_t)(3 * valid * H * 2));
+    if (tid < 3 * ROWS) {                        // one activation row per thread (a warp per net): a bulk copy of H * 2 bytes
+      const int net = tid / ROWS, row = tid - net * ROWS;
+      const uint32_t d = sh_b + (uint32_t)((net * ROWS + row) * HP) * 2;
+      if (row < valid) {
+        bulk_g2s(d, net_h(net) + (long long)(row0 + row) * net_ldh(net), (uint32_t)H * 2, bar_u + b * 8);
+      } else {                                   // rows past the end are zero (their gradients are, too: no NaN from stale bits)
+        for (int c = 0; c < H * 2; c += 16) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(d + c), "r"(0) : "memory");
+      }
+    }
+    // the record: 3 * A / 4 16-byte pieces of the action-wise arrays (A % 4 == 0 on this path) and 7 scalars per row,
+    // spread over the row's SUB lanes (4-byte cp.async costs the LSU a pass per lane, so as few of those as possible)
+    const bool rok = r < valid;
+    const uint32_t rec_row = rec_u + (uint32_t)((b * ROWS + r) * RS) * 4;
+    const int a4 = A >> 2;
+#pragma unroll
+    for (int c0 = 0; c0 < 3 * NO / 4; c0 += SUB) {
+      const int c = c0 + sub, arr = c / a4, part = c - arr * a4;
+      if (arr < 3) {
+        const float* g = (arr == 0 ? L.actions : arr == 1 ? L.old_mu : L.old_sigma) + src * A + part * 4;
+        cp_async16(rec_row + (uint32_t)(arr * NO + part * 4) * 4, g, rok);
+      }
+    }
+    if (sub < 7) {
+      const float* g = sub == 0 ? L.old_log_prob + src : sub == 1 ? L.advantages + src : sub == 2 ? L.returns + src
+                     : sub == 3 ? L.old_values + src : L.critic_obs + src * L.ld_cobs + L.lv_col + (sub - 4);
+      cp_async4(rec_row + (uint32_t)(RS_SCALARS + sub) * 4, g, rok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // ---- software pipeline over the block's tiles: tile t + 1 is in flight (cp.async, second buffer) while tile t is
+  // computed on, and the permutation index of tile t + 2 sits in a register.  Unpipelined, every block spent 7.5 of its
+  // ~19 us per 64 rows waiting for loads, all blocks at the same time (device timeline, tools/bench_loss.py).
+  issue_loads(blockIdx.x, 0, record_row(blockIdx.x));
+  long long src_next = record_row(blockIdx.x + gridDim.x);
+  // ---- once per block: weights as three bf16 terms, biases, per-action constants, zeroed gradient tiles
+#pragma unroll
+  for (int u = 0; u < STEPS; ++u) {
+    if (dst[u] < 0) continue;
+    const float w[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+    __align__(8) __nv_bfloat16 t[3][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      t[0][e] = __float2bfloat16_rn(w[e]);
+      const float r1 = w[e] - __bfloat162float(t[0][e]);
+      t[1][e] = __float2bfloat16_rn(r1);
+      t[2][e] = __float2bfloat16_rn(r1 - __bfloat162float(t[1][e]));
+    }
+#pragma unroll
+    for (int sp = 0; sp < 3; ++sp)
+      *reinterpret_cast<uint2*>(wm + (size_t)sp * NO * HP + dst[u]) = *reinterpret_cast<const uint2*>(t[sp]);
+  }
+  for (int i = tid; i < 3 * 2 * ROWS * DP / 2; i += THREADS) reinterpret_cast<uint32_t*>(s_dO)[i] = 0u;
+  if (tid < 3 * NO) s_bias[tid] = b_early;
+  if (tid < NO) {
+    const float sd = sd_early;
+    s_c[tid] = sd;
+    s_c[NO + tid] = 1.f / (2.f * sd * sd);
+    s_c[2 * NO + tid] = logf(sd);
+    s_c[3 * NO + tid] = 1.f / sd;
+  }
   __syncthreads();
+  if (tid == 0) trace(0x001);
 
   // ---- accumulators that live for the whole launch
   float gWf[MAXP][2][4];      // [pair][n8 tile][fragment]: rows = outputs g8 / g8+8, cols = 2 t4, 2 t4 + 1
@@ -592,53 +678,31 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
 #pragma unroll
     for (int i = 0; i < 4; ++i) gWf[j][0][i] = gWf[j][1][i] = gbh[j][i] = 0.f;
   }
-  float st_v = 0.f, st_s = 0.f, st_l = 0.f, st_k = 0.f, st_e = 0.f;
+  float st_v = 0.f, st_s = 0.f, st_l = 0.f, st_k = 0.f;
   float gb_a[AJ], gs_a[AJ], gb_c = 0.f, gb_l[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < AJ; ++j) gb_a[j] = gs_a[j] = 0.f;
 
-  const int r = tid / SUB, sub = tid % SUB;
-  const float inv_rows = L.inv_world / (float)L.rows;      // 1 / (rows over all ranks)
-  const int ntiles = (L.rows + ROWS - 1) / ROWS;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
     const int row0 = tile * ROWS;
     const int valid = min(ROWS, L.rows - row0);
     const bool row_ok = r < valid;
-    // -- activations: global -> shared with cp.async (rows beyond `valid` zero-filled)
-#pragma unroll
-    for (int net = 0; net < 3; ++net) {
-#pragma unroll
-      for (int u = 0; u < MAXCH; ++u) {
-        if (st_row[u] < ROWS) {
-          const bool ok = st_row[u] < valid;
-          cp_async16(sh_u + (uint32_t)((net * ROWS + st_row[u]) * HP + st_col[u]) * 2,
-                     net_h(net) + (long long)(row0 + (ok ? st_row[u] : 0)) * net_ldh(net) + st_col[u], ok);
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    // -- the row's old-policy record, straight into registers (independent loads, consumed after the forward GEMMs)
-    const long long src = row_ok ? (L.idx ? __ldg(L.idx + row0 + r) : (long long)(row0 + r)) : 0;
-    float r_act[AJ], r_mu[AJ], r_sd[AJ];
-#pragma unroll
-    for (int j = 0; j < AJ; ++j) {
-      const int a = sub + SUB * j;
-      const bool ok = row_ok && a < A;
-      r_act[j] = ok ? __ldg(L.actions + src * A + a) : 0.f;
-      r_mu[j] = ok ? __ldg(L.old_mu + src * A + a) : 0.f;
-      r_sd[j] = ok ? __ldg(L.old_sigma + src * A + a) : 1.f;
-    }
-    const float r_logp = row_ok ? __ldg(L.old_log_prob + src) : 0.f;
-    const float r_adv = row_ok ? __ldg(L.advantages + src) : 0.f;
-    float r_ret = 0.f, r_vold = 0.f, r_tgt[3] = {0.f, 0.f, 0.f};
-    if (row_ok && sub == 0) {
-      r_ret = __ldg(L.returns + src);
-      r_vold = __ldg(L.old_values + src);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) r_tgt[j] = __ldg(L.critic_obs + src * L.ld_cobs + L.lv_col + j);
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int round = tile / (int)gridDim.x;
+    if (tid == 0) trace(0x002, round);
+    if (tile + (int)gridDim.x < ntiles) issue_loads(tile + gridDim.x, buf ^ 1, src_next);
+    else asm volatile("cp.async.commit_group;" ::: "memory");     // (empty group: keeps the wait below uniform)
+    src_next = record_row(tile + 2 * gridDim.x);
+    if (tid == 0) trace(0x008, round);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");          // this tile's record has landed; the next one may be in flight
+    mbar_wait(bar_u + buf * 8, (uint32_t)(it >> 1) & 1u);         // ... and its activation rows (k-th use of the buffer: parity k & 1)
     __syncthreads();
+    if (tid == 0) trace(0x003, round);
+    const __nv_bfloat16* sh = sh0 + (size_t)buf * (lay.sh_buf / 2);
+    const uint32_t sh_u = sh0_u + (uint32_t)(buf * lay.sh_buf);
+    const float* rec = s_rec + (size_t)(buf * ROWS + r) * RS;           // this thread's row
+    const float* rowrec = rec + RS_SCALARS;
 
     // -- forward: out[net][64][16] = h W^T.  Jobs = (net, 16-row group, n8 tile); the second n8 tile exists only for the
     //    actor (outputs 8..A-1): 16 jobs, two per warp.
@@ -666,10 +730,11 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
       *reinterpret_cast<float2*>(o + (g8 + 8) * NO) = make_float2(c[2], c[3]);
     }
     __syncthreads();
+    if (tid == 0) trace(0x004, round);
 
     // -- losses and d loss / d outputs (same math as ppo_head_loss_kernel; SUB lanes per row split the actions)
     {
-      float logp = 0.f, ent = 0.f, kl = 0.f;
+      float logp = 0.f, kl = 0.f;
       float m[AJ];
 #pragma unroll
       for (int j = 0; j < AJ; ++j) {
@@ -678,18 +743,16 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
         if (a < A && row_ok) {
           m[j] = s_out[r * NO + a] + s_bias[a];
           const float sd = s_c[a], i2v = s_c[NO + a], lsd = s_c[2 * NO + a];
-          const float d = r_act[j] - m[j];
+          const float d = rec[a] - m[j];
           logp += -(d * d) * i2v - lsd - LOG_SQRT_2PI;
-          ent += HALF_LOG_2PI_PLUS_HALF + lsd;
-          const float osd = r_sd[j];
-          const float dm = r_mu[j] - m[j];
+          const float osd = rec[2 * NO + a];
+          const float dm = rec[NO + a] - m[j];
           kl += logf(sd * __frcp_rn(osd) + 1.e-5f) + (osd * osd + dm * dm) * i2v - 0.5f;
         }
       }
 #pragma unroll
       for (int o = SUB >> 1; o > 0; o >>= 1) {
         logp += __shfl_xor_sync(0xffffffffu, logp, o);
-        ent += __shfl_xor_sync(0xffffffffu, ent, o);
         kl += __shfl_xor_sync(0xffffffffu, kl, o);
       }
       float g_logp = 0.f;
@@ -702,16 +765,17 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
         base[ROWS * DP + r * DP + col] = __float2bfloat16_rn(g - __bfloat162float(hi));
       };
       if (row_ok) {
-        const float ratio = expf(logp - r_logp);
+        const float r_adv = rowrec[1];
+        const float ratio = expf(logp - rowrec[0]);
         const float s1 = -r_adv * ratio;
         const float s2 = -r_adv * fminf(fmaxf(ratio, 1.f - L.clip_param), 1.f + L.clip_param);
         g_logp = (s1 >= s2 ? s1 : 0.f) * inv_rows;               // d surr / d logp  (ties: clamp passes gradient)
         if (sub == 0) {
-          st_s += fmaxf(s1, s2); st_k += kl; st_e += ent;
-          const float R = r_ret, v = s_out[ROWS * NO + r * NO] + s_bias[NO];
+          st_s += fmaxf(s1, s2); st_k += kl;
+          const float R = rowrec[2], v = s_out[ROWS * NO + r * NO] + s_bias[NO];
           float vl, g_v;
           if (L.use_clipped_value_loss) {
-            const float vo = r_vold;
+            const float vo = rowrec[3];
             const float dv = v - vo;
             const float vc = vo + fminf(fmaxf(dv, -L.clip_param), L.clip_param);
             const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
@@ -729,7 +793,7 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
           float lsq = 0.f;
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            const float e = s_out[2 * ROWS * NO + r * NO + 1 + j] + s_bias[2 * NO + 1 + j] - r_tgt[j];
+            const float e = s_out[2 * ROWS * NO + r * NO + 1 + j] + s_bias[2 * NO + 1 + j] - rowrec[4 + j];
             lsq += e * e;
             const float gl = L.lin_vel_coef * 2.f * e * inv_rows * (1.f / 3.f);
             put(dOl, 1 + j, gl);
@@ -749,7 +813,7 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
           float gm = 0.f;
           if (row_ok) {
             const float isd = s_c[3 * NO + a], ivar = 2.f * s_c[NO + a];
-            const float d = r_act[j] - m[j];
+            const float d = rec[a] - m[j];
             gm = g_logp * d * ivar;
             gs_a[j] += g_logp * (d * d * ivar * isd - isd) - L.entropy_coef * inv_rows * isd;
           }
@@ -759,6 +823,7 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
       }
     }
     __syncthreads();
+    if (tid == 0) trace(0x005, round);
 
     // -- backward: each warp owns up to MAXP (net, 16-column tile) pairs for the whole launch
 #pragma unroll
@@ -790,8 +855,9 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
         ldsm_x4_t(bh, w_u + w_off);
         ldsm_x4_t(bm, w_u + (uint32_t)(NO * HP) * 2 + w_off);
         const __nv_bfloat16* h_lane = sh + (size_t)(net * ROWS + g8) * HP + n0 + 2 * t4;    // this lane's first (row, col)
-        const long long ldz = net_lddz(net);
-        __nv_bfloat16* dz_lane = net_dz(net) + (long long)(row0 + g8) * ldz + n0 + 2 * t4;
+        const long long ldz8 = 8ll * net_lddz(net);
+        __nv_bfloat16* dz_lane = net_dz(net) + (long long)(row0 + g8) * net_lddz(net) + n0 + 2 * t4;   // stepped 8 rows at a time
+        const int rows_left = valid - g8;
 #pragma unroll
         for (int rg = 0; rg < ROWS / 16; ++rg) {
           uint32_t ah[4], al[4];
@@ -806,22 +872,24 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
           mma16816(c[0], ah, bh[0], bh[1]);
           mma16816(c[1], ah, bh[2], bh[3]);
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt) {
+          for (int hf = 0; hf < 2; ++hf, dz_lane += ldz8) {   // rows g8 and g8 + 8
+            const int off = rg * 16 + hf * 8;                 // row offset from this lane's first row (g8)
+            const bool ok = off < rows_left;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {             // rows g8 and g8 + 8
-              const int off = rg * 16 + hf * 8;          // row offset from this lane's first row (g8)
+            for (int nt = 0; nt < 2; ++nt) {
               const float2 h2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(h_lane + off * HP + nt * 8));
               const float z0 = c[nt][2 * hf] * (h2.x > 0.f ? 1.f : h2.x + 1.f);
               const float z1 = c[nt][2 * hf + 1] * (h2.y > 0.f ? 1.f : h2.y + 1.f);
               gbh[j][2 * nt] += z0;
               gbh[j][2 * nt + 1] += z1;
-              if (g8 + off < valid) *reinterpret_cast<uint32_t*>(dz_lane + off * ldz + nt * 8) = pack_bf16x2(z0, z1);
+              if (ok) *reinterpret_cast<uint32_t*>(dz_lane + nt * 8) = pack_bf16x2(z0, z1);
             }
           }
         }
       }
     }
     __syncthreads();       // the next tile overwrites sh / s_out / s_dO
+    if (tid == 0) trace(0x006, round);
   }
   if (tid == 0) pdl_launch_dependents();     // persistent grid, every block resident: the successor's launch overlaps the flush
 
@@ -869,7 +937,7 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
   gb_c = warp_sum(gb_c);
 #pragma unroll
   for (int j = 0; j < 3; ++j) gb_l[j] = warp_sum(gb_l[j]);
-  st_v = warp_sum(st_v); st_s = warp_sum(st_s); st_l = warp_sum(st_l); st_k = warp_sum(st_k); st_e = warp_sum(st_e);
+  st_v = warp_sum(st_v); st_s = warp_sum(st_s); st_l = warp_sum(st_l); st_k = warp_sum(st_k);
   if (lane == 0) {
     atomicAdd(L.critic.gb, gb_c);
 #pragma unroll
@@ -878,25 +946,38 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
     atomicAdd(L.stats + 1, st_s);
     atomicAdd(L.stats + 2, st_l);
     atomicAdd(L.stats + 3, st_k);
-    atomicAdd(L.stats + 4, st_e);
   }
+  // The entropy of a diagonal Gaussian does not depend on the row: rows * sum_a (1/2 + log sqrt(2 pi) + log sigma_a), added
+  // once.  (Summed row by row in fp32 it drifts: every block adds the SAME value, so the rounding of the adds is a bias.)
+  if (blockIdx.x == 0 && tid == 0) {
+    double e = 0.0;
+    for (int a = 0; a < A; ++a) e += (double)(HALF_LOG_2PI_PLUS_HALF + s_c[2 * NO + a]);
+    atomicAdd(L.stats + 4, (float)(e * (double)L.rows));
+  }
+  if (tid == 0) trace(0x007);
 }
+HG_TRACE_SETTER(trace_set_heads)
 
 static bool loss_mma_eligible(const HgLossArgs& L) {
   const int H = L.actor.H;
-  return H == L.critic.H && H == L.linvel.H && H % 32 == 0 && H >= 32 && H <= mh::HMAX && L.A <= mh::NO;
+  const uintptr_t rec_align = reinterpret_cast<uintptr_t>(L.actions) | reinterpret_cast<uintptr_t>(L.old_mu) | reinterpret_cast<uintptr_t>(L.old_sigma);
+  const uintptr_t w_align = reinterpret_cast<uintptr_t>(L.actor.W) | reinterpret_cast<uintptr_t>(L.critic.W) | reinterpret_cast<uintptr_t>(L.linvel.W);
+  const uintptr_t h_align = reinterpret_cast<uintptr_t>(L.actor.h) | reinterpret_cast<uintptr_t>(L.critic.h) | reinterpret_cast<uintptr_t>(L.linvel.h) |
+                            (uintptr_t)((L.actor.ld_h | L.critic.ld_h | L.linvel.ld_h) & 7) * 2;
+  return H == L.critic.H && H == L.linvel.H && H % 32 == 0 && H >= 32 && H <= mh::HMAX && L.A <= mh::NO && L.A % 4 == 0 && ((w_align | rec_align | h_align) & 15) == 0;
 }
 
 static int launch_loss_mma(const HgLossArgs& L, cudaStream_t s) {
   const size_t smem = mh::Layout(L.actor.H).total;
+  auto kernel = ppo_head_loss_mma_kernel;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    HG_CUDA(cudaFuncSetAttribute(ppo_head_loss_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int ntiles = (L.rows + mh::ROWS - 1) / mh::ROWS;
   const int cap = 2 * num_sms();
-  HG_CUDA(launch_kernel(ppo_head_loss_mma_kernel, dim3(ntiles < cap ? ntiles : cap), dim3(mh::THREADS), smem, s, 1, L));
+  HG_CUDA(launch_kernel(kernel, dim3(ntiles < cap ? ntiles : cap), dim3(mh::THREADS), smem, s, 1, L));
   HG_LAUNCH_CHECK();
   count_launch();
   return HG_OK;

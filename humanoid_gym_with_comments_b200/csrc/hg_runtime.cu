@@ -45,9 +45,10 @@ int num_sms() {
 namespace hg {
 int trace_set_gemm(void* p);
 int trace_set_env(void* p);
+int trace_set_heads(void* p);
 }  // namespace hg
 // trace builds only (not part of the ABI): device timeline table, u64 [4 * 64 * 4 * 512] (hg_common.cuh); null switches off
-extern "C" int hg_trace_set(void* buf) { return hg::trace_set_gemm(buf) | hg::trace_set_env(buf); }
+extern "C" int hg_trace_set(void* buf) { return hg::trace_set_gemm(buf) | hg::trace_set_env(buf) | hg::trace_set_heads(buf); }
 #endif
 
 extern "C" const char* hg_last_error(void) { return hg::g_err; }

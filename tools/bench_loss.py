@@ -38,3 +38,34 @@ for i in range(8):
     e0.record(); check(lib.hg_ppo_head_loss(C.byref(args), current_stream())); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
 print("loss head", "SIMT" if os.environ.get("HG_LOSS_SIMT") else "mma", f"rows {rows}: median {sorted(ts[2:])[3]:.1f} us  all {[round(t, 1) for t in ts]}")
+
+if hasattr(lib, "hg_trace_set") and os.environ.get("HG_TRACE_LOSS"):
+    # device timeline of one launch (trace build: ALL=1 tools/build_variant.sh trace -DHG_TRACE): per tile round, when each
+    # block reached the phase boundaries (ns after the launch's first record; min / median / max over blocks)
+    TB = 512
+    table = torch.zeros(4 * 64 * 4 * TB, dtype=torch.int64, device=DEV)
+    lib.hg_trace_set.restype = C.c_int
+    lib.hg_trace_set.argtypes = [C.c_void_p]
+    flush.zero_(); torch.cuda.synchronize()
+    assert lib.hg_trace_set(table.data_ptr()) == 0
+    check(lib.hg_ppo_head_loss(C.byref(args), current_stream())); torch.cuda.synchronize()
+    assert lib.hg_trace_set(None) == 0
+    hh = table.cpu().view(4, 64, 4, TB)[0]
+    t0 = int(hh[hh > 0].min())
+    names = {0: "kernel entry", 8: "next tile issued", 1: "prologue done", 2: "tile start", 3: "activations landed", 4: "forward done", 5: "loss done", 6: "backward done", 7: "kernel end"}
+    for rnd in range(4):
+        for pt in (2, 8, 3, 4, 5, 6):
+            v = hh[pt, rnd]; v = sorted((v[v > 0] - t0).tolist())
+            if v: print(f"round {rnd} {names[pt]:20s} n={len(v):4d} min {v[0]:7d} med {v[len(v)//2]:7d} max {v[-1]:7d}")
+    for pt in (0, 1, 7):
+        v = hh[pt, 0]; v = sorted((v[v > 0] - t0).tolist())
+        print(f"{names[pt]:28s} n={len(v):4d} min {v[0]:7d} med {v[len(v)//2]:7d} max {v[-1]:7d}")
+    # per-block phase durations (median over blocks and rounds)
+    import statistics
+    for a, b_, nm in ((2, 8, "issue next"), (8, 3, "load wait"), (3, 4, "forward"), (4, 5, "loss"), (5, 6, "backward")):
+        d = []
+        for rnd in range(4):
+            x, y = hh[a, rnd], hh[b_, rnd]
+            m = (x > 0) & (y > 0)
+            d += (y[m] - x[m]).tolist()
+        print(f"phase {nm:10s}: median {statistics.median(d):.0f} ns  mean {statistics.mean(d):.0f}  max {max(d)}")
