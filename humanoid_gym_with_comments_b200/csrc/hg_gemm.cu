@@ -49,7 +49,9 @@ struct Cfg {
   static constexpr int BIAS_SLICE_BYTES = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32) ? 0 : 256;
   static constexpr bool F32_OUT = (EPI == HG_EPI_ATOMIC_F32 || EPI == HG_EPI_STORE_F32);
   // epilogue warps: 4 per scheduler for the bf16 epilogues (they bound the short-K launches: 16 beat 8 by ~20 %);
-  // the fp32 ones sit behind K = rows main loops and keep 8 so that their 4 KB staging tiles leave a deeper TMA ring
+  // the fp32 ones sit behind K = rows main loops and keep 8 so that their 4.5 KB staging tiles leave a deeper TMA ring
+  // (16, -DHG_F32_EPI_WARPS=16: dW 1.498 -> 1.476 ms per iteration, within noise -- the exposed part of that epilogue is
+  // the L2's fp32 reduction rate, not the warps issuing it)
   static constexpr int EPI_WARPS = F32_OUT ? HG_F32_EPI_WARPS : HG_EPI_WARPS;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int COL_SPLIT = EPI_WARPS / 4;       // column slices per tile

@@ -1,4 +1,7 @@
-"""Stand-alone timing of hg_ppo_head_loss at the update's minibatch shape (61440 rows, H=128, A=12)."""
+"""Stand-alone timing of hg_ppo_head_loss at the update's minibatch shape (61440 rows, H=128, A=12); CUDA events around
+the C call, so ~15 us of host launch latency are inside the figure (the device timeline below and ncu are not affected).
+HG_TRACE_LOSS=1 with a trace build (ALL=1 tools/build_variant.sh trace -DHG_TRACE; HG_LIB_PATH=variants/libhgb200_trace.so)
+prints the kernel's device timeline: when each block passed its phase boundaries, per tile round."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
