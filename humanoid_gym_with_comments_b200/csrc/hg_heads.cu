@@ -457,10 +457,12 @@ __global__ void __launch_bounds__(LH_THREADS) ppo_head_loss_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------ update head on tensor cores
-// Same operator as ppo_head_loss_kernel for the common shape (three heads of equal hidden width H <= 128, H % 16 == 0,
-// A <= 16): the three tiny GEMMs per row tile run on the tensor cores (warp-level mma.sync m16n8k16 bf16 -> fp32,
-// operands through ldmatrix) and the blocks are PERSISTENT, so the weight gradients live in accumulator registers for
-// the whole launch and are added to global memory once per block instead of once per 64 rows.
+// Same operator as ppo_head_loss_kernel for the common shape (three heads of equal hidden width H <= 128, H % 32 == 0,
+// A <= 16, A % 4 == 0, 16-byte aligned arrays): the three tiny GEMMs per row tile run on the tensor cores (warp-level
+// mma.sync m16n8k16 bf16 -> fp32, operands through ldmatrix) and the blocks are PERSISTENT, so the weight gradients live
+// in accumulator registers for the whole launch and are added to global memory once per block instead of once per tile.
+// The tiles (32 rows) run through a two-stage software pipeline: while one is computed on, the next one's activation
+// rows (TMA bulk copies, completion on an mbarrier) and old-policy record (cp.async) are in flight into the other buffer.
 //   forward : out = h W^T with W = W_hi + W_mid + W_lo (three bf16 terms = all 24 mantissa bits; h is bf16, every
 //             product is exact in fp32), so the means match the fp32 rollout head to accumulation-order rounding --
 //             the PPO ratio is sensitive to exactly that.
@@ -704,8 +706,8 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
     const float* rec = s_rec + (size_t)(buf * ROWS + r) * RS;           // this thread's row
     const float* rowrec = rec + RS_SCALARS;
 
-    // -- forward: out[net][64][16] = h W^T.  Jobs = (net, 16-row group, n8 tile); the second n8 tile exists only for the
-    //    actor (outputs 8..A-1): 16 jobs, two per warp.
+    // -- forward: out[net][ROWS][16] = h W^T.  Jobs = (net, 16-row group, n8 tile); the second n8 tile exists only for the
+    //    actor (outputs 8..A-1): 8 jobs, one per warp.
     for (int job = warp; job < 4 * (ROWS / 16); job += WARPS) {
       const int q = job / (ROWS / 16), rg = job - q * (ROWS / 16);
       const int net = q < 2 ? 0 : q - 1, nt = q == 1 ? 1 : 0;
@@ -834,7 +836,7 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
         const uint32_t h_u = sh_u + (uint32_t)(net * ROWS * HP) * 2;
         const uint32_t d_u = dO_u + (uint32_t)(net * 2 * ROWS * DP) * 2;
         const uint32_t w_u = wm_u + (uint32_t)((net == 0 ? 0 : 3) * NO * HP) * 2;
-        // gW[16 outputs x 16 cols] += dOut^T[16 x 64 rows] h[64 rows x 16 cols]:
+        // gW[16 outputs x 16 cols] += dOut^T[16 x ROWS] h[ROWS x 16 cols]:
         //   A(m = output, k = row) is dOut[row][output]  -> transposed 8x8 loads, matrices {k 0-7 | 8-15} x {m 0-7 | 8-15}
         //   B(k = row, n = col)    is h[row][col]        -> transposed 8x8 loads
         for (int k0 = 0; k0 < ROWS; k0 += 16) {

@@ -232,7 +232,7 @@ typedef struct HgLossArgs {
   int32_t use_clipped_value_loss;
   float inv_world;         /* 1/world_size: gradients are pre-scaled so that a SUM all-reduce yields the global mean */
   /* stats[0..4] += {sum value-loss terms, sum surrogate terms, sum lin-vel sq err, sum kl, sum entropy} over the
-   * minibatch rows (fp32, one atomic per 64-row block).  Lives in the 8 floats that FOLLOW the gradient arena so
+   * minibatch rows (fp32; a few atomics per thread block).  Lives in the 8 floats that FOLLOW the gradient arena so
    * that the single gradient all-reduce also reduces the KL (every rank derives the same learning rate). */
   float* stats;
 } HgLossArgs;
