@@ -34,6 +34,16 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.hg_launch_count() == 0            # nothing launched on a CPU box
 
 
+def test_every_entry_point_is_documented_against_the_reference_interface():
+    """INTEGRATION.md names, for every exported entry point, the reference interface it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    # `hg_gemm_plan_{create,run,destroy}` style rows spell several names at once
+    for m in re.finditer(r"(hg_[a-z0-9_]*)\{([a-z0-9_,]+)\}", doc):
+        doc += " " + " ".join(m.group(1) + part for part in m.group(2).split(","))
+    missing = [f for f in header_functions() if f not in doc]
+    assert not missing, missing
+
+
 def test_library_contains_sm100a_tensor_core_code():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
