@@ -597,13 +597,12 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
     const int row = t * ROWS + r;
     if (t >= ntiles || row >= L.rows) return 0;
     if (!L.idx) return (long long)row;
-    long long v;      // volatile: the load is issued HERE, a tile ahead of its use (left to the compiler it sinks to the use)
+    long long v;      // volatile asm: the load keeps its place in program order, a tile ahead of its use
     asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(L.idx + row));
     return v;
   };
-  // Everything tile t needs, global -> shared buffer b with cp.async: the three activation tiles (rows past the end
-  // zero-filled) and the old-policy record -- each thread fetches the action-wise words it will consume itself, the SUB
-  // lanes of a row one per-row scalar each.
+  // Everything tile t needs, global -> shared buffer b: the three activation tiles (one TMA bulk copy per row, rows past
+  // the end zero-filled) and the rows' old-policy records (cp.async).
   auto issue_loads = [&](int t, int b, long long src) {
     const int row0 = t * ROWS;
     const int valid = min(ROWS, L.rows - row0);
@@ -619,7 +618,7 @@ __global__ void __launch_bounds__(mh::THREADS, 2) ppo_head_loss_mma_kernel(const
       }
     }
     // the record: 3 * A / 4 16-byte pieces of the action-wise arrays (A % 4 == 0 on this path) and 7 scalars per row,
-    // spread over the row's SUB lanes (4-byte cp.async costs the LSU a pass per lane, so as few of those as possible)
+    // spread over the row's SUB lanes: 3 copy instructions per thread instead of 13 four-byte ones
     const bool rok = r < valid;
     const uint32_t rec_row = rec_u + (uint32_t)((b * ROWS + r) * RS) * 4;
     const int a4 = A >> 2;
